@@ -1,0 +1,211 @@
+/* gpsa_b200 -- C ABI of the B200-native GPSA variational-ELBO hot path.
+ *
+ * The reference (andrewcharlesjones/spatial-alignment, gpsa 0.6) is pure Python/PyTorch and has no
+ * FFI of its own; this header is the boundary underneath its Python API.  Every entry point names
+ * the reference code it replaces.  All pointers are DEVICE pointers to contiguous row-major fp32
+ * unless marked otherwise; every call is asynchronous on `stream`, never synchronises with the
+ * host and never allocates.  Return value: 0 = ok, 1 = bad argument, 2 = CUDA launch error,
+ * 3 = unsupported size/kind.
+ *
+ * Shapes use the symbols of SURVEY.md:  M inducing points, D spatial dims (1..3), R = S*N rows
+ * (Monte-Carlo sample s, spot n; r = s*N + n), L latent outputs (genes), V views.
+ * Kernel kinds: 0 = rbf (gpsa/util/util.py:8-23), 1 = matern12 (gpsa/util/util.py:33-47).
+ */
+#ifndef GPSA_B200_H
+#define GPSA_B200_H
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int gpsa_version(void);
+
+/* ---- covariance functions -------------------------------------------------------------------
+ * K[m,r] = k(x1[m], x2[r]);  x1 [M,D], x2 [R,D], K [M,R].  log_ls / log_var: device scalars.
+ * Replaces rbf_kernel / matern12_kernel (gpsa/util/util.py:8-23, :33-47) as called at
+ * gpsa/models/vgpsa.py:314-318, :390, :409. */
+int gpsa_kernel_matrix_fwd(int kind, int D, int M, long R, const float* x1, const float* x2, const float* log_ls,
+                           const float* log_var, float* K, cudaStream_t stream);
+/* Gradient of sum(Kbar * K).  acc_x1 [M,D] and acc_hyp [2] = (d/dlog_ls, d/dlog_var) are fp64
+ * accumulators that are ADDED to; x2bar [R,D] is overwritten (may be NULL); acc_x2 (fp64 [R,D],
+ * may be NULL) is added to instead of writing x2bar -- used for k(Z,Z) where x2 is the parameter
+ * itself.  Replaces autograd through the same reference lines. */
+int gpsa_kernel_matrix_bwd(int kind, int D, int M, long R, const float* x1, const float* x2, const float* log_ls,
+                           const float* log_var, const float* Kbar, double* acc_x1, float* x2bar, double* acc_x2,
+                           double* acc_hyp, cudaStream_t stream);
+
+/* ---- batched Cholesky / triangular inverse, one CTA per matrix ------------------------------
+ * A [batch,M,M] is factorised in place (lower factor, zeros above, like torch.cholesky);
+ * half_logdet[b] = sum_i log L_ii; info[b] = 1 if a non-positive pivot was met.  Either may be NULL.
+ * Replaces torch.cholesky at gpsa/models/vgpsa.py:257, :320, :394, :412. */
+int gpsa_potrf_batched_f32(int M, int batch, float* A, float* half_logdet, int* info, cudaStream_t stream);
+int gpsa_potrf_batched_f64(int M, int batch, double* A, double* half_logdet, int* info, cudaStream_t stream);
+/* X = L^-1 (lower).  X must not alias L.  Stands in for the triangular solves of
+ * torch.cholesky_solve (gpsa/models/vgpsa.py:177) and of the MultivariateNormal KL (:506-530). */
+int gpsa_trtri_batched_f32(int M, int batch, const float* L, float* X, cudaStream_t stream);
+int gpsa_trtri_batched_f64(int M, int batch, const double* L, double* X, cudaStream_t stream);
+
+/* ---- plain strided batched GEMM (fp32 SIMT) --------------------------------------------------
+ * C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b];  element (i,k) of op(A) at A[b*sA + i*ars + k*acs],
+ * (k,j) of op(B) at B[b*sB + k*brs + j*bcs], C row-major with leading dimension ldc. */
+int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA, const float* B,
+                  long brs, long bcs, long sB, float beta, float* C, long ldc, long sC, int batch,
+                  cudaStream_t stream);
+
+/* ---- prior covariance K_uu: fp64 factorisation of k(Z,Z) + 1e-5 I -----------------------------
+ * Outputs the fp32 Cholesky factor Lk [M,M] (the reference's cached Kuu_chol_*), K^-1 [M,M] and
+ * half_logdet (fp64 scalar, sum log diag).  ws64: 3*M*M doubles.  info: 1 int.
+ * Replaces gpsa/models/vgpsa.py:314-321 and :390-394. */
+int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_ls, const float* log_var, float* Lk,
+                       float* Kinv, double* half_logdet, int* info, double* ws64, cudaStream_t stream);
+
+/* ---- variational covariances Omega = Omega_sqt Omega_sqt^T + 1e-5 I, batched ------------------
+ * Replaces get_Omega_from_Omega_sqt + torch.cholesky (gpsa/models/vgpsa.py:206-210, :255-257, :410-412).
+ * Omega, Ltril: [B,M,M]; half_logdet [B]; info [B]. */
+int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, float* half_logdet, int* info,
+                       cudaStream_t stream);
+/* Backward: Osq_bar = 2 (Obar + coef[b] * Omega^-1) Osq.  Obar [B,M,M] is modified in place;
+ * coef: device [B] (the -1/2 dKL factor of the log-det term, 0 for slices without a KL term);
+ * Linv: [B,M,M] scratch. */
+int gpsa_omega_grad(int M, int B, const float* Osq, const float* Ltril, float* Obar, const float* coef, float* Linv,
+                    float* Osq_bar, cudaStream_t stream);
+
+/* ---- implicit-feature quadratic form (the hot contraction) ------------------------------------
+ * q2[r,p] = a_r^T Omega_p a_r with a_r = A[:,r];  replaces the [S,L,N,M] broadcast bmm at
+ * gpsa/models/vgpsa.py:193-196 and its autograd.  W is the packed feature matrix [gpsa_feat_count(M), L]. */
+long gpsa_feat_count(int M);
+int gpsa_feat_pack(int M, int L, const float* Omega, float* W, cudaStream_t stream);
+/* Obar[p] = sym(H[:,p]) + add_scale * (*add_scale_dev) * Add   (Add [M,M], may be NULL) */
+int gpsa_feat_unpack(int M, int L, const float* H, const float* Add, float add_scale, const float* add_scale_dev,
+                     float* Obar, cudaStream_t stream);
+int gpsa_quadform_fwd_f32(int M, long R, int L, const float* A, const float* W, float* q2, cudaStream_t stream);
+int gpsa_quadform_bwd_omega_f32(int M, long R, int L, const float* A, const float* G, float* H,
+                                cudaStream_t stream);
+int gpsa_quadform_bwd_alpha_f32(int M, long R, int L, const float* A, const float* G, const float* W, float* Abar,
+                                cudaStream_t stream);
+
+/* ---- warp layer, one non-fixed view -------------------------------------------------------------
+ * Replaces the body of the view loop, gpsa/models/vgpsa.py:275-351 (K_uu, K_uf, compute_mean_and_var
+ * :174-204 in its 2-D branch, reparameterised sampling) and this view's KL terms in loss_fn (:498-516).
+ * Reference quirks kept: sample scale is the variance (:334-340), variance uses Omega slice v*D+j
+ * (:336-339) while the KL uses slice j*V+v (:508), jitter added twice (:191,:204). */
+typedef struct {
+  int kind, D, M, V, v, S;
+  long n;                 /* spots of this view (all modalities concatenated) */
+  const float* Z;         /* Xtilde[v]            [M,D] */
+  const float* dlt;       /* delta_G_list[v]      [M,D] */
+  const float* log_ls;    /* &warp_kernel_lengthscales[v] */
+  const float* log_var;   /* &warp_kernel_variances[v]    */
+  const float* Omega_G;   /* [V*D,M,M] from gpsa_omega_prepare */
+  const float* hld_Omega; /* [V*D] half log-dets of Omega_G */
+  const float* X;         /* [n,D] observed coordinates */
+  const float* eps;       /* [S,n,D] standard-normal draws */
+  float* Lk;              /* out [M,M]  Kuu_chol_list[v] */
+  float* Kinv;            /* out [M,M] */
+  double* hld_K;          /* out fp64 scalar */
+  int* info;              /* out 1 int */
+  float* A;               /* out [M,n]  K^-1 K_uf   (saved) */
+  float* B;               /* out [M,n]  K_uf        (saved) */
+  float* T;               /* out [D,M,n] Omega_{vD+j} A (saved) */
+  float* Ke;              /* out [D,M]  K^-1 (Z_j - dlt_j)  (saved) */
+  float* var;             /* out [n,D] marginal "variance" (saved) */
+  float* Gmean;           /* out [n,D] */
+  float* Gs;              /* out: sample s at Gs + s*gs_stride, [n,D] each */
+  long gs_stride;
+  double* kl_acc;         /* fp64 scalar, ADDED to */
+  double* ws64;           /* 3*M*M doubles */
+} gpsa_warp_fwd_args;
+int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t stream);
+
+typedef struct {
+  int kind, D, M, V, v, S;
+  long n;
+  const float *Z, *dlt, *log_ls, *log_var, *Omega_G, *X, *eps;
+  const float *Kinv, *A, *B, *T, *Ke;
+  const float* Gs_bar;    /* sample s at Gs_bar + s*gs_stride, [n,D]; may be NULL */
+  long gs_stride;
+  const float* Gm_bar;    /* [n,D], may be NULL */
+  const float* kl_bar;    /* device scalar: upstream gradient of the KL term */
+  double* acc_Z;          /* fp64 [M,D], ADDED to: gradient of Xtilde[v] */
+  double* acc_dlt;        /* fp64 [M,D], ADDED to: gradient of delta_G_list[v] */
+  double* acc_hyp;        /* fp64 [2]: (log_ls, log_var) of this view */
+  float* Obar_G;          /* [V*D,M,M] ADDED to (slices v*D+j and j*V+v) */
+  /* scratch */
+  float *mubar, *varbar, *q1bar; /* [n,D], [n,D], [n] */
+  float *Abar, *C, *AS;          /* [M,n], [M,n], [D,M,n] */
+  float *Kbar, *Som, *T1;        /* [M,M] each */
+} gpsa_warp_bwd_args;
+int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t stream);
+
+/* ---- data layer, one modality -------------------------------------------------------------------
+ * Replaces gpsa/models/vgpsa.py:390-426 (K_uu, K_uf for all S samples, compute_mean_and_var in its
+ * 3-D branch :192-204, F = mu + sqrt(var) eps) and the modality's KL term (:520-530). */
+typedef struct {
+  int kind, D, M, L;
+  long R;                 /* S*N rows */
+  const float* Gt;        /* Gtilde [M,D] */
+  const float *log_ls, *log_var;
+  const float* dlt;       /* delta_F [M,L] */
+  const float* Omega;     /* [L,M,M] from gpsa_omega_prepare */
+  const float* hld_Omega; /* [L] */
+  const float* G;         /* G_samples flattened [R,D] */
+  const float* eps;       /* [R,L] */
+  float *Lk, *Kinv;       /* out [M,M] each */
+  double* hld_K;
+  int* info;
+  float *A, *B;           /* out [M,R] (saved) */
+  float* q1;              /* out [R] */
+  float* W;               /* out [gpsa_feat_count(M), L] (saved) */
+  float* KD;              /* out [M,L] K^-1 delta (saved) */
+  float* F;               /* out [R,L] latent samples */
+  float* var;             /* out [R,L] marginal variances (saved) */
+  double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
+  double* ws64;           /* 3*M*M doubles */
+  int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 */
+} gpsa_data_fwd_args;
+int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
+
+typedef struct {
+  int kind, D, M, L;
+  long R;
+  const float *Gt, *log_ls, *log_var, *dlt, *Omega, *G, *eps;
+  const float *Kinv, *A, *B, *W, *KD, *var;
+  const float* F_bar;     /* [R,L] */
+  const float* kl_bar;    /* device scalar */
+  float* G_bar;           /* out [R,D] */
+  double* acc_Gt;         /* fp64 [M,D] ADDED to */
+  double* acc_hyp;        /* fp64 [2] ADDED to */
+  float* dlt_bar;         /* out [M,L] */
+  float* Obar;            /* out [L,M,M]  (feed to gpsa_omega_grad) */
+  /* scratch */
+  float* Gm;              /* [R,L] dLoss/dvar */
+  float* q1bar;           /* [R] */
+  float *Abar, *C;        /* [M,R] each */
+  float* H;               /* [gpsa_feat_count(M), L] */
+  float *Kbar, *Som, *T1; /* [M,M] each */
+  int engine;
+} gpsa_data_bwd_args;
+int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t stream);
+
+/* ---- Gaussian log-likelihood ----------------------------------------------------------------------
+ * ll_acc += sum_{r,p} log N(Y[n,p]; F[r,p], sigma) / S,  sigma = exp(*log_noise) + 1e-5 used as the
+ * Normal SCALE exactly as the reference does (gpsa/models/vgpsa.py:217, :532-538); r = s*N + n.
+ * F [S*N,P], Y [N,P]. */
+int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
+                         double* ll_acc, cudaStream_t stream);
+/* F_bar[r,p] = ll_bar * dLL/dF,  acc_noise += ll_bar * dLL/dlog_noise (fp64).  ll_bar: device scalar. */
+int gpsa_gaussian_ll_bwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
+                         const float* ll_bar, float* F_bar, double* acc_noise, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSA_B200_H */

@@ -1,0 +1,47 @@
+// Shared helpers for the gpsa_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GPSA_OK 0
+#define GPSA_ERR_ARG 1
+#define GPSA_ERR_CUDA 2
+#define GPSA_ERR_UNSUPPORTED 3
+
+#define GPSA_KIND_RBF 0
+#define GPSA_KIND_MATERN12 1
+
+#define GPSA_OFF 1e-5f  // diagonal_offset, reference gpsa/models/gpsa.py:153
+
+#define GPSA_LAUNCH_CHECK()                      \
+  do {                                           \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) return GPSA_ERR_CUDA; \
+  } while (0)
+
+static inline int gpsa_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` needs >= 32 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : T(0);
+  if (w == 0) v = warp_sum(v);
+  return v;
+}

@@ -1,0 +1,184 @@
+// Register-tiled SIMT GEMM engine (fp32 / fp64) shared by every non-tensor-core
+// contraction of the path: A = K^-1 B, the predictive-mean product, Omega =
+// Omega_sqt Omega_sqt^T, the K-bar / Omega-bar backward products, and -- with an
+// on-the-fly operand generator -- the implicit-feature quadratic-form GEMMs.
+//
+//   C tile (BM x BN) per CTA, (BM/TM)*(BN/TN) threads, each a TM x TN micro-tile.
+//   Operand tiles are staged k-major in shared memory: As[kk][i], Bs[kk][j], so
+//   the inner loop reads TM + TN values with 128-bit loads for TM*TN FMAs.
+//   Loaders and the epilogue are functors so that operands can be strided views,
+//   generated products, or gathered rows.
+#pragma once
+#include "common.cuh"
+
+template <typename T, int BM_, int BN_, int BK_, int TM_, int TN_>
+struct GemmCfg {
+  using elem = T;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, TM = TM_, TN = TN_;
+  static constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
+  static constexpr int PAD = 4;
+  static constexpr int LDA = BM + PAD, LDB = BN + PAD;
+  static constexpr int SMEM_ELEMS = BK * (LDA + LDB);
+  static_assert(TM % 4 == 0 && TN % 4 == 0, "micro-tile is built from 4-wide chunks");
+};
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, T (&v)[4]);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void ld4<double>(const double* p, double (&v)[4]) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// Row r (0..TM) of a thread's micro-tile maps to tile row  (r/4)*(BM/(TM/4)) + ty*4 + r%4.
+template <class C>
+__device__ __forceinline__ int tile_row(int ty, int r) { return (r >> 2) * (C::BM / (C::TM / 4)) + ty * 4 + (r & 3); }
+template <class C>
+__device__ __forceinline__ int tile_col(int tx, int c) { return (c >> 2) * (C::BN / (C::TN / 4)) + tx * 4 + (c & 3); }
+
+// acc[r][c] += sum_k A(m0 + row(r), k) * B(k, n0 + col(c)) for k in [k_begin, k_end).
+// al.fill(As, m0, k0, k_end) must write As[kk*LDA + i] for kk<BK, i<BM (zero where out of range);
+// bl.fill(Bs, n0, k0, k_end) likewise.  All threads of the CTA must call this.
+template <class C, class AL, class BL>
+__device__ __forceinline__ void gemm_mainloop(const AL& al, const BL& bl, int m0, int n0, long k_begin, long k_end,
+                                               typename C::elem* As, typename C::elem* Bs,
+                                               typename C::elem (&acc)[C::TM][C::TN]) {
+  using T = typename C::elem;
+  const int tx = threadIdx.x % C::TX, ty = threadIdx.x / C::TX;
+  for (long k0 = k_begin; k0 < k_end; k0 += C::BK) {
+    al.fill(As, m0, k0, k_end);
+    bl.fill(Bs, n0, k0, k_end);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < C::BK; ++kk) {
+      T a[C::TM], b[C::TN];
+#pragma unroll
+      for (int r = 0; r < C::TM; r += 4) {
+        T t[4];
+        ld4<T>(As + kk * C::LDA + tile_row<C>(ty, r), t);
+        a[r] = t[0]; a[r + 1] = t[1]; a[r + 2] = t[2]; a[r + 3] = t[3];
+      }
+#pragma unroll
+      for (int c = 0; c < C::TN; c += 4) {
+        T t[4];
+        ld4<T>(Bs + kk * C::LDB + tile_col<C>(tx, c), t);
+        b[c] = t[0]; b[c + 1] = t[1]; b[c + 2] = t[2]; b[c + 3] = t[3];
+      }
+#pragma unroll
+      for (int r = 0; r < C::TM; ++r)
+#pragma unroll
+        for (int c = 0; c < C::TN; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+}
+
+// Strided-view loader: element (i, k) at base[i*rs + k*cs], i < rows.  TI may differ from the
+// compute type (fp32 data feeding an fp64 accumulation).
+template <class C, typename TI, int B /*BM or BN*/, int LD>
+struct StridedLoader {
+  const TI* base;
+  long rs, cs;
+  long rows;
+  __device__ __forceinline__ void fill(typename C::elem* S, int r0, long k0, long k_end) const {
+    using T = typename C::elem;
+    if (cs == 1) {  // k contiguous in memory: consecutive threads walk k
+      for (int idx = threadIdx.x; idx < B * C::BK; idx += C::NT) {
+        const int kk = idx % C::BK, i = idx / C::BK;
+        const long gi = r0 + i, gk = k0 + kk;
+        S[kk * LD + i] = (gi < rows && gk < k_end) ? T(base[gi * rs + gk]) : T(0);
+      }
+    } else {  // consecutive threads walk the row index
+      for (int idx = threadIdx.x; idx < B * C::BK; idx += C::NT) {
+        const int i = idx % B, kk = idx / B;
+        const long gi = r0 + i, gk = k0 + kk;
+        S[kk * LD + i] = (gi < rows && gk < k_end) ? T(base[gi * rs + gk * cs]) : T(0);
+      }
+    }
+  }
+};
+
+// C[b] = alpha * A[b] * B[b] + beta * C[b] (+ diag on the diagonal), generic strides.
+//   A(i,k) = A[b*sA + i*ars + k*acs],  B(k,j) = B[b*sB + k*brs + j*bcs],  C(i,j) = C[b*sC + i*ldc + j].
+//   split_k > 1: gridDim.z = batch*split_k, partial products are atomically added to C
+//   (C must be pre-initialised, beta is ignored).
+//   lower_only: skip tiles strictly above the diagonal (symmetric/triangular outputs).
+//   alpha_dev: optional device scalar(s) multiplied into alpha (per batch with stride 1, shared with stride 0).
+template <class C, typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long K, double alpha, const TA* A, long ars,
+                                                              long acs, long sA, const TB* B, long brs, long bcs,
+                                                              long sB, double beta, TC* Cm, long ldc, long sC,
+                                                              int split_k, double diag, int lower_only,
+                                                              const float* alpha_dev, int alpha_dev_stride) {
+  using T = typename C::elem;
+  __shared__ __align__(16) T smem[C::SMEM_ELEMS];
+  T* As = smem;
+  T* Bs = smem + C::BK * C::LDA;
+  const int b = blockIdx.z / split_k, ks = blockIdx.z % split_k;
+  const int m0 = blockIdx.x * C::BM, n0 = blockIdx.y * C::BN;  // rows on x: R-sized row counts exceed the y limit
+  if (lower_only && n0 > m0 + C::BM - 1) return;
+  const long kchunk = ((K + split_k - 1) / split_k + C::BK - 1) / C::BK * C::BK;
+  const long k_begin = ks * kchunk;
+  const long k_end = (k_begin + kchunk < K) ? k_begin + kchunk : K;
+  StridedLoader<C, TA, C::BM, C::LDA> al{A + b * sA, ars, acs, M};
+  StridedLoader<C, TB, C::BN, C::LDB> bl{B + b * sB, bcs, brs, N};  // "row" of the B tile is the column j
+  T acc[C::TM][C::TN];
+#pragma unroll
+  for (int r = 0; r < C::TM; ++r)
+#pragma unroll
+    for (int c = 0; c < C::TN; ++c) acc[r][c] = T(0);
+  if (k_begin < k_end) gemm_mainloop<C>(al, bl, m0, n0, k_begin, k_end, As, Bs, acc);
+  const int tx = threadIdx.x % C::TX, ty = threadIdx.x / C::TX;
+  TC* Cb = Cm + b * sC;
+  if (alpha_dev) alpha *= (double)alpha_dev[(long)b * alpha_dev_stride];  // device-resident scale (e.g. upstream dKL)
+#pragma unroll
+  for (int r = 0; r < C::TM; ++r) {
+    const int i = m0 + tile_row<C>(ty, r);
+    if (i >= M) continue;
+#pragma unroll
+    for (int c = 0; c < C::TN; ++c) {
+      const int j = n0 + tile_col<C>(tx, c);
+      if (j >= N) continue;
+      T v = T(alpha) * acc[r][c];
+      if (split_k > 1) {
+        if (k_begin < k_end) atomicAdd(&Cb[i * ldc + j], TC(v));
+      } else {
+        if (beta != 0.0) v += T(beta) * T(Cb[i * ldc + j]);
+        if (i == j) v += T(diag);
+        Cb[i * ldc + j] = TC(v);
+      }
+    }
+  }
+}
+
+// Host-side launcher.  Picks a small or a large tile from the problem shape.
+template <typename T, typename TA, typename TB, typename TC>
+static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long ars, long acs, long sA,
+                        const TB* B, long brs, long bcs, long sB, double beta, TC* Cm, long ldc, long sC, int batch,
+                        int split_k = 1, double diag = 0.0, int lower_only = 0, const float* alpha_dev = nullptr,
+                        int alpha_dev_stride = 0) {
+  if (M <= 0 || N <= 0 || batch <= 0) return GPSA_OK;
+  if (split_k < 1) split_k = 1;
+  const bool big = (sizeof(T) == 4) && M >= 96 && N >= 96;
+  if (big) {
+    using Cfg = GemmCfg<T, 128, 128, 8, 8, 8>;
+    dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
+    gemm_strided_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB,
+                                                                   beta, Cm, ldc, sC, split_k, diag, lower_only, alpha_dev,
+                                                                   alpha_dev_stride);
+  } else {
+    using Cfg = GemmCfg<T, 64, 64, 16, 4, 4>;
+    dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
+    gemm_strided_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB,
+                                                                   beta, Cm, ldc, sC, split_k, diag, lower_only, alpha_dev,
+                                                                   alpha_dev_stride);
+  }
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}

@@ -1,0 +1,653 @@
+// Layer-level entry points of the ELBO hot path: prior / variational covariance preparation, the
+// warp layer (one view), the data layer (one modality) and the Gaussian log-likelihood, each as
+// an explicit forward and an explicit analytic backward (no autograd tape below this boundary).
+// Every function only enqueues kernels on the caller's stream.
+#include "gemm.cuh"
+#include "gpsa_b200.h"
+
+#include <math.h>
+
+#define TRY(x)                   \
+  do {                           \
+    int rc__ = (x);              \
+    if (rc__ != GPSA_OK) return rc__; \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// GEMM conveniences (row-major, fp32)
+// ------------------------------------------------------------------------------------------------
+int pick_split(int M, int N, long K, int batch) {
+  const int t = (M >= 96 && N >= 96) ? 128 : 64;
+  const long tiles = (long)gpsa_cdiv(M, t) * gpsa_cdiv(N, t) * batch;
+  if (tiles >= 296 || K < 4096) return 1;
+  long s = (592 + tiles - 1) / tiles;
+  const long smax = K / 1024;
+  if (s > smax) s = smax;
+  return s < 1 ? 1 : (int)s;
+}
+
+// C = alpha*A*B + beta*C with A [M,K] (lda), B [K,N] (ldb)
+int gemm_nn(cudaStream_t st, int M, int N, long K, double alpha, const float* A, long lda, const float* B, long ldb,
+            double beta, float* C, long ldc, const float* alpha_dev = nullptr) {
+  return gemm_strided<float, float, float, float>(st, M, N, K, alpha, A, lda, 1, 0, B, ldb, 1, 0, beta, C, ldc, 0, 1,
+                                                  1, 0.0, 0, alpha_dev, 0);
+}
+// C = alpha*A*B^T + beta*C with A [M,K] (lda), B [N,K] (ldb).  beta must be 0 or 1; large K is split.
+int gemm_nt(cudaStream_t st, int M, int N, long K, double alpha, const float* A, long lda, const float* B, long ldb,
+            double beta, float* C, long ldc, const float* alpha_dev = nullptr) {
+  const int split = pick_split(M, N, K, 1);
+  if (split > 1 && beta == 0.0) {
+    if (ldc != N) return GPSA_ERR_ARG;
+    if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  }
+  return gemm_strided<float, float, float, float>(st, M, N, K, alpha, A, lda, 1, 0, B, 1, ldb, 0, beta, C, ldc, 0, 1,
+                                                  split, 0.0, 0, alpha_dev, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior covariance in fp64
+// ------------------------------------------------------------------------------------------------
+template <int D, int KIND>
+__global__ void prior_kuu_kernel(int M, const float* __restrict__ Z, const float* __restrict__ log_ls,
+                                 const float* __restrict__ log_var, double* __restrict__ K) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * M) return;
+  const int i = idx / M, j = idx % M;
+  const double inv_ls = exp(-(double)log_ls[0]), var = exp((double)log_var[0]);
+  double r2 = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double t = (double)Z[i * D + d] - (double)Z[j * D + d];
+    r2 += t * t;
+  }
+  double k;
+  if (KIND == GPSA_KIND_RBF) k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
+  else k = var * exp(-0.5 * sqrt(r2 + 1e-10) * inv_ls);
+  if (i == j) k += 1e-5;
+  K[idx] = k;
+}
+
+__global__ void cvt_d2f_kernel(long n, const double* __restrict__ src, float* __restrict__ dst) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise / reduction kernels
+// ------------------------------------------------------------------------------------------------
+// y += alpha * (*alpha_dev) * x
+__global__ void axpy_dev_kernel(long n, float alpha, const float* __restrict__ alpha_dev, const float* __restrict__ x,
+                                float* __restrict__ y) {
+  const float a = alpha * (alpha_dev ? alpha_dev[0] : 1.f);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+int axpy_dev(cudaStream_t st, long n, float alpha, const float* alpha_dev, const float* x, float* y) {
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  axpy_dev_kernel<<<blocks, 256, 0, st>>>(n, alpha, alpha_dev, x, y);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+// S[e] = sum_{b<count} X[b*stride + e]
+__global__ void sum_batch_kernel(long n, int count, long stride, const float* __restrict__ X, float* __restrict__ S) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < count; ++b) s += X[(long)b * stride + e];
+  S[e] = s;
+}
+
+// q1[r] = sum_m A[m,r] B[m,r]
+__global__ void q1_kernel(int M, long R, const float* __restrict__ A, const float* __restrict__ B,
+                          float* __restrict__ q1) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s = fmaf(A[(long)m * R + r], B[(long)m * R + r], s);
+  q1[r] = s;
+}
+
+// out[m,r] = q[r] * X[m,r]   (accumulate = 0)   or   out[m,r] += q[r] * X[m,r]  (accumulate = 1)
+__global__ void colscale_kernel(long total, long R, const float* __restrict__ q, const float* __restrict__ X,
+                                float* __restrict__ out, int accumulate) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float v = q[i % R] * X[i];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+int colscale(cudaStream_t st, int M, long R, const float* q, const float* X, float* out, int accumulate) {
+  const long total = (long)M * R;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  colscale_kernel<<<blocks, 256, 0, st>>>(total, R, q, X, out, accumulate);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data layer: sampling and its backward
+// ------------------------------------------------------------------------------------------------
+// in:  F = predictive mean, var = q2.   out: var = sigma2 - q1 + q2 + 2 off, F = mean + sqrt(var) eps
+__global__ void sample_fwd_kernel(long total, int L, const float* __restrict__ q1, const float* __restrict__ eps,
+                                  const float* __restrict__ log_var, float* __restrict__ F, float* __restrict__ var) {
+  const float s2 = expf(log_var[0]);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / L;
+    const float v = ((s2 - q1[r]) + var[i] + GPSA_OFF) + GPSA_OFF;  // jitter twice: vgpsa.py:201,:204
+    var[i] = v;
+    F[i] = fmaf(sqrtf(v), eps[i], F[i]);
+  }
+}
+
+// one warp per row r: Gm[r,p] = Fbar*eps/(2 sqrt(var)); q1bar[r] = -sum_p Gm; acc_hyp[1] += sigma2 * sum Gm
+__global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const float* __restrict__ Fbar,
+                                                         const float* __restrict__ eps, const float* __restrict__ var,
+                                                         const float* __restrict__ log_var, float* __restrict__ Gm,
+                                                         float* __restrict__ q1bar, double* acc_hyp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  double tot = 0.0;
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + warp; r < R; r += nwarps) {
+    float s = 0.f;
+    for (int p = lane; p < L; p += 32) {
+      const long i = r * L + p;
+      const float g = 0.5f * Fbar[i] * eps[i] * rsqrtf(var[i]);
+      Gm[i] = g;
+      s += g;
+    }
+    s = warp_sum(s);
+    if (lane == 0) { q1bar[r] = -s; tot += s; }
+  }
+  __shared__ double red[8];
+  if (lane == 0) red[warp] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(&acc_hyp[1], t * (double)expf(log_var[0]));
+  }
+}
+
+// KL(q(u_p) || p(u)) summed over genes: one CTA per gene.
+//   kl_p = hldK - hldOm[p] + 0.5 (tr(K^-1 Omega_p) + delta_p^T K^-1 delta_p - M)
+__global__ void __launch_bounds__(256) kl_F_kernel(int M, int L, const float* __restrict__ Kinv,
+                                                   const float* __restrict__ Omega, const float* __restrict__ hldOm,
+                                                   const float* __restrict__ dlt, const float* __restrict__ KD,
+                                                   const double* __restrict__ hldK, double* kl_acc) {
+  const int p = blockIdx.x;
+  const float* Om = Omega + (long)p * M * M;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += (double)Kinv[i] * (double)Om[i];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) s += (double)dlt[(long)m * L + p] * (double)KD[(long)m * L + p];
+  __shared__ double red[32];
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) atomicAdd(kl_acc, hldK[0] - (double)hldOm[p] + 0.5 * (s - (double)M));
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp layer kernels
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) warp_predict_kernel(int M, long n, int S, const float* __restrict__ Z,
+                                                           const float* __restrict__ dlt, const float* __restrict__ A,
+                                                           const float* __restrict__ B, const float* __restrict__ T,
+                                                           const float* __restrict__ X, const float* __restrict__ eps,
+                                                           const float* __restrict__ log_var, float* __restrict__ var,
+                                                           float* __restrict__ Gmean, float* __restrict__ Gs,
+                                                           long gs_stride) {
+  extern __shared__ float dmz[];  // [M*D]  delta - mu_z  (mean function = identity: mu_z = Z)
+  for (int i = threadIdx.x; i < M * D; i += blockDim.x) dmz[i] = dlt[i] - Z[i];
+  __syncthreads();
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float q1 = 0.f, mu[D], q2[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { mu[d] = X[r * D + d]; q2[d] = 0.f; }
+  for (int m = 0; m < M; ++m) {
+    const float a = A[(long)m * n + r];
+    q1 = fmaf(a, B[(long)m * n + r], q1);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      mu[d] = fmaf(a, dmz[m * D + d], mu[d]);
+      q2[d] = fmaf(a, T[((long)d * M + m) * n + r], q2[d]);
+    }
+  }
+  const float s2 = expf(log_var[0]);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float v = ((s2 - q1) + q2[d] + GPSA_OFF) + GPSA_OFF;
+    var[r * D + d] = v;
+    Gmean[r * D + d] = mu[d];
+    for (int s = 0; s < S; ++s)  // the reference uses the VARIANCE as the Normal scale (vgpsa.py:334-340)
+      Gs[(long)s * gs_stride + r * D + d] = fmaf(v, eps[((long)s * n + r) * D + d], mu[d]);
+  }
+}
+
+// KL terms of view v: one CTA per spatial dim j.  Stores Ke[j,:] = K^-1 (Z_j - delta_j).
+__global__ void __launch_bounds__(256) kl_G_kernel(int M, int D, int V, int v, const float* __restrict__ Kinv,
+                                                   const float* __restrict__ Omega_G,
+                                                   const float* __restrict__ hldOm, const float* __restrict__ Z,
+                                                   const float* __restrict__ dlt, const double* __restrict__ hldK,
+                                                   float* __restrict__ Ke, double* kl_acc) {
+  const int j = blockIdx.x;
+  const int slot = j * V + v;  // the KL uses slice j*V+v (vgpsa.py:508)
+  const float* Om = Omega_G + (long)slot * M * M;
+  extern __shared__ float e[];  // [M]
+  for (int m = threadIdx.x; m < M; m += blockDim.x) e[m] = Z[m * D + j] - dlt[m * D + j];
+  __syncthreads();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += (double)Kinv[i] * (double)Om[i];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < M; ++k) t = fmaf(Kinv[(long)m * M + k], e[k], t);
+    Ke[(long)j * M + m] = t;
+    s += (double)t * (double)e[m];
+  }
+  __shared__ double red[32];
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) atomicAdd(kl_acc, hldK[0] - (double)hldOm[slot] + 0.5 * (s - (double)M));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) warp_bwd_prep_kernel(long n, int S, const float* __restrict__ Gs_bar,
+                                                            long gs_stride, const float* __restrict__ Gm_bar,
+                                                            const float* __restrict__ eps,
+                                                            const float* __restrict__ log_var,
+                                                            float* __restrict__ mubar, float* __restrict__ varbar,
+                                                            float* __restrict__ q1bar, double* acc_hyp) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  float tot = 0.f;
+  if (r < n) {
+    float q = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      float mb = Gm_bar ? Gm_bar[r * D + d] : 0.f, vb = 0.f;
+      if (Gs_bar) {
+        for (int s = 0; s < S; ++s) {
+          const float g = Gs_bar[(long)s * gs_stride + r * D + d];
+          mb += g;
+          vb = fmaf(g, eps[((long)s * n + r) * D + d], vb);
+        }
+      }
+      mubar[r * D + d] = mb;
+      varbar[r * D + d] = vb;
+      q += vb;
+    }
+    q1bar[r] = -q;
+    tot = q;
+  }
+  __shared__ float red[32];
+  tot = block_sum<float>(tot, red);
+  if (threadIdx.x == 0) atomicAdd(&acc_hyp[1], (double)tot * (double)expf(log_var[0]));
+}
+
+// Abar = (delta - Z) mubar^T + q1bar o B + 2 sum_j varbar_j o T_j ;  AS_j = A o varbar_j
+template <int D>
+__global__ void warp_abar_kernel(int M, long n, const float* __restrict__ Z, const float* __restrict__ dlt,
+                                 const float* __restrict__ A, const float* __restrict__ B,
+                                 const float* __restrict__ T, const float* __restrict__ mubar,
+                                 const float* __restrict__ varbar, const float* __restrict__ q1bar,
+                                 float* __restrict__ Abar, float* __restrict__ AS) {
+  const long total = (long)M * n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = i / n;
+    const long r = i % n;
+    const float a = A[i];
+    float s = q1bar[r] * B[i];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float vb = varbar[r * D + d];
+      s = fmaf(dlt[m * D + d] - Z[m * D + d], mubar[r * D + d], s);
+      s = fmaf(2.f * vb, T[(long)d * total + i], s);
+      AS[(long)d * total + i] = a * vb;
+    }
+    Abar[i] = s;
+  }
+}
+
+// d(delta - Z)[m,j] = sum_r A[m,r] mubar[r,j]:  +acc_dlt, -acc_Z.  One warp per m, column chunks on y.
+template <int D>
+__global__ void __launch_bounds__(256) warp_dmz_kernel(int M, long n, long chunk, const float* __restrict__ A,
+                                                       const float* __restrict__ mubar, double* acc_dlt,
+                                                       double* acc_Z) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const long r0 = (long)blockIdx.y * chunk, r1 = (r0 + chunk < n) ? r0 + chunk : n;
+  float g[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) g[d] = 0.f;
+  for (long r = r0 + lane; r < r1; r += 32) {
+    const float a = A[(long)m * n + r];
+#pragma unroll
+    for (int d = 0; d < D; ++d) g[d] = fmaf(a, mubar[r * D + d], g[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float t = warp_sum(g[d]);
+    if (lane == 0) {
+      atomicAdd(&acc_dlt[m * D + d], (double)t);
+      atomicAdd(&acc_Z[m * D + d], -(double)t);
+    }
+  }
+}
+
+// e-bar_j = kl_bar * Ke_j :  acc_Z[:,j] += , acc_dlt[:,j] -=
+__global__ void kl_e_bwd_kernel(int M, int D, const float* __restrict__ Ke, const float* __restrict__ kl_bar,
+                                double* acc_Z, double* acc_dlt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  const int m = i / D, j = i % D;
+  const double g = (double)kl_bar[0] * (double)Ke[(long)j * M + m];
+  acc_Z[i] += g;
+  acc_dlt[i] -= g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian log-likelihood
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ll_fwd_kernel(long N, int P, int S, const float* __restrict__ F,
+                                                     const float* __restrict__ Y, const float* __restrict__ log_noise,
+                                                     double* ll_acc) {
+  const float sigma = expf(log_noise[0]) + GPSA_OFF;  // vgpsa.py:217
+  const float inv = 1.f / sigma;
+  const long NP = N * P, total = NP * S;
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float z = (Y[i % NP] - F[i]) * inv;
+    acc += (double)(z * z);
+  }
+  __shared__ double red[32];
+  acc = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) {
+    double v = -0.5 * acc;
+    if (blockIdx.x == 0) v -= (double)total * ((double)logf(sigma) + 0.91893853320467274178);
+    atomicAdd(ll_acc, v / (double)S);
+  }
+}
+
+__global__ void __launch_bounds__(256) ll_bwd_kernel(long N, int P, int S, const float* __restrict__ F,
+                                                     const float* __restrict__ Y, const float* __restrict__ log_noise,
+                                                     const float* __restrict__ ll_bar, float* __restrict__ F_bar,
+                                                     double* acc_noise) {
+  const float en = expf(log_noise[0]);
+  const float sigma = en + GPSA_OFF;
+  const float inv = 1.f / sigma;
+  const float c = ll_bar[0] * inv * inv / (float)S;
+  const long NP = N * P, total = NP * S;
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float d = Y[i % NP] - F[i];
+    F_bar[i] = c * d;
+    const float z = d * inv;
+    acc += (double)(z * z);
+  }
+  __shared__ double red[32];
+  acc = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) {
+    // dLL/dsigma = sum((y-f)^2/sigma^3 - 1/sigma)/S ; dsigma/dlog_noise = exp(log_noise)
+    double v = acc * (double)inv;
+    if (blockIdx.x == 0) v -= (double)total * (double)inv;
+    atomicAdd(acc_noise, (double)ll_bar[0] * v * (double)en / (double)S);
+  }
+}
+
+int grid_for(long n, int per_block = 256, int cap = 148 * 16) {
+  const long b = (n + per_block - 1) / per_block;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+// ================================================================================================
+// exported entry points
+// ================================================================================================
+extern "C" int gpsa_version(void) { return 100; }
+
+extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA,
+                             const float* B, long brs, long bcs, long sB, float beta, float* C, long ldc, long sC,
+                             int batch, cudaStream_t st) {
+  return gemm_strided<float, float, float, float>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, C, ldc,
+                                                  sC, batch);
+}
+
+extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_ls, const float* log_var,
+                                  float* Lk, float* Kinv, double* half_logdet, int* info, double* ws64,
+                                  cudaStream_t st) {
+  if (M <= 0 || D < 1 || D > 3) return GPSA_ERR_ARG;
+  const long MM = (long)M * M;
+  double* Kd = ws64;
+  double* Xd = ws64 + MM;
+  double* Kinv_d = ws64 + 2 * MM;
+  const int blocks = gpsa_cdiv(MM, 256);
+#define PK(DD, KK) prior_kuu_kernel<DD, KK><<<blocks, 256, 0, st>>>(M, Z, log_ls, log_var, Kd)
+  if (kind == GPSA_KIND_RBF) {
+    if (D == 1) PK(1, GPSA_KIND_RBF); else if (D == 2) PK(2, GPSA_KIND_RBF); else PK(3, GPSA_KIND_RBF);
+  } else if (kind == GPSA_KIND_MATERN12) {
+    if (D == 1) PK(1, GPSA_KIND_MATERN12); else if (D == 2) PK(2, GPSA_KIND_MATERN12); else PK(3, GPSA_KIND_MATERN12);
+  } else {
+    return GPSA_ERR_UNSUPPORTED;
+  }
+#undef PK
+  GPSA_LAUNCH_CHECK();
+  TRY(gpsa_potrf_batched_f64(M, 1, Kd, half_logdet, info, st));
+  TRY(gpsa_trtri_batched_f64(M, 1, Kd, Xd, st));
+  // K^-1 = X^T X
+  TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv_d, M, 0, 1)));
+  cvt_d2f_kernel<<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
+  cvt_d2f_kernel<<<grid_for(MM), 256, 0, st>>>(MM, Kinv_d, Kinv);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, float* half_logdet,
+                                  int* info, cudaStream_t st) {
+  if (M <= 0 || B <= 0) return GPSA_OK;
+  const long MM = (long)M * M;
+  TRY((gemm_strided<float, float, float, float>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, Omega, M, MM, B, 1,
+                                                (double)GPSA_OFF)));
+  if (cudaMemcpyAsync(Ltril, Omega, sizeof(float) * MM * B, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return GPSA_ERR_CUDA;
+  return gpsa_potrf_batched_f32(M, B, Ltril, half_logdet, info, st);
+}
+
+extern "C" int gpsa_omega_grad(int M, int B, const float* Osq, const float* Ltril, float* Obar, const float* coef,
+                               float* Linv, float* Osq_bar, cudaStream_t st) {
+  if (M <= 0 || B <= 0) return GPSA_OK;
+  const long MM = (long)M * M;
+  if (coef) {
+    TRY(gpsa_trtri_batched_f32(M, B, Ltril, Linv, st));
+    // Obar[b] += coef[b] * Linv^T Linv
+    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 1.0, Linv, 1, M, MM, Linv, M, 1, MM, 1.0, Obar, M, MM, B,
+                                                  1, 0.0, 0, coef, 1)));
+  }
+  // Osq_bar = (Obar + Obar^T) Osq = 2 Obar Osq  (Obar symmetric)
+  return gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
+                                                  B);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t st) {
+  const int M = a->M, D = a->D;
+  const long n = a->n, MM = (long)M * M;
+  if (n <= 0) return GPSA_OK;
+  if (D < 1 || D > 3) return GPSA_ERR_ARG;
+  TRY(gpsa_prior_prepare(a->kind, D, M, a->Z, a->log_ls, a->log_var, a->Lk, a->Kinv, a->hld_K, a->info, a->ws64, st));
+  TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, n, a->Z, a->X, a->log_ls, a->log_var, a->B, st));
+  TRY(gemm_nn(st, M, (int)n, M, 1.0, a->Kinv, M, a->B, n, 0.0, a->A, n));
+  // T_j = Omega_{v*D+j} A  -- the marginal variance uses slice v*D+j (vgpsa.py:336-339)
+  TRY((gemm_strided<float, float, float, float>(st, M, (int)n, M, 1.0, a->Omega_G + (long)a->v * D * MM, M, 1, MM, a->A,
+                                                n, 1, 0, 0.0, a->T, n, (long)M * n, D)));
+  const size_t smem = (size_t)M * D * sizeof(float);
+  const int blocks = gpsa_cdiv(n, 256);
+#define WP(DD)                                                                                                       \
+  warp_predict_kernel<DD><<<blocks, 256, smem, st>>>(M, n, a->S, a->Z, a->dlt, a->A, a->B, a->T, a->X, a->eps,       \
+                                                     a->log_var, a->var, a->Gmean, a->Gs, a->gs_stride)
+  if (D == 1) WP(1); else if (D == 2) WP(2); else WP(3);
+#undef WP
+  GPSA_LAUNCH_CHECK();
+  if (a->kl_acc) {
+    kl_G_kernel<<<D, 256, M * sizeof(float), st>>>(M, D, a->V, a->v, a->Kinv, a->Omega_G, a->hld_Omega, a->Z, a->dlt,
+                                                   a->hld_K, a->Ke, a->kl_acc);
+    GPSA_LAUNCH_CHECK();
+  }
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t st) {
+  const int M = a->M, D = a->D, V = a->V, v = a->v;
+  const long n = a->n, MM = (long)M * M;
+  if (n <= 0) return GPSA_OK;
+  if (D < 1 || D > 3) return GPSA_ERR_ARG;
+  const int blocks = gpsa_cdiv(n, 256);
+#define WB(DD)                                                                                                 \
+  warp_bwd_prep_kernel<DD><<<blocks, 256, 0, st>>>(n, a->S, a->Gs_bar, a->gs_stride, a->Gm_bar, a->eps,        \
+                                                   a->log_var, a->mubar, a->varbar, a->q1bar, a->acc_hyp)
+  if (D == 1) WB(1); else if (D == 2) WB(2); else WB(3);
+#undef WB
+  GPSA_LAUNCH_CHECK();
+  const int eb = grid_for((long)M * n);
+#define WA(DD)                                                                                                  \
+  warp_abar_kernel<DD><<<eb, 256, 0, st>>>(M, n, a->Z, a->dlt, a->A, a->B, a->T, a->mubar, a->varbar, a->q1bar, \
+                                           a->Abar, a->AS)
+  if (D == 1) WA(1); else if (D == 2) WA(2); else WA(3);
+#undef WA
+  GPSA_LAUNCH_CHECK();
+  {
+    const int row_ctas = gpsa_cdiv(M, 8);
+    long nchunk = (148 * 4 + row_ctas - 1) / row_ctas;
+    const long maxc = (n + 1023) / 1024;
+    if (nchunk > maxc) nchunk = maxc;
+    if (nchunk < 1) nchunk = 1;
+    const long chunk = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
+    dim3 grid(row_ctas, gpsa_cdiv(n, chunk));
+#define WD(DD) warp_dmz_kernel<DD><<<grid, 256, 0, st>>>(M, n, chunk, a->A, a->mubar, a->acc_dlt, a->acc_Z)
+    if (D == 1) WD(1); else if (D == 2) WD(2); else WD(3);
+#undef WD
+    GPSA_LAUNCH_CHECK();
+  }
+  // Omega-bar_{v*D+j} += (A o varbar_j) A^T
+  {
+    const int split = pick_split(M, M, n, D);
+    TRY((gemm_strided<float, float, float, float>(st, M, M, n, 1.0, a->AS, n, 1, (long)M * n, a->A, 1, n, 0, 1.0,
+                                                  a->Obar_G + (long)v * D * MM, M, MM, D, split)));
+  }
+  // C = K^-1 Abar ; Kbar = -C A^T ; Bbar = C + q1bar o A
+  TRY(gemm_nn(st, M, (int)n, M, 1.0, a->Kinv, M, a->Abar, n, 0.0, a->C, n));
+  TRY(gemm_nt(st, M, M, n, -1.0, a->C, n, a->A, n, 0.0, a->Kbar, M));
+  TRY(colscale(st, M, n, a->q1bar, a->A, a->C, 1));
+  if (a->kl_bar) {
+    // KL_v = sum_j [hldK - hldOm_j' + 0.5 (tr(K^-1 Om_j') + e_j^T K^-1 e_j - M)],  j' = j*V+v
+    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, D, (long)V * MM, a->Omega_G + (long)v * MM, a->Som);
+    GPSA_LAUNCH_CHECK();
+    TRY(gemm_nn(st, M, M, M, 1.0, a->Kinv, M, a->Som, M, 0.0, a->T1, M));
+    TRY(gemm_nn(st, M, M, M, -0.5, a->T1, M, a->Kinv, M, 1.0, a->Kbar, M, a->kl_bar));
+    TRY((gemm_strided<float, float, float, float>(st, M, M, D, -0.5, a->Ke, 1, M, 0, a->Ke, M, 1, 0, 1.0, a->Kbar, M, 0,
+                                                  1, 1, 0.0, 0, a->kl_bar, 0)));
+    TRY(axpy_dev(st, MM, 0.5f * (float)D, a->kl_bar, a->Kinv, a->Kbar));
+    for (int j = 0; j < D; ++j)
+      TRY(axpy_dev(st, MM, 0.5f, a->kl_bar, a->Kinv, a->Obar_G + (long)(j * V + v) * MM));
+    kl_e_bwd_kernel<<<gpsa_cdiv(M * D, 256), 256, 0, st>>>(M, D, a->Ke, a->kl_bar, a->acc_Z, a->acc_dlt);
+    GPSA_LAUNCH_CHECK();
+  }
+  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, n, a->Z, a->X, a->log_ls, a->log_var, a->C, a->acc_Z, nullptr, nullptr,
+                             a->acc_hyp, st));
+  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, M, a->Z, a->Z, a->log_ls, a->log_var, a->Kbar, a->acc_Z, nullptr, a->acc_Z,
+                             a->acc_hyp, st));
+  return GPSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st) {
+  const int M = a->M, D = a->D, L = a->L;
+  const long R = a->R;
+  if (R <= 0 || L <= 0) return GPSA_OK;
+  if (D < 1 || D > 3) return GPSA_ERR_ARG;
+  TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->hld_K, a->info, a->ws64, st));
+  TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
+  TRY(gemm_nn(st, M, (int)R, M, 1.0, a->Kinv, M, a->B, R, 0.0, a->A, R));
+  q1_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->q1);
+  GPSA_LAUNCH_CHECK();
+  // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
+  TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
+                                                1)));
+  TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
+  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
+  sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->q1, a->eps, a->log_var, a->F, a->var);
+  GPSA_LAUNCH_CHECK();
+  // KD = K^-1 delta
+  TRY(gemm_nn(st, M, L, M, 1.0, a->Kinv, M, a->dlt, L, 0.0, a->KD, L));
+  if (a->kl_acc) {
+    kl_F_kernel<<<L, 256, 0, st>>>(M, L, a->Kinv, a->Omega, a->hld_Omega, a->dlt, a->KD, a->hld_K, a->kl_acc);
+    GPSA_LAUNCH_CHECK();
+  }
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st) {
+  const int M = a->M, D = a->D, L = a->L;
+  const long R = a->R, MM = (long)M * M;
+  if (R <= 0 || L <= 0) return GPSA_OK;
+  if (D < 1 || D > 3) return GPSA_ERR_ARG;
+  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  {
+    long b = (R + 7) / 8;
+    if (b > 148 * 8) b = 148 * 8;
+    sample_bwd_kernel<<<(int)b, 256, 0, st>>>(R, L, a->F_bar, a->eps, a->var, a->log_var, a->Gm, a->q1bar, a->acc_hyp);
+    GPSA_LAUNCH_CHECK();
+  }
+  // delta-bar = A Fbar (+ kl_bar K^-1 delta)
+  {
+    const int split = pick_split(M, L, R, 1);
+    if (cudaMemsetAsync(a->dlt_bar, 0, sizeof(float) * (size_t)M * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
+    TRY((gemm_strided<float, float, float, float>(st, M, L, R, 1.0, a->A, R, 1, 0, a->F_bar, L, 1, 0, 1.0, a->dlt_bar,
+                                                  L, 0, 1, split)));
+  }
+  if (a->kl_bar) TRY(axpy_dev(st, (long)M * L, 1.f, a->kl_bar, a->KD, a->dlt_bar));
+  // Abar = q1bar o B + delta Fbar^T + 2 (sum_p Gm Omega_p) a
+  TRY(colscale(st, M, R, a->q1bar, a->B, a->Abar, 0));
+  TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
+                                                R, 0, 1)));
+  TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
+  // Omega-bar = sum_r Gm a a^T (+ 0.5 kl_bar K^-1)
+  TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
+  TRY(gpsa_feat_unpack(M, L, a->H, a->kl_bar ? a->Kinv : nullptr, 0.5f, a->kl_bar, a->Obar, st));
+  // C = K^-1 Abar ; Kbar = -C A^T ; Bbar = C + q1bar o A
+  TRY(gemm_nn(st, M, (int)R, M, 1.0, a->Kinv, M, a->Abar, R, 0.0, a->C, R));
+  TRY(gemm_nt(st, M, M, R, -1.0, a->C, R, a->A, R, 0.0, a->Kbar, M));
+  TRY(colscale(st, M, R, a->q1bar, a->A, a->C, 1));
+  if (a->kl_bar) {
+    // KL_F = sum_p [hldK - hldOm_p + 0.5 (tr(K^-1 Om_p) + d_p^T K^-1 d_p - M)]
+    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, L, MM, a->Omega, a->Som);
+    GPSA_LAUNCH_CHECK();
+    TRY(gemm_nn(st, M, M, M, 1.0, a->Kinv, M, a->Som, M, 0.0, a->T1, M));
+    TRY(gemm_nn(st, M, M, M, -0.5, a->T1, M, a->Kinv, M, 1.0, a->Kbar, M, a->kl_bar));
+    TRY(gemm_nt(st, M, M, L, -0.5, a->KD, L, a->KD, L, 1.0, a->Kbar, M, a->kl_bar));
+    TRY(axpy_dev(st, MM, 0.5f * (float)L, a->kl_bar, a->Kinv, a->Kbar));
+  }
+  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->C, a->acc_Gt, a->G_bar, nullptr,
+                             a->acc_hyp, st));
+  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, M, a->Gt, a->Gt, a->log_ls, a->log_var, a->Kbar, a->acc_Gt, nullptr,
+                             a->acc_Gt, a->acc_hyp, st));
+  return GPSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
+                                    double* ll_acc, cudaStream_t st) {
+  if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
+  ll_fwd_kernel<<<grid_for(N * P * S, 1024, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_acc);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_gaussian_ll_bwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
+                                    const float* ll_bar, float* F_bar, double* acc_noise, cudaStream_t st) {
+  if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
+  ll_bwd_kernel<<<grid_for(N * P * S, 1024, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_bar, F_bar, acc_noise);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}

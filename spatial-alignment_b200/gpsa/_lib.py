@@ -1,0 +1,150 @@
+"""ctypes binding of the C ABI declared in include/gpsa_b200.h.
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is no
+CPU or PyTorch fallback: if the library is missing or a tensor is not a contiguous CUDA float32
+tensor the call raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpsa_b200.so")
+
+KIND_RBF, KIND_MATERN12 = 0, 1
+OFF = 1e-5
+
+_lib = None
+
+_ERR = {1: "bad argument", 2: "CUDA launch error", 3: "unsupported size or kernel kind"}
+
+
+class GPSALibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GPSALibraryError(
+                f"{LIB_PATH} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "gpsa_b200 has no CPU fallback."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+P = C.c_void_p
+I = C.c_int
+LNG = C.c_long
+F = C.c_float
+
+
+class WarpFwdArgs(C.Structure):
+    _fields_ = [
+        ("kind", I), ("D", I), ("M", I), ("V", I), ("v", I), ("S", I), ("n", LNG),
+        ("Z", P), ("dlt", P), ("log_ls", P), ("log_var", P), ("Omega_G", P), ("hld_Omega", P), ("X", P), ("eps", P),
+        ("Lk", P), ("Kinv", P), ("hld_K", P), ("info", P),
+        ("A", P), ("B", P), ("T", P), ("Ke", P), ("var", P), ("Gmean", P), ("Gs", P), ("gs_stride", LNG),
+        ("kl_acc", P), ("ws64", P),
+    ]
+
+
+class WarpBwdArgs(C.Structure):
+    _fields_ = [
+        ("kind", I), ("D", I), ("M", I), ("V", I), ("v", I), ("S", I), ("n", LNG),
+        ("Z", P), ("dlt", P), ("log_ls", P), ("log_var", P), ("Omega_G", P), ("X", P), ("eps", P),
+        ("Kinv", P), ("A", P), ("B", P), ("T", P), ("Ke", P),
+        ("Gs_bar", P), ("gs_stride", LNG), ("Gm_bar", P), ("kl_bar", P),
+        ("acc_Z", P), ("acc_dlt", P), ("acc_hyp", P), ("Obar_G", P),
+        ("mubar", P), ("varbar", P), ("q1bar", P), ("Abar", P), ("C", P), ("AS", P),
+        ("Kbar", P), ("Som", P), ("T1", P),
+    ]
+
+
+class DataFwdArgs(C.Structure):
+    _fields_ = [
+        ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
+        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P), ("eps", P),
+        ("Lk", P), ("Kinv", P), ("hld_K", P), ("info", P),
+        ("A", P), ("B", P), ("q1", P), ("W", P), ("KD", P), ("F", P), ("var", P),
+        ("kl_acc", P), ("ws64", P), ("engine", I),
+    ]
+
+
+class DataBwdArgs(C.Structure):
+    _fields_ = [
+        ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
+        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("G", P), ("eps", P),
+        ("Kinv", P), ("A", P), ("B", P), ("W", P), ("KD", P), ("var", P),
+        ("F_bar", P), ("kl_bar", P),
+        ("G_bar", P), ("acc_Gt", P), ("acc_hyp", P), ("dlt_bar", P), ("Obar", P),
+        ("Gm", P), ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("Kbar", P), ("Som", P), ("T1", P),
+        ("engine", I),
+    ]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); kept in one table so the CPU test can
+# check that every symbol of include/gpsa_b200.h is exported.
+SIGNATURES = {
+    "gpsa_version": [],
+    "gpsa_kernel_matrix_fwd": [I, I, I, LNG, P, P, P, P, P, P],
+    "gpsa_kernel_matrix_bwd": [I, I, I, LNG, P, P, P, P, P, P, P, P, P, P],
+    "gpsa_potrf_batched_f32": [I, I, P, P, P, P],
+    "gpsa_potrf_batched_f64": [I, I, P, P, P, P],
+    "gpsa_trtri_batched_f32": [I, I, P, P, P],
+    "gpsa_trtri_batched_f64": [I, I, P, P, P],
+    "gpsa_gemm_f32": [I, I, LNG, F, P, LNG, LNG, LNG, P, LNG, LNG, LNG, F, P, LNG, LNG, I, P],
+    "gpsa_prior_prepare": [I, I, I, P, P, P, P, P, P, P, P, P],
+    "gpsa_omega_prepare": [I, I, P, P, P, P, P, P],
+    "gpsa_omega_grad": [I, I, P, P, P, P, P, P, P],
+    "gpsa_feat_count": [I],
+    "gpsa_feat_pack": [I, I, P, P, P],
+    "gpsa_feat_unpack": [I, I, P, P, F, P, P, P],
+    "gpsa_quadform_fwd_f32": [I, LNG, I, P, P, P, P],
+    "gpsa_quadform_bwd_omega_f32": [I, LNG, I, P, P, P, P],
+    "gpsa_quadform_bwd_alpha_f32": [I, LNG, I, P, P, P, P, P],
+    "gpsa_warp_view_fwd": [C.POINTER(WarpFwdArgs), P],
+    "gpsa_warp_view_bwd": [C.POINTER(WarpBwdArgs), P],
+    "gpsa_data_layer_fwd": [C.POINTER(DataFwdArgs), P],
+    "gpsa_data_layer_bwd": [C.POINTER(DataBwdArgs), P],
+    "gpsa_gaussian_ll_fwd": [LNG, I, I, P, P, P, P, P],
+    "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
+}
+_RESTYPE = {"gpsa_feat_count": LNG}
+
+
+def _declare(l):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, I)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GPSALibraryError(f"{what} failed: {_ERR.get(rc, rc)}")
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GPSALibraryError("gpsa_b200 is CUDA-only: got a CPU tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise GPSALibraryError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise GPSALibraryError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def feat_count(M):
+    return int(lib().gpsa_feat_count(int(M)))

@@ -1,0 +1,306 @@
+"""torch.autograd.Function wrappers with EXPLICIT forward and backward around the C ABI
+(include/gpsa_b200.h).  Nothing below this file uses autograd; every gradient is the analytic
+backward implemented in CUDA."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import DataBwdArgs, DataFwdArgs, WarpBwdArgs, WarpFwdArgs, check, lib, ptr, stream
+
+f32, f64, i32 = torch.float32, torch.float64, torch.int32
+
+KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12}
+
+# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16
+ENGINE = {"value": 0}
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _new(like, *shape, dtype=f32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _zeros(like, *shape, dtype=f32):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+def check_info(info, what):
+    """Raise like torch.cholesky does when a matrix was not positive definite (this reads a device
+    flag, i.e. it synchronises; callers gate it behind GPSA_B200_CHECK=1 / debug mode)."""
+    bad = torch.nonzero(info)
+    if bad.numel():
+        raise RuntimeError(f"{what}: matrix {int(bad[0, 0])} is not positive-definite")
+
+
+# --------------------------------------------------------------------------------------------------
+class KernelMatrix(torch.autograd.Function):
+    """K[m, r] = k(x1[m], x2[r]) for x1 [M,D], x2 [R,D]; differentiable in all four tensors."""
+
+    @staticmethod
+    def forward(ctx, kind, x1, x2, log_ls, log_var):
+        x1, x2 = _c(x1.detach()), _c(x2.detach())
+        log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
+        M, D = x1.shape
+        R = x2.shape[0]
+        if x2.shape[1] != D or not 1 <= D <= 3:
+            raise ValueError("kernel inputs must share a trailing dimension of 1, 2 or 3")
+        K = _new(x1, M, R)
+        check(lib().gpsa_kernel_matrix_fwd(kind, D, M, R, ptr(x1), ptr(x2), ptr(log_ls), ptr(log_var), ptr(K), stream()),
+              "kernel_matrix_fwd")
+        ctx.kind = kind
+        ctx.save_for_backward(x1, x2, log_ls, log_var)
+        return K
+
+    @staticmethod
+    def backward(ctx, Kbar):
+        x1, x2, log_ls, log_var = ctx.saved_tensors
+        M, D = x1.shape
+        R = x2.shape[0]
+        Kbar = _c(Kbar)
+        acc_x1 = _zeros(x1, M, D, dtype=f64)
+        acc_h = _zeros(x1, 2, dtype=f64)
+        x2bar = _new(x1, R, D)
+        check(lib().gpsa_kernel_matrix_bwd(ctx.kind, D, M, R, ptr(x1), ptr(x2), ptr(log_ls), ptr(log_var), ptr(Kbar),
+                                           ptr(acc_x1, f64), ptr(x2bar), None, ptr(acc_h, f64), stream()),
+              "kernel_matrix_bwd")
+        h = acc_h.to(f32)
+        return None, acc_x1.to(f32), x2bar, h[0:1], h[1:2]
+
+
+def kernel_matrix(kind_name, x1, x2, log_ls, log_var):
+    """Batch-broadcasting front end used by gpsa.rbf_kernel / gpsa.matern12_kernel:
+    x1 [n1,D], x2 [..., n2, D] -> [..., n1, n2]  (reference gpsa/util/util.py:18-23 semantics)."""
+    kind = KINDS[kind_name]
+    if x1.dim() != 2:
+        if x1.shape[:-2] == x2.shape[:-2] and x1.dim() == x2.dim():
+            flat1, flat2 = x1.reshape(-1, *x1.shape[-2:]), x2.reshape(-1, *x2.shape[-2:])
+            out = torch.stack([kernel_matrix(kind_name, a, b, log_ls, log_var) for a, b in zip(flat1, flat2)])
+            return out.reshape(*x1.shape[:-2], x1.shape[-2], x2.shape[-2])
+        raise NotImplementedError("x1 must be [n1, D] or share x2's batch dimensions")
+    batch = x2.shape[:-2]
+    n2, D = x2.shape[-2:]
+    K = KernelMatrix.apply(kind, x1, x2.reshape(-1, D), log_ls.reshape(-1)[:1], log_var.reshape(-1)[:1])
+    if len(batch) == 0:
+        return K
+    n1 = x1.shape[0]
+    return K.reshape(n1, -1, n2).movedim(0, 1).reshape(*batch, n1, n2)
+
+
+# --------------------------------------------------------------------------------------------------
+def omega_prepare(Osq):
+    """Omega = Osq Osq^T + 1e-5 I, its Cholesky factor, half log-dets, info flags."""
+    B, M, _ = Osq.shape
+    Omega, Ltril = _new(Osq, B, M, M), _new(Osq, B, M, M)
+    hld = _new(Osq, B)
+    info = _new(Osq, B, dtype=i32)
+    check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(hld), ptr(info, i32), stream()),
+          "omega_prepare")
+    return Omega, Ltril, hld, info
+
+
+def omega_grad(Osq, Ltril, Obar, coef):
+    B, M, _ = Osq.shape
+    Linv = _new(Osq, B, M, M) if coef is not None else None
+    out = _new(Osq, B, M, M)
+    check(lib().gpsa_omega_grad(M, B, ptr(Osq), ptr(Ltril), ptr(Obar), ptr(coef), ptr(Linv), ptr(out), stream()),
+          "omega_grad")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+class WarpLayer(torch.autograd.Function):
+    """All non-fixed views of the warp GP (reference gpsa/models/vgpsa.py:255-351, KL :498-516).
+
+    forward(meta, Xtilde, delta_G, Omega_sqt_G, log_ls, log_var, *[X_v, eps_v for each free view])
+      -> (KL_G, Kuu_chol_list, Omega_tril_G, info, *[Gmean_v, Gsamples_v ...])
+    meta = dict(kind=int, V=int, S=int, free=[view indices], with_kl=bool)
+    """
+
+    @staticmethod
+    def forward(ctx, meta, Xtilde, delta_G, Osq_G, log_ls, log_var, *xe):
+        Xtilde, delta_G, Osq_G = _c(Xtilde.detach()), _c(delta_G.detach()), _c(Osq_G.detach())
+        log_ls, log_var = _c(log_ls.detach()), _c(log_var.detach())
+        V, M, D = Xtilde.shape
+        S, free, kind = meta["S"], meta["free"], meta["kind"]
+        Omega_G, Ltril_G, hld_G, info_G = omega_prepare(Osq_G)
+        kl = _zeros(Xtilde, 1, dtype=f64)
+        Lk_all = torch.full((V, M, M), float("nan"), dtype=f32, device=Xtilde.device)  # NaN rows for fixed views (:237-242)
+        ws64 = _new(Xtilde, 3 * M * M, dtype=f64)
+        info = _zeros(Xtilde, V, dtype=i32)
+        hldK = _zeros(Xtilde, V, dtype=f64)
+        saved, outs = [], []
+        for k, v in enumerate(free):
+            X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
+            n = X.shape[0]
+            Kinv = _new(X, M, M)
+            A, B, T = _new(X, M, n), _new(X, M, n), _new(X, D, M, n)
+            Ke, var = _new(X, D, M), _new(X, n, D)
+            Gmean, Gs = _new(X, n, D), _new(X, S, n, D)
+            if n > 0:
+                a = WarpFwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
+                                Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
+                                log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v,
+                                Omega_G=ptr(Omega_G), hld_Omega=ptr(hld_G), X=ptr(X), eps=ptr(eps),
+                                Lk=ptr(Lk_all) + 4 * v * M * M, Kinv=ptr(Kinv), hld_K=ptr(hldK, f64) + 8 * v,
+                                info=ptr(info, i32) + 4 * v, A=ptr(A), B=ptr(B), T=ptr(T), Ke=ptr(Ke), var=ptr(var),
+                                Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
+                                kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64))
+                check(lib().gpsa_warp_view_fwd(C.byref(a), stream()), "warp_view_fwd")
+            saved += [X, eps, Kinv, A, B, T, Ke]
+            outs += [Gmean, Gs]
+        ctx.meta = meta
+        ctx.save_for_backward(Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, Ltril_G, *saved)
+        info_all = torch.cat([info_G, info])
+        ctx.mark_non_differentiable(Lk_all, Ltril_G, info_all)
+        return (kl.to(f32).reshape(()), Lk_all, Ltril_G, info_all, *outs)
+
+    @staticmethod
+    def backward(ctx, kl_bar, _1, _2, _3, *gouts):
+        meta = ctx.meta
+        Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, Ltril_G, *saved = ctx.saved_tensors
+        V, M, D = Xtilde.shape
+        S, free, kind = meta["S"], meta["free"], meta["kind"]
+        dev = Xtilde
+        use_kl = meta["with_kl"] and kl_bar is not None
+        klb = _c(kl_bar.to(f32).reshape(1)) if use_kl else None
+        acc_Z, acc_dlt = _zeros(dev, V, M, D, dtype=f64), _zeros(dev, V, M, D, dtype=f64)
+        acc_hyp = _zeros(dev, V, 2, dtype=f64)
+        Obar = _zeros(dev, V * D, M, M)
+        Kbar, Som, T1 = _new(dev, M, M), _new(dev, M, M), _new(dev, M, M)
+        xgrads = []
+        for k, v in enumerate(free):
+            X, eps, Kinv, A, B, T, Ke = saved[7 * k: 7 * k + 7]
+            n = X.shape[0]
+            gm, gs = gouts[2 * k], gouts[2 * k + 1]
+            xgrads += [None, None]
+            if n == 0:
+                continue
+            gm = _c(gm) if gm is not None else None
+            gs = _c(gs) if gs is not None else None
+            mubar, varbar, q1bar = _new(dev, n, D), _new(dev, n, D), _new(dev, n)
+            Abar, Cm, AS = _new(dev, M, n), _new(dev, M, n), _new(dev, D, M, n)
+            a = WarpBwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
+                            Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
+                            log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v, Omega_G=ptr(Omega_G),
+                            X=ptr(X), eps=ptr(eps), Kinv=ptr(Kinv), A=ptr(A), B=ptr(B), T=ptr(T), Ke=ptr(Ke),
+                            Gs_bar=ptr(gs), gs_stride=n * D, Gm_bar=ptr(gm), kl_bar=ptr(klb),
+                            acc_Z=ptr(acc_Z, f64) + 8 * v * M * D, acc_dlt=ptr(acc_dlt, f64) + 8 * v * M * D,
+                            acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
+                            mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm),
+                            AS=ptr(AS), Kbar=ptr(Kbar), Som=ptr(Som), T1=ptr(T1))
+            check(lib().gpsa_warp_view_bwd(C.byref(a), stream()), "warp_view_bwd")
+        coef = None
+        if use_kl:
+            # d(-half_logdet Omega_{j*V+v})/dOmega = -1/2 Omega^-1 on the free views' KL slices only;
+            # meta["kl_mask"] holds -0.5 there and 0 elsewhere (device tensor, built once by the model)
+            coef = _c(meta["kl_mask"] * klb)
+        Osq_bar = omega_grad(Osq_G, Ltril_G, Obar, coef)
+        hyp = acc_hyp.to(f32)
+        return (None, acc_Z.to(f32), acc_dlt.to(f32), Osq_bar, _c(hyp[:, 0]), _c(hyp[:, 1]), *xgrads)
+
+
+# --------------------------------------------------------------------------------------------------
+class DataLayer(torch.autograd.Function):
+    """One modality of the data GP (reference gpsa/models/vgpsa.py:390-426, KL :520-530).
+
+    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D], eps [S,N,L])
+      -> (F_latent [S,N,L], KL_F, Kuu_chol_F, Omega_tril_F, info)
+    """
+
+    @staticmethod
+    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps):
+        Gtilde, delta_F, Osq_F = _c(Gtilde.detach()), _c(delta_F.detach()), _c(Osq_F.detach())
+        log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
+        G, eps = _c(G.detach()), _c(eps.detach())
+        M, D = Gtilde.shape
+        L = delta_F.shape[1]
+        S, N = G.shape[0], G.shape[1]
+        R = S * N
+        kind = meta["kind"]
+        pre = meta.get("omega")
+        Omega, Ltril, hld, info_O = pre if pre is not None else omega_prepare(Osq_F)
+        Lk, Kinv = _new(G, M, M), _new(G, M, M)
+        hldK = _zeros(G, 1, dtype=f64)
+        info = _zeros(G, 1, dtype=i32)
+        A, B, q1 = _new(G, M, R), _new(G, M, R), _new(G, R)
+        W = _new(G, _lib.feat_count(M), L)
+        KD = _new(G, M, L)
+        Fo, var = _new(G, S, N, L), _new(G, R, L)
+        kl = _zeros(G, 1, dtype=f64)
+        ws64 = _new(G, 3 * M * M, dtype=f64)
+        a = DataFwdArgs(kind=kind, D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls), log_var=ptr(log_var),
+                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld), G=ptr(G), eps=ptr(eps),
+                        Lk=ptr(Lk), Kinv=ptr(Kinv), hld_K=ptr(hldK, f64), info=ptr(info, i32),
+                        A=ptr(A), B=ptr(B), q1=ptr(q1), W=ptr(W), KD=ptr(KD), F=ptr(Fo), var=ptr(var),
+                        kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
+                        engine=ENGINE["value"])
+        check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
+        ctx.meta = meta
+        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, Ltril, Kinv, A, B, W, KD, var)
+        info_all = torch.cat([info_O, info])
+        ctx.mark_non_differentiable(Lk, Ltril, info_all)
+        return Fo, kl.to(f32).reshape(()), Lk, Ltril, info_all
+
+    @staticmethod
+    def backward(ctx, F_bar, kl_bar, _1, _2, _3):
+        meta = ctx.meta
+        Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, Ltril, Kinv, A, B, W, KD, var = ctx.saved_tensors
+        M, D = Gtilde.shape
+        L = delta_F.shape[1]
+        S, N = G.shape[0], G.shape[1]
+        R = S * N
+        dev = G
+        use_kl = meta["with_kl"] and kl_bar is not None
+        klb = _c(kl_bar.to(f32).reshape(1)) if use_kl else None
+        F_bar = _c(F_bar) if F_bar is not None else _zeros(dev, S, N, L)
+        G_bar = _new(dev, S, N, D)
+        acc_Gt, acc_hyp = _zeros(dev, M, D, dtype=f64), _zeros(dev, 2, dtype=f64)
+        dlt_bar, Obar = _new(dev, M, L), _new(dev, L, M, M)
+        Gm, q1bar = _new(dev, R, L), _new(dev, R)
+        Abar, Cm = _new(dev, M, R), _new(dev, M, R)
+        H = _new(dev, W.shape[0], L)
+        Kbar, Som, T1 = _new(dev, M, M), _new(dev, M, M), _new(dev, M, M)
+        a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
+                        log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G), eps=ptr(eps),
+                        Kinv=ptr(Kinv), A=ptr(A), B=ptr(B), W=ptr(W), KD=ptr(KD), var=ptr(var),
+                        F_bar=ptr(F_bar), kl_bar=ptr(klb), G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
+                        acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar), Gm=ptr(Gm),
+                        q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), Kbar=ptr(Kbar), Som=ptr(Som),
+                        T1=ptr(T1), engine=ENGINE["value"])
+        check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
+        coef = _c((-0.5 * klb).expand(L)) if use_kl else None
+        Osq_bar = omega_grad(Osq_F, Ltril, Obar, coef)
+        hyp = acc_hyp.to(f32)
+        return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar, None
+
+
+# --------------------------------------------------------------------------------------------------
+class GaussianLL(torch.autograd.Function):
+    """sum log N(Y; F, sigma) / S with sigma = exp(log_noise) + 1e-5 as the Normal scale
+    (reference gpsa/models/vgpsa.py:217, :532-538).  F [S,N,P], Y [N,P], log_noise: 1 element."""
+
+    @staticmethod
+    def forward(ctx, F, Y, log_noise):
+        F, Y, log_noise = _c(F.detach()), _c(Y.detach()), _c(log_noise.detach().reshape(1))
+        S, N, P = F.shape
+        if Y.shape != (N, P):
+            raise ValueError(f"outputs have shape {tuple(Y.shape)}, F_samples imply {(N, P)}")
+        acc = _zeros(F, 1, dtype=f64)
+        check(lib().gpsa_gaussian_ll_fwd(N, P, S, ptr(F), ptr(Y), ptr(log_noise), ptr(acc, f64), stream()), "ll_fwd")
+        ctx.save_for_backward(F, Y, log_noise)
+        return acc.to(f32).reshape(())
+
+    @staticmethod
+    def backward(ctx, ll_bar):
+        F, Y, log_noise = ctx.saved_tensors
+        S, N, P = F.shape
+        llb = _c(ll_bar.to(f32).reshape(1))
+        F_bar = _new(F, S, N, P)
+        acc = _zeros(F, 1, dtype=f64)
+        check(lib().gpsa_gaussian_ll_bwd(N, P, S, ptr(F), ptr(Y), ptr(log_noise), ptr(llb), ptr(F_bar),
+                                         ptr(acc, f64), stream()), "ll_bwd")
+        return F_bar, None, acc.to(f32)

@@ -1,0 +1,362 @@
+"""Variational GPSA: the deep-GP ELBO hot path on B200.
+
+Public surface of reference gpsa/models/vgpsa.py (constructor :15-34, forward :212, loss_fn :491)
+with the arithmetic moved into the CUDA library behind include/gpsa_b200.h.  The reference's
+documented quirks are reproduced on purpose; each is marked below.
+"""
+import os
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+import torch.nn as nn
+from sklearn.cluster import KMeans
+
+from .gpsa import GPSA
+from .. import _ops
+from ..util.util import matern12_kernel, rbf_kernel
+
+_DEBUG_CHECKS = os.environ.get("GPSA_B200_CHECK", "0") == "1"
+
+
+def _kernel_kind(fn):
+    """The model receives kernel CALLABLES (reference :25-26); the fused path recognises the two it
+    implements by identity.  Anything else is an explicit error -- there is no slow fallback."""
+    if fn is rbf_kernel:
+        return "rbf"
+    if fn is matern12_kernel:
+        return "matern12"
+    raise NotImplementedError(
+        f"kernel function {getattr(fn, '__name__', fn)!r} is not supported by the fused B200 path; "
+        "use gpsa.rbf_kernel or gpsa.matern12_kernel"
+    )
+
+
+class VariationalGPSA(GPSA):
+    def __init__(
+        self,
+        data_dict,
+        m_X_per_view,
+        m_G,
+        data_init=True,
+        minmax_init=False,
+        grid_init=False,
+        n_spatial_dims=2,
+        n_noise_variance_params=2,
+        kernel_func_warp=rbf_kernel,
+        kernel_func_data=rbf_kernel,
+        n_latent_gps=None,
+        mean_function="identity_fixed",
+        mean_penalty_param=0.0,
+        fixed_warp_kernel_variances=None,
+        fixed_warp_kernel_lengthscales=None,
+        fixed_data_kernel_lengthscales=None,
+        fixed_view_idx=None,
+    ):
+        # quirk 8: n_spatial_dims / n_noise_variance_params / mean_function / minmax_init are ignored
+        # (reference :35-46 hard-codes 2 / 2 / the default identity mean)
+        super().__init__(
+            data_dict,
+            data_init=True,
+            n_spatial_dims=2,
+            n_noise_variance_params=2,
+            kernel_func_warp=kernel_func_warp,
+            kernel_func_data=kernel_func_data,
+            mean_penalty_param=mean_penalty_param,
+            fixed_warp_kernel_variances=fixed_warp_kernel_variances,
+            fixed_warp_kernel_lengthscales=fixed_warp_kernel_lengthscales,
+            fixed_data_kernel_lengthscales=fixed_data_kernel_lengthscales,
+        )
+        self._kind_warp = _kernel_kind(kernel_func_warp)
+        self._kind_data = _kernel_kind(kernel_func_data)
+        self.m_X_per_view = m_X_per_view
+        self.m_G = m_G
+        self.n_latent_gps = n_latent_gps
+        self.n_latent_outputs = {}
+        for mod in self.modality_names:
+            # quirk 8: n_latent_gps must be a dict; the default None raises TypeError here like :54
+            k = self.n_latent_gps[mod]
+            self.n_latent_outputs[mod] = k if k is not None else self.Ps[mod]
+        self.fixed_view_idx = fixed_view_idx
+        V, D = self.n_views, self.n_spatial_dims
+
+        if data_init:  # reference :61-92
+            Xtilde = torch.zeros([V, self.m_X_per_view, D])
+            for vv in range(V):
+                xs = [data_dict[mod]["spatial_coords"][self.view_idx[mod][vv], :] for mod in self.modality_names]
+                curr_X = torch.cat(xs, dim=0)
+                km = KMeans(n_clusters=self.m_X_per_view)
+                km.fit(curr_X.detach().cpu().numpy())
+                Xtilde[vv] = torch.tensor(km.cluster_centers_)
+            self.Xtilde = nn.Parameter(Xtilde.clone())
+            # the reference draws (and discards) a random subset here (:81-85); the draw is kept so that
+            # seeded construction consumes the numpy RNG identically -- including its ValueError when
+            # m_G exceeds the size of the last view
+            np.random.choice(np.arange(curr_X.shape[0]), size=self.m_G, replace=False)
+            all_X = torch.cat([data_dict[mod]["spatial_coords"] for mod in self.modality_names])
+            km = KMeans(n_clusters=self.m_G)
+            km.fit(all_X.detach().cpu().numpy())
+            self.Gtilde = nn.Parameter(torch.tensor(km.cluster_centers_))
+        elif grid_init:  # reference :94-121 (2-D only)
+            if D == 2:
+                coords = data_dict[self.modality_names[0]]["spatial_coords"].cpu().numpy()
+                (xlow, ylow), (xhigh, yhigh) = coords.min(0), coords.max(0)
+                numticks = np.ceil(np.sqrt(self.m_G)).astype(int)
+                self.m_G = numticks**2
+                self.m_X_per_view = numticks**2
+                X1, X2 = np.meshgrid(np.linspace(xlow, xhigh, num=numticks), np.linspace(ylow, yhigh, num=numticks))
+                grid = np.vstack([X1.ravel(), X2.ravel()]).T
+                Xt = torch.zeros([V, grid.shape[0], D])
+                for vv in range(V):
+                    Xt[vv] = torch.tensor(grid)
+                self.Xtilde = nn.Parameter(Xt.clone())
+                self.Gtilde = nn.Parameter(torch.tensor(grid).float())
+        else:  # reference :123-128
+            self.Xtilde = nn.Parameter(torch.randn([V, self.m_X_per_view, D]))
+            self.Gtilde = nn.Parameter(torch.randn([self.m_G, D]))
+
+        M_X, M_G = int(self.m_X_per_view), int(self.m_G)
+        # variational covariance square roots; slot j*V + v (reference :131-143)
+        Osq_G = torch.zeros([V * D, M_X, M_X])
+        for vv in range(V):
+            for jj in range(D):
+                Osq_G[jj * V + vv] = 0.1 * torch.randn(size=[M_X, M_X])
+        self.Omega_sqt_G_list = nn.Parameter(Osq_G)
+
+        self.Omega_sqt_F_dict = nn.ParameterDict()
+        for mod in self.modality_names:  # reference :145-153
+            L = self.n_latent_outputs[mod]
+            curr = torch.zeros([L, M_G, M_G])
+            for jj in range(L):
+                curr[jj] = 0.1 * torch.randn(size=[M_G, M_G])
+            self.Omega_sqt_F_dict[mod] = nn.Parameter(curr)
+
+        # variational means (reference :156-164)
+        self.delta_G_list = nn.Parameter(self.Xtilde.detach().clone())
+        self.delta_F_dict = nn.ParameterDict()
+        for mod in self.modality_names:
+            self.delta_F_dict[mod] = nn.Parameter(torch.randn(size=[M_G, self.n_latent_outputs[mod]]))
+
+        # LMC loadings (reference :167-172)
+        self.W_dict = nn.ParameterDict()
+        for mod in self.modality_names:
+            if self.n_latent_gps[mod] is not None:
+                self.W_dict[mod] = nn.Parameter(torch.randn([self.n_latent_gps[mod], self.Ps[mod]]))
+
+        scale = torch.ones(V, 1, 1)
+        for vv in range(V):
+            if self._is_fixed(vv):
+                scale[vv] = 100.0  # reference :235
+        self.register_buffer("_mu_z_scale", scale, persistent=False)
+        kl_mask = torch.zeros(V * D)
+        self.register_buffer("_kl_mask", kl_mask, persistent=False)
+        self._idx_cache = {}
+        self._kl = None
+
+    # ----------------------------------------------------------------------------------------------
+    def _is_fixed(self, vv):
+        f = self.fixed_view_idx  # reference :230-234
+        if f is None:
+            return False
+        return (vv in f) if isinstance(f, Iterable) else (f == vv)
+
+    def _device_index(self, idx, device):
+        """view_idx entries are numpy index arrays; the reference re-uploads them on every indexing
+        op (:268-271,:291,:344,:351).  Here each is uploaded once and cached; contiguous ranges
+        (what create_view_idx_dict produces) become slices."""
+        key = (id(idx), str(device))
+        hit = self._idx_cache.get(key)
+        if hit is not None and hit[0] is idx:
+            return hit[1]
+        arr = np.asarray(idx)
+        if arr.size > 0 and arr.ndim == 1 and np.array_equal(arr, np.arange(arr[0], arr[0] + arr.size)):
+            val = slice(int(arr[0]), int(arr[0]) + int(arr.size))
+        elif arr.size == 0:
+            val = slice(0, 0)
+        else:
+            val = torch.as_tensor(arr, dtype=torch.long, device=device)
+        self._idx_cache[key] = (idx, val)
+        return val
+
+    def get_Omega_from_Omega_sqt(self, Omega_sqt):
+        """Omega_sqt Omega_sqt^T + 1e-5 I (reference :206-210)."""
+        Omega, _, _, _ = _ops.omega_prepare(Omega_sqt.detach().contiguous())
+        return Omega
+
+    # ----------------------------------------------------------------------------------------------
+    def forward(self, X_spatial, view_idx, Ns, S=1, prediction_mode=False, G_test=None, _eps=None):
+        """Same contract as reference gpsa/models/vgpsa.py:212-489.
+
+        Returns (G_means, G_samples, F_latent_samples, F_observed_samples) -- plus the two *_test
+        dicts when G_test is given -- each a {modality: Tensor} dict.  `_eps` (tests only) injects
+        the noise: {"G": {v: [S,n_v,D]}, "F": {mod: [S,N,L]}, "F_test": {mod: [...]}}; without it the
+        noise is drawn with torch in exactly the reference's call order.
+        """
+        if prediction_mode:
+            self.eval()
+        dev = self.Xtilde.device
+        if dev.type != "cuda":
+            raise RuntimeError("VariationalGPSA.forward needs the model on a CUDA device: gpsa_b200 has no CPU path")
+        V, D, mods = self.n_views, self.n_spatial_dims, self.modality_names
+        S = int(S)
+
+        self.noise_variance_pos = torch.exp(self.noise_variance) + self.diagonal_offset  # reference :217
+        self.mu_z_G = self.Xtilde * self._mu_z_scale  # identity mean; x100 on fixed views (:219-235)
+
+        # ---- gather each view's coordinates over the modalities (reference :284-294)
+        free, X_views, sizes = [], {}, {}
+        for vv in range(V):
+            if self._is_fixed(vv):
+                continue
+            xs = [X_spatial[mod][self._device_index(view_idx[mod][vv], dev)] for mod in mods]
+            sizes[vv] = [int(x.shape[0]) for x in xs]
+            Xv = xs[0] if len(xs) == 1 else torch.cat(xs, dim=0)
+            if Xv.shape[0] == 0:  # reference :296-297
+                continue
+            free.append(vv)
+            X_views[vv] = Xv
+
+        # ---- noise, in the reference's draw order (per free view S draws, reference :346-348)
+        eps_G = {}
+        for vv in free:
+            if _eps is not None:
+                eps_G[vv] = _eps["G"][vv].to(dev, torch.float32)
+            else:
+                e = torch.empty(S, X_views[vv].shape[0], D, device=dev)
+                for ss in range(S):
+                    e[ss].normal_()
+                eps_G[vv] = e
+
+        if not self._kl_mask_ready(free):
+            self._set_kl_mask(free)
+        meta = {"kind": _ops.KINDS[self._kind_warp], "V": V, "S": S, "free": free, "with_kl": True,
+                "kl_mask": self._kl_mask}
+        flat = []
+        for vv in free:
+            flat += [X_views[vv], eps_G[vv]]
+        outs = _ops.WarpLayer.apply(
+            meta, self.Xtilde, self.delta_G_list, self.Omega_sqt_G_list, self.warp_kernel_lengthscales,
+            self.warp_kernel_variances, *flat,
+        )
+        kl_G, self.Kuu_chol_list, self.curr_Omega_tril_list, info_G = outs[:4]
+        per_view = {vv: (outs[4 + 2 * k], outs[5 + 2 * k]) for k, vv in enumerate(free)}
+
+        # ---- assemble G_means / G_samples per modality (reference :262-273, :342-351)
+        G_means, G_samples = {}, {}
+        for mm, mod in enumerate(mods):
+            N = int(Ns[mod])
+            idxs = [self._device_index(view_idx[mod][vv], dev) for vv in range(V)]
+            parts_m, parts_s = [], []
+            for vv in range(V):
+                if vv in per_view:
+                    o = sum(sizes[vv][:mm])
+                    n = sizes[vv][mm]
+                    parts_m.append(per_view[vv][0][o:o + n])
+                    parts_s.append(per_view[vv][1][:, o:o + n])
+                else:  # fixed (or empty) view: observed coordinates pass through for every sample
+                    xv = X_spatial[mod][idxs[vv]]
+                    parts_m.append(xv)
+                    parts_s.append(xv.unsqueeze(0).expand(S, -1, -1))
+            ordered = all(isinstance(i, slice) for i in idxs) and all(
+                idxs[k].stop == idxs[k + 1].start for k in range(V - 1)) and idxs[0].start == 0
+            if ordered and idxs[-1].stop == N:
+                G_means[mod] = torch.cat(parts_m, dim=0)
+                G_samples[mod] = torch.cat(parts_s, dim=1)
+            else:
+                gm = torch.full((N, D), float("nan"), device=dev)
+                gs = torch.full((S, N, D), float("nan"), device=dev)
+                for vv in range(V):
+                    gm = gm.index_put((self._as_index(idxs[vv], dev),), parts_m[vv])
+                    gs = gs.index_put((slice(None), self._as_index(idxs[vv], dev)), parts_s[vv])
+                G_means[mod], G_samples[mod] = gm, gs
+
+        # ---- data layer per modality (reference :390-435)
+        self.curr_Omega_tril_F = {}
+        self.F_latent_samples, self.F_observed_samples = {}, {}
+        if G_test is not None:
+            self.F_latent_samples_test, self.F_observed_samples_test = {}, {}
+        kl = kl_G
+        infos = [info_G]
+        kind_d = _ops.KINDS[self._kind_data]
+        for mod in mods:
+            L = self.n_latent_outputs[mod]
+            N = int(Ns[mod])
+            Osq = self.Omega_sqt_F_dict[mod]
+            pre = _ops.omega_prepare(Osq.detach().contiguous())
+            eps_F = _eps["F"][mod].to(dev, torch.float32) if _eps is not None else torch.randn(S, N, L, device=dev)
+            F_lat, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayer.apply(
+                {"kind": kind_d, "with_kl": True, "omega": pre},
+                self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod], Osq,
+                G_samples[mod], eps_F,
+            )
+            kl = kl + kl_F
+            infos.append(info_F)
+            self.curr_Omega_tril_F[mod] = Ltril_F
+            W = self.W_dict[mod] if self.n_latent_gps[mod] is not None else None
+            self.F_latent_samples[mod] = F_lat
+            self.F_observed_samples[mod] = torch.matmul(F_lat, W) if W is not None else F_lat  # LMC (:428-432)
+            if G_test is not None:  # prediction at given aligned coordinates (reference :437-477)
+                Gt = G_test[mod].to(dev, torch.float32)
+                if _eps is not None:
+                    eps_t = _eps["F_test"][mod].to(dev, torch.float32)
+                else:
+                    eps_t = torch.randn(Gt.shape[0], Gt.shape[1], L, device=dev)
+                F_t = _ops.DataLayer.apply(
+                    {"kind": kind_d, "with_kl": False, "omega": pre},
+                    self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod],
+                    Osq, Gt, eps_t,
+                )[0]
+                self.F_latent_samples_test[mod] = F_t
+                self.F_observed_samples_test[mod] = torch.matmul(F_t, W) if W is not None else F_t
+        self._kl = kl
+        self._info = infos
+        if _DEBUG_CHECKS:
+            self.check_factorisations()
+
+        if G_test is not None:
+            return (G_means, G_samples, self.F_latent_samples, self.F_observed_samples,
+                    self.F_latent_samples_test, self.F_observed_samples_test)
+        return G_means, G_samples, self.F_latent_samples, self.F_observed_samples
+
+    def check_factorisations(self):
+        """Raise if any Cholesky of the last forward met a non-positive pivot (torch.cholesky raises
+        eagerly in the reference; here the flags stay on the device until asked, so the hot path has
+        no host synchronisation).  GPSA_B200_CHECK=1 calls this after every forward."""
+        for info in self._info:
+            _ops.check_info(info, "VariationalGPSA.forward")
+
+    @staticmethod
+    def _as_index(i, dev):
+        if isinstance(i, slice):
+            return torch.arange(i.start, i.stop, device=dev)
+        return i
+
+    def _kl_mask_ready(self, free):
+        return getattr(self, "_kl_mask_free", None) == tuple(free)
+
+    def _set_kl_mask(self, free):
+        V, D = self.n_views, self.n_spatial_dims
+        m = torch.zeros(V * D)
+        for vv in free:
+            for jj in range(D):
+                m[jj * V + vv] = -0.5  # quirk 2: the KL uses slice j*V+v (reference :508)
+        self._kl_mask.copy_(m)
+        self._kl_mask_free = tuple(free)
+
+    # ----------------------------------------------------------------------------------------------
+    def loss_fn(self, data_dict, F_samples):
+        """Negative ELBO, reference gpsa/models/vgpsa.py:491-540: -LL/S-averaged + KL_G + KL_F, where the
+        KL terms are those of the most recent forward (they depend on the parameters only)."""
+        if self._kl is None:
+            raise RuntimeError("loss_fn needs a preceding forward (it reads the factors cached there)")
+        LL = 0
+        for mm, mod in enumerate(self.modality_names):
+            Y = data_dict[mod]["outputs"]
+            F = F_samples[mod]
+            idx = self.noise_variance.shape[0] - self.n_modalities + mm  # quirk 6: index -n_modalities+mm (:534)
+            LL = LL + _ops.GaussianLL.apply(F, Y.to(F.device, torch.float32), self.noise_variance[idx:idx + 1])
+        return -LL + self._kl
+
+
+if __name__ == "__main__":
+    pass

@@ -1,0 +1,232 @@
+"""Kernel-level parity (-m gpu): every C-ABI op against the oracle / a float64 torch evaluation of the
+same expression, called through the C ABI (ctypes), at odd sizes and at the large M the configs use."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from golden_io import relerr
+from oracle import gpsa_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+f32, f64, i32 = torch.float32, torch.float64, torch.int32
+
+
+@pytest.fixture(scope="module")
+def L():
+    from gpsa import _lib
+
+    assert torch.cuda.is_available()
+    return _lib
+
+
+def dev(x, dtype=f32):
+    return torch.as_tensor(x).to("cuda", dtype).contiguous()
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["rbf", "matern12"])
+@pytest.mark.parametrize("D", [1, 2, 3])
+@pytest.mark.parametrize("M,R", [(1, 1), (7, 33), (25, 300), (50, 1000), (200, 2049)])
+def test_kernel_matrix_fwd_bwd(L, kind, D, M, R):
+    import gpsa
+
+    g = torch.Generator().manual_seed(M * 1000 + R + D)
+    x1 = torch.rand(M, D, generator=g) * 10
+    x2 = torch.rand(R, D, generator=g) * 10
+    ls, var = torch.tensor([0.7]), torch.tensor([-0.3])
+    Kbar = torch.randn(M, R, generator=g)
+    fn = gpsa.rbf_kernel if kind == "rbf" else gpsa.matern12_kernel
+    a = [t.cuda().requires_grad_() for t in (x1, x2, ls, var)]
+    K = fn(a[0], a[1], a[2], a[3])
+    (K * Kbar.cuda()).sum().backward()
+    b = [t.double().requires_grad_() for t in (x1, x2, ls, var)]
+    Kr = orc.kernel_matrix(kind, b[0], b[1], b[2], b[3])
+    (Kr * Kbar.double()).sum().backward()
+    assert relerr(K.detach().cpu(), Kr.detach()) < 2e-6
+    for got, ref, name in zip(a, b, ("x1", "x2", "log_ls", "log_var")):
+        assert relerr(got.grad.cpu(), ref.grad) < 2e-5, name
+
+
+def test_kernel_matrix_batch_broadcast(L):
+    import gpsa
+
+    g = torch.Generator().manual_seed(3)
+    x1 = torch.rand(9, 2, generator=g)
+    x2 = torch.rand(4, 13, 2, generator=g)
+    ls, var = torch.tensor(0.2), torch.tensor(0.1)
+    K = gpsa.matern12_kernel(x1.cuda(), x2.cuda(), ls.cuda(), var.cuda())
+    Kr = orc.kernel_matrix("matern12", x1.double(), x2.double(), ls.double(), var.double())
+    assert K.shape == (4, 9, 13)
+    assert relerr(K.cpu(), Kr) < 2e-6
+    with pytest.raises(Exception):
+        gpsa.rbf_kernel(x1, x2, ls, var)  # CPU tensors: no fallback
+
+
+# --------------------------------------------------------------------------------------------------
+def _spd(B, M, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(B, M, M, generator=g, dtype=f64)
+    return (A @ A.transpose(1, 2) / M + 0.5 * torch.eye(M, dtype=f64)).to(dtype)
+
+
+@pytest.mark.parametrize("M", [1, 5, 31, 32, 33, 50, 64, 100, 200, 256, 512])
+@pytest.mark.parametrize("dtype", [f32, f64])
+def test_potrf_trtri(L, M, dtype):
+    """Cholesky factors compared to torch.linalg.cholesky, as north_star asks."""
+    B = 3
+    A = _spd(B, M, M, dtype)
+    ref = torch.linalg.cholesky(A.double())
+    a = A.cuda().contiguous()
+    hld = torch.empty(B, dtype=dtype, device="cuda")
+    info = torch.empty(B, dtype=i32, device="cuda")
+    sfx = "f32" if dtype == f32 else "f64"
+    rc = getattr(L.lib(), f"gpsa_potrf_batched_{sfx}")(M, B, a.data_ptr(), hld.data_ptr(), info.data_ptr(), stream())
+    assert rc == 0
+    tol = 2e-5 if dtype == f32 else 1e-12
+    assert int(info.abs().sum()) == 0
+    assert relerr(a.cpu(), ref) < tol
+    assert torch.equal(a.triu(1), torch.zeros_like(a))
+    assert relerr(hld.cpu(), torch.log(torch.diagonal(ref, dim1=1, dim2=2)).sum(1)) < tol
+    x = torch.empty_like(a)
+    rc = getattr(L.lib(), f"gpsa_trtri_batched_{sfx}")(M, B, a.data_ptr(), x.data_ptr(), stream())
+    assert rc == 0
+    assert relerr(x.cpu(), torch.linalg.inv(ref)) < (2e-4 if dtype == f32 else 1e-10)
+
+
+def test_potrf_flags_non_pd(L):
+    A = torch.eye(40, dtype=f32).repeat(2, 1, 1)
+    A[1, 17, 17] = -1.0
+    a = A.cuda()
+    info = torch.zeros(2, dtype=i32, device="cuda")
+    assert L.lib().gpsa_potrf_batched_f32(40, 2, a.data_ptr(), None, info.data_ptr(), stream()) == 0
+    assert info.cpu().tolist() == [0, 1]
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (50, 7, 33), (64, 64, 16), (130, 257, 100), (200, 1000, 200),
+                                    (25, 3, 5000)])
+def test_gemm_strided(L, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    batch = 2
+    A = torch.randn(batch, K, M, generator=g)  # stored transposed: op(A)(i,k) = A[k,i]
+    B = torch.randn(batch, K, N, generator=g)
+    Cin = torch.randn(batch, M, N, generator=g)
+    ref = 1.5 * A.double().transpose(1, 2) @ B.double() - 0.5 * Cin.double()
+    a, b, c = A.cuda(), B.cuda(), Cin.cuda().clone()
+    rc = L.lib().gpsa_gemm_f32(M, N, K, 1.5, a.data_ptr(), 1, M, K * M, b.data_ptr(), N, 1, K * N, -0.5, c.data_ptr(),
+                               N, M * N, batch, stream())
+    assert rc == 0
+    assert relerr(c.cpu(), ref) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,R,Lg", [(5, 3, 2), (25, 200, 30), (50, 1000, 5), (200, 700, 130), (33, 129, 257)])
+def test_quadform_fwd_bwd(L, M, R, Lg):
+    """q2 = a^T Omega a and both backward products against a float64 einsum."""
+    g = torch.Generator().manual_seed(M * 7 + R)
+    A = torch.randn(M, R, generator=g) * 0.3
+    Osq = torch.randn(Lg, M, M, generator=g) * 0.1
+    Om = Osq @ Osq.transpose(1, 2) + 1e-5 * torch.eye(M)
+    G = torch.randn(R, Lg, generator=g)
+    Ad = A.double().requires_grad_()
+    Omd = Om.double().requires_grad_()
+    q2r = torch.einsum("mr,pmk,kr->rp", Ad, Omd, Ad)
+    (q2r * G.double()).sum().backward()
+
+    lib = L.lib()
+    nf = L.feat_count(M)
+    a, om, gg = A.cuda(), Om.cuda().contiguous(), G.cuda()
+    W = torch.empty(nf, Lg, device="cuda")
+    q2 = torch.empty(R, Lg, device="cuda")
+    assert lib.gpsa_feat_pack(M, Lg, om.data_ptr(), W.data_ptr(), stream()) == 0
+    assert lib.gpsa_quadform_fwd_f32(M, R, Lg, a.data_ptr(), W.data_ptr(), q2.data_ptr(), stream()) == 0
+    assert relerr(q2.cpu(), q2r.detach()) < 1e-5
+    H = torch.empty(nf, Lg, device="cuda")
+    Obar = torch.empty(Lg, M, M, device="cuda")
+    assert lib.gpsa_quadform_bwd_omega_f32(M, R, Lg, a.data_ptr(), gg.data_ptr(), H.data_ptr(), stream()) == 0
+    assert lib.gpsa_feat_unpack(M, Lg, H.data_ptr(), None, 0.0, None, Obar.data_ptr(), stream()) == 0
+    assert relerr(Obar.cpu(), Omd.grad) < 1e-5
+    Abar = torch.zeros(M, R, device="cuda")
+    assert lib.gpsa_quadform_bwd_alpha_f32(M, R, Lg, a.data_ptr(), gg.data_ptr(), W.data_ptr(), Abar.data_ptr(),
+                                           stream()) == 0
+    assert relerr(Abar.cpu(), Ad.grad) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,B", [(12, 4), (50, 6), (200, 3)])
+def test_omega_prepare_and_grad(L, M, B):
+    from gpsa import _ops
+
+    g = torch.Generator().manual_seed(M)
+    Osq = (torch.randn(B, M, M, generator=g) * 0.1)
+    Obar_in = torch.randn(B, M, M, generator=g)
+    Obar_in = Obar_in + Obar_in.transpose(1, 2)
+    coef = torch.tensor([-0.5, 0.0, -0.25, -0.5, 0.0, -0.5][:B])
+    od = Osq.double().requires_grad_()
+    Omr = orc.omega_from_sqt(od)
+    Lr = torch.linalg.cholesky(Omr)
+    # loss whose gradient wrt Omega is Obar_in + coef * Omega^-1:  <Obar_in, Omega> + 2 coef * half_logdet
+    hld_r = torch.log(torch.diagonal(Lr, dim1=1, dim2=2)).sum(1)
+    ((Obar_in.double() * Omr).sum() + (2 * coef.double() * hld_r).sum()).backward()
+
+    Omega, Ltril, hld, info = _ops.omega_prepare(Osq.cuda())
+    assert int(info.abs().sum()) == 0
+    assert relerr(Omega.cpu(), Omr.detach()) < 1e-5
+    assert relerr(Ltril.cpu(), Lr.detach()) < 1e-3
+    assert relerr(hld.cpu(), hld_r.detach()) < 1e-4
+    out = _ops.omega_grad(Osq.cuda(), Ltril, Obar_in.cuda().contiguous(), coef.cuda())
+    assert relerr(out.cpu(), od.grad) < 2e-3
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern12"])
+@pytest.mark.parametrize("M,D", [(25, 2), (200, 2), (256, 3)])
+def test_prior_prepare(L, kind, M, D):
+    g = torch.Generator().manual_seed(M + D)
+    Z = torch.rand(M, D, generator=g) * 10
+    ls, var = torch.tensor([math.log(10.0)]), torch.tensor([0.0])  # the reference's ill-conditioned default
+    Kd = orc.kernel_matrix(kind, Z.double(), Z.double(), ls.double(), var.double()) + 1e-5 * torch.eye(M, dtype=f64)
+    Lr = torch.linalg.cholesky(Kd)
+    z, l_, v_ = Z.cuda(), ls.cuda(), var.cuda()
+    Lk, Kinv = torch.empty(M, M, device="cuda"), torch.empty(M, M, device="cuda")
+    hld = torch.zeros(1, dtype=f64, device="cuda")
+    info = torch.zeros(1, dtype=i32, device="cuda")
+    ws = torch.empty(3 * M * M, dtype=f64, device="cuda")
+    rc = L.lib().gpsa_prior_prepare(orc_kind(kind), D, M, z.data_ptr(), l_.data_ptr(), v_.data_ptr(), Lk.data_ptr(),
+                                    Kinv.data_ptr(), hld.data_ptr(), info.data_ptr(), ws.data_ptr(), stream())
+    assert rc == 0 and int(info) == 0
+    assert relerr(Lk.cpu(), Lr) < 1e-6  # fp64 factorisation rounded once to fp32
+    assert relerr(Kinv.cpu(), torch.linalg.inv(Kd)) < 1e-6
+    assert abs(float(hld) - float(torch.log(torch.diagonal(Lr)).sum())) < 1e-8 * M
+
+
+def orc_kind(kind):
+    return {"rbf": 0, "matern12": 1}[kind]
+
+
+# --------------------------------------------------------------------------------------------------
+def test_gaussian_ll(L):
+    from gpsa import _ops
+
+    g = torch.Generator().manual_seed(5)
+    S, N, P = 3, 37, 5
+    F = torch.randn(S, N, P, generator=g)
+    Y = torch.randn(N, P, generator=g)
+    ln = torch.tensor([-0.4])
+    Fd, lnd = F.double().requires_grad_(), ln.double().requires_grad_()
+    sigma = torch.exp(lnd) + 1e-5
+    ref = torch.distributions.Normal(Fd, sigma).log_prob(Y.double()).sum() / S
+    ref.backward()
+    Fc, lc = F.cuda().requires_grad_(), ln.cuda().requires_grad_()
+    ll = _ops.GaussianLL.apply(Fc, Y.cuda(), lc)
+    (-ll).backward()
+    assert abs(float(ll) - float(ref)) < 1e-5 * abs(float(ref))
+    assert relerr(-Fc.grad.cpu(), Fd.grad) < 1e-5
+    assert relerr(-lc.grad.cpu(), lnd.grad) < 1e-5
