@@ -61,22 +61,23 @@ int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, l
                   cudaStream_t stream);
 
 /* ---- prior covariance K_uu: fp64 factorisation of k(Z,Z) + 1e-5 I -----------------------------
- * Outputs the fp32 Cholesky factor Lk [M,M] (the reference's cached Kuu_chol_*), K^-1 [M,M] and
- * half_logdet (fp64 scalar, sum log diag).  ws64: 3*M*M doubles.  info: 1 int.
- * Replaces gpsa/models/vgpsa.py:314-321 and :390-394. */
+ * Outputs the fp32 Cholesky factor Lk [M,M] (the reference's cached Kuu_chol_*), K^-1 in fp32
+ * (Kinv, may be NULL) and fp64 (Kinv64) and half_logdet (fp64 scalar, sum log diag).
+ * ws64: 2*M*M doubles.  info: 1 int.  Replaces gpsa/models/vgpsa.py:314-321 and :390-394. */
 int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_ls, const float* log_var, float* Lk,
-                       float* Kinv, double* half_logdet, int* info, double* ws64, cudaStream_t stream);
+                       float* Kinv, double* Kinv64, double* half_logdet, int* info, double* ws64,
+                       cudaStream_t stream);
 
 /* ---- variational covariances Omega = Omega_sqt Omega_sqt^T + 1e-5 I, batched ------------------
  * Replaces get_Omega_from_Omega_sqt + torch.cholesky (gpsa/models/vgpsa.py:206-210, :255-257, :410-412).
  * Omega, Ltril: [B,M,M]; half_logdet [B]; info [B]. */
-int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, float* half_logdet, int* info,
-                       cudaStream_t stream);
-/* Backward: Osq_bar = 2 (Obar + coef[b] * Omega^-1) Osq.  Obar [B,M,M] is modified in place;
- * coef: device [B] (the -1/2 dKL factor of the log-det term, 0 for slices without a KL term);
- * Linv: [B,M,M] scratch. */
-int gpsa_omega_grad(int M, int B, const float* Osq, const float* Ltril, float* Obar, const float* coef, float* Linv,
-                    float* Osq_bar, cudaStream_t stream);
+int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, double* L64, double* half_logdet,
+                       int* info, cudaStream_t stream);
+/* Backward: Osq_bar = 2 (Obar + coef[b] * Omega^-1) Osq.  Obar [B,M,M] symmetric; coef: device [B]
+ * (the -1/2 dKL factor of the log-det term, 0 for slices without a KL term; NULL = no such term);
+ * L64: the fp64 factor from gpsa_omega_prepare; Linv64, Y64: [B,M,M] fp64 scratch. */
+int gpsa_omega_grad(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
+                    double* Linv64, double* Y64, float* Osq_bar, cudaStream_t stream);
 
 /* ---- implicit-feature quadratic form (the hot contraction) ------------------------------------
  * q2[r,p] = a_r^T Omega_p a_r with a_r = A[:,r];  replaces the [S,L,N,M] broadcast bmm at
@@ -105,23 +106,24 @@ typedef struct {
   const float* log_ls;    /* &warp_kernel_lengthscales[v] */
   const float* log_var;   /* &warp_kernel_variances[v]    */
   const float* Omega_G;   /* [V*D,M,M] from gpsa_omega_prepare */
-  const float* hld_Omega; /* [V*D] half log-dets of Omega_G */
+  const double* hld_Omega; /* [V*D] half log-dets of Omega_G */
   const float* X;         /* [n,D] observed coordinates */
   const float* eps;       /* [S,n,D] standard-normal draws */
   float* Lk;              /* out [M,M]  Kuu_chol_list[v] */
-  float* Kinv;            /* out [M,M] */
+  float* Kinv;            /* out [M,M] fp32 copy of K^-1 (may be NULL) */
+  double* Kinv64;         /* out [M,M] fp64 K^-1 (saved) */
   double* hld_K;          /* out fp64 scalar */
   int* info;              /* out 1 int */
-  float* A;               /* out [M,n]  K^-1 K_uf   (saved) */
-  float* B;               /* out [M,n]  K_uf        (saved) */
-  float* T;               /* out [D,M,n] Omega_{vD+j} A (saved) */
-  float* Ke;              /* out [D,M]  K^-1 (Z_j - dlt_j)  (saved) */
+  double* A;              /* out fp64 [M,n]  K^-1 K_uf   (saved) */
+  double* B;              /* out fp64 [M,n]  K_uf        (saved) */
+  double* T;              /* out fp64 [D,M,n] Omega_{vD+j} A (saved) */
+  double* Ke;             /* out fp64 [D,M]  K^-1 (Z_j - dlt_j)  (saved) */
   float* var;             /* out [n,D] marginal "variance" (saved) */
   float* Gmean;           /* out [n,D] */
   float* Gs;              /* out: sample s at Gs + s*gs_stride, [n,D] each */
   long gs_stride;
-  double* kl_acc;         /* fp64 scalar, ADDED to */
-  double* ws64;           /* 3*M*M doubles */
+  double* kl_acc;         /* fp64 scalar, ADDED to (may be NULL) */
+  double* ws64;           /* 2*M*M doubles */
 } gpsa_warp_fwd_args;
 int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t stream);
 
@@ -129,7 +131,7 @@ typedef struct {
   int kind, D, M, V, v, S;
   long n;
   const float *Z, *dlt, *log_ls, *log_var, *Omega_G, *X, *eps;
-  const float *Kinv, *A, *B, *T, *Ke;
+  const double *Kinv64, *A, *B, *T, *Ke;   /* fp64, saved by the forward */
   const float* Gs_bar;    /* sample s at Gs_bar + s*gs_stride, [n,D]; may be NULL */
   long gs_stride;
   const float* Gm_bar;    /* [n,D], may be NULL */
@@ -140,8 +142,8 @@ typedef struct {
   float* Obar_G;          /* [V*D,M,M] ADDED to (slices v*D+j and j*V+v) */
   /* scratch */
   float *mubar, *varbar, *q1bar; /* [n,D], [n,D], [n] */
-  float *Abar, *C, *AS;          /* [M,n], [M,n], [D,M,n] */
-  float *Kbar, *Som, *T1;        /* [M,M] each */
+  double *Abar, *C, *AS;         /* fp64 [M,n], [M,n], [D,M,n] */
+  double* ws64;                  /* 3*M*M doubles */
 } gpsa_warp_bwd_args;
 int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t stream);
 
@@ -155,20 +157,21 @@ typedef struct {
   const float *log_ls, *log_var;
   const float* dlt;       /* delta_F [M,L] */
   const float* Omega;     /* [L,M,M] from gpsa_omega_prepare */
-  const float* hld_Omega; /* [L] */
+  const double* hld_Omega; /* [L] */
   const float* G;         /* G_samples flattened [R,D] */
   const float* eps;       /* [R,L] */
-  float *Lk, *Kinv;       /* out [M,M] each */
+  float *Lk, *Kinv;       /* out [M,M] each (fp32) */
+  double* Kinv64;         /* out [M,M] fp64 (saved) */
   double* hld_K;
   int* info;
   float *A, *B;           /* out [M,R] (saved) */
-  float* q1;              /* out [R] */
+  float* kq;              /* out [R]  K_ff - a^T K a */
   float* W;               /* out [gpsa_feat_count(M), L] (saved) */
-  float* KD;              /* out [M,L] K^-1 delta (saved) */
+  double* KD;             /* out fp64 [M,L] K^-1 delta (saved) */
   float* F;               /* out [R,L] latent samples */
   float* var;             /* out [R,L] marginal variances (saved) */
   double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
-  double* ws64;           /* 3*M*M doubles */
+  double* ws64;           /* 2*M*M doubles */
   int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 */
 } gpsa_data_fwd_args;
 int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
@@ -177,7 +180,11 @@ typedef struct {
   int kind, D, M, L;
   long R;
   const float *Gt, *log_ls, *log_var, *dlt, *Omega, *G, *eps;
-  const float *Kinv, *A, *B, *W, *KD, *var;
+  const float* Kinv;
+  const double* Kinv64;
+  const float *A, *B, *W;
+  const double* KD;
+  const float* var;
   const float* F_bar;     /* [R,L] */
   const float* kl_bar;    /* device scalar */
   float* G_bar;           /* out [R,D] */
@@ -190,7 +197,7 @@ typedef struct {
   float* q1bar;           /* [R] */
   float *Abar, *C;        /* [M,R] each */
   float* H;               /* [gpsa_feat_count(M), L] */
-  float *Kbar, *Som, *T1; /* [M,M] each */
+  double* ws64;           /* 3*M*M doubles */
   int engine;
 } gpsa_data_bwd_args;
 int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t stream);

@@ -213,13 +213,10 @@ __global__ void __launch_bounds__(256) trtri_kernel(int M, const T* L, T* X, lon
 template <typename T>
 int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t st) {
   const size_t smem = (size_t)(NB * LDP + (size_t)M * LDP) * sizeof(T);
-  if (smem > 227 * 1024) return GPSA_ERR_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(potrf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return GPSA_ERR_CUDA;
-    attr_done = true;
-  }
+  if (smem > 220 * 1024) return GPSA_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(potrf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return GPSA_ERR_CUDA;
   potrf_kernel<T><<<batch, 256, smem, st>>>(M, A, (long)M * M, half_logdet, info);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
@@ -228,13 +225,10 @@ int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t
 template <typename T>
 int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
   const size_t smem = (size_t)(NB * LDP + (size_t)M * NB) * sizeof(T);
-  if (smem > 227 * 1024) return GPSA_ERR_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(trtri_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return GPSA_ERR_CUDA;
-    attr_done = true;
-  }
+  if (smem > 220 * 1024) return GPSA_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(trtri_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return GPSA_ERR_CUDA;
   trtri_kernel<T><<<batch, 256, smem, st>>>(M, L, X, (long)M * M);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;

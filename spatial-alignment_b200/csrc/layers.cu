@@ -2,53 +2,73 @@
 // warp layer (one view), the data layer (one modality) and the Gaussian log-likelihood, each as
 // an explicit forward and an explicit analytic backward (no autograd tape below this boundary).
 // Every function only enqueues kernels on the caller's stream.
+//
+// Precision policy.  Data, parameters and every R- or R x L-sized tensor are fp32 like the
+// reference.  Everything M x M (factorisations, inverses, the K-bar assembly) and every product
+// that applies K^-1 accumulates in fp64: with the reference's default RBF initialisation
+// cond(K_uu) ~ 1e7 ~ 1/eps_fp32, and an explicit fp32 inverse would not be backward stable the way
+// the reference's triangular solves are.  That work is O(M^3 + M^2 R), < 2 % of the iteration.
 #include "gemm.cuh"
 #include "gpsa_b200.h"
 
 #include <math.h>
 
-#define TRY(x)                   \
-  do {                           \
-    int rc__ = (x);              \
+#define TRY(x)                        \
+  do {                                \
+    int rc__ = (x);                   \
     if (rc__ != GPSA_OK) return rc__; \
   } while (0)
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// GEMM conveniences (row-major, fp32)
+// GEMM conveniences (row-major)
 // ------------------------------------------------------------------------------------------------
-int pick_split(int M, int N, long K, int batch) {
-  const int t = (M >= 96 && N >= 96) ? 128 : 64;
-  const long tiles = (long)gpsa_cdiv(M, t) * gpsa_cdiv(N, t) * batch;
+int pick_split(int M, int N, long K, int batch, int tile) {
+  const long tiles = (long)gpsa_cdiv(M, tile) * gpsa_cdiv(N, tile) * batch;
   if (tiles >= 296 || K < 4096) return 1;
   long s = (592 + tiles - 1) / tiles;
   const long smax = K / 1024;
   if (s > smax) s = smax;
   return s < 1 ? 1 : (int)s;
 }
+template <typename T>
+int tile_of(int M, int N) { return (sizeof(T) == 4 && M >= 96 && N >= 96) ? 128 : 64; }
 
-// C = alpha*A*B + beta*C with A [M,K] (lda), B [K,N] (ldb)
-int gemm_nn(cudaStream_t st, int M, int N, long K, double alpha, const float* A, long lda, const float* B, long ldb,
-            double beta, float* C, long ldc, const float* alpha_dev = nullptr) {
-  return gemm_strided<float, float, float, float>(st, M, N, K, alpha, A, lda, 1, 0, B, ldb, 1, 0, beta, C, ldc, 0, 1,
-                                                  1, 0.0, 0, alpha_dev, 0);
+// C = alpha*A*B + beta*C with A [M,K] (lda), B [K,N] (ldb).  T = accumulation type.
+template <typename T = float, typename TA = float, typename TB = float, typename TC = float>
+int gemm_nn(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long lda, const TB* B, long ldb,
+            double beta, TC* C, long ldc, const float* alpha_dev = nullptr) {
+  return gemm_strided<T, TA, TB, TC>(st, M, N, K, alpha, A, lda, 1, 0, B, ldb, 1, 0, beta, C, ldc, 0, 1, 1, 0.0, 0,
+                                     alpha_dev, 0);
 }
-// C = alpha*A*B^T + beta*C with A [M,K] (lda), B [N,K] (ldb).  beta must be 0 or 1; large K is split.
-int gemm_nt(cudaStream_t st, int M, int N, long K, double alpha, const float* A, long lda, const float* B, long ldb,
-            double beta, float* C, long ldc, const float* alpha_dev = nullptr) {
-  const int split = pick_split(M, N, K, 1);
+// C = alpha*A*B^T + beta*C with A [M,K] (lda), B [N,K] (ldb).  beta must be 0 or 1; a long K is split.
+template <typename T = float, typename TA = float, typename TB = float, typename TC = float>
+int gemm_nt(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long lda, const TB* B, long ldb,
+            double beta, TC* C, long ldc, const float* alpha_dev = nullptr) {
+  const int split = pick_split(M, N, K, 1, tile_of<T>(M, N));
   if (split > 1 && beta == 0.0) {
     if (ldc != N) return GPSA_ERR_ARG;
-    if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st) != cudaSuccess) return GPSA_ERR_CUDA;
+    if (cudaMemsetAsync(C, 0, sizeof(TC) * (size_t)M * N, st) != cudaSuccess) return GPSA_ERR_CUDA;
   }
-  return gemm_strided<float, float, float, float>(st, M, N, K, alpha, A, lda, 1, 0, B, 1, ldb, 0, beta, C, ldc, 0, 1,
-                                                  split, 0.0, 0, alpha_dev, 0);
+  return gemm_strided<T, TA, TB, TC>(st, M, N, K, alpha, A, lda, 1, 0, B, 1, ldb, 0, beta, C, ldc, 0, 1, split, 0.0,
+                                     0, alpha_dev, 0);
+}
+
+int grid_for(long n, int per_block = 256, int cap = 148 * 16) {
+  const long b = (n + per_block - 1) / per_block;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
 // ------------------------------------------------------------------------------------------------
 // prior covariance in fp64
 // ------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double kval64(double r2, double inv_ls, double var) {
+  if (KIND == GPSA_KIND_RBF) return var * exp(-0.5 * r2 * inv_ls * inv_ls);
+  return var * exp(-0.5 * sqrt(r2 + 1e-10) * inv_ls);
+}
+
 template <int D, int KIND>
 __global__ void prior_kuu_kernel(int M, const float* __restrict__ Z, const float* __restrict__ log_ls,
                                  const float* __restrict__ log_var, double* __restrict__ K) {
@@ -62,66 +82,200 @@ __global__ void prior_kuu_kernel(int M, const float* __restrict__ Z, const float
     const double t = (double)Z[i * D + d] - (double)Z[j * D + d];
     r2 += t * t;
   }
-  double k;
-  if (KIND == GPSA_KIND_RBF) k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
-  else k = var * exp(-0.5 * sqrt(r2 + 1e-10) * inv_ls);
+  double k = kval64<KIND>(r2, inv_ls, var);
   if (i == j) k += 1e-5;
   K[idx] = k;
 }
 
-__global__ void cvt_d2f_kernel(long n, const double* __restrict__ src, float* __restrict__ dst) {
+// Gradient of sum(Kbar o k(Z,Z)) with Kbar in fp64 (both argument roles of Z): one warp per row i.
+//   Zbar_i = -sum_j (Kbar_ij + Kbar_ji) coef_ij (z_i - z_j);  hyp += sum_ij Kbar_ij (dK/dlog_ls, K)
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) prior_bwd_kernel(int M, const float* __restrict__ Z,
+                                                        const float* __restrict__ log_ls,
+                                                        const float* __restrict__ log_var,
+                                                        const double* __restrict__ Kbar, double* acc_Z,
+                                                        double* acc_hyp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  const double inv_ls = exp(-(double)log_ls[0]), var = exp((double)log_var[0]);
+  double g[D], gls = 0, gvar = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) g[d] = 0;
+  if (i < M) {
+    double zi[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) zi[d] = (double)Z[i * D + d];
+    for (int j = lane; j < M; j += 32) {
+      double dd[D], r2 = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        dd[d] = zi[d] - (double)Z[j * D + d];
+        r2 += dd[d] * dd[d];
+      }
+      double k, coef, dls;
+      if (KIND == GPSA_KIND_RBF) {
+        k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
+        coef = k * inv_ls * inv_ls;
+        dls = coef * r2;
+      } else {
+        const double t = sqrt(r2 + 1e-10);
+        k = var * exp(-0.5 * t * inv_ls);
+        coef = 0.5 * k * inv_ls / t;
+        dls = 0.5 * k * t * inv_ls;
+      }
+      const double kij = Kbar[(long)i * M + j], kji = Kbar[(long)j * M + i];
+      const double w = -(kij + kji) * coef;
+#pragma unroll
+      for (int d = 0; d < D; ++d) g[d] += w * dd[d];
+      gls += kij * dls;
+      gvar += kij * k;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) g[d] = warp_sum(g[d]);
+  gls = warp_sum(gls);
+  gvar = warp_sum(gvar);
+  if (lane == 0 && i < M) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) atomicAdd(&acc_Z[i * D + d], g[d]);
+    atomicAdd(&acc_hyp[0], gls);
+    atomicAdd(&acc_hyp[1], gvar);
+  }
+}
+
+// K_uf in fp64 for the warp layer: B[m,r] = k(Z[m], X[r]).  The warp GP's interpolation weights
+// A = K^-1 B reach 1e3 with the reference's default lengthscale, so an fp32-rounded B would already
+// cost 1e-3 in the marginal variance; the layer is O(V M^2 n) and is kept in fp64 end to end.
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) kuf64_kernel(int M, long n, const float* __restrict__ Z,
+                                                    const float* __restrict__ X, const float* __restrict__ log_ls,
+                                                    const float* __restrict__ log_var, double* __restrict__ B) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double inv_ls = exp(-(double)log_ls[0]), var = exp((double)log_var[0]);
+  double x[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) x[d] = (double)X[r * D + d];
+  for (int m = blockIdx.y; m < M; m += gridDim.y) {
+    double r2 = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double t = (double)Z[m * D + d] - x[d];
+      r2 += t * t;
+    }
+    B[(long)m * n + r] = kval64<KIND>(r2, inv_ls, var);
+  }
+}
+
+// Gradient of sum(Bbar o k(Z, X)) w.r.t. Z and the two hyper-parameters, fp64: one warp per row m.
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) kuf64_bwd_kernel(int M, long n, long chunk, const float* __restrict__ Z,
+                                                        const float* __restrict__ X,
+                                                        const float* __restrict__ log_ls,
+                                                        const float* __restrict__ log_var,
+                                                        const double* __restrict__ Bbar, double* acc_Z,
+                                                        double* acc_hyp) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const long r0 = (long)blockIdx.y * chunk, r1 = (r0 + chunk < n) ? r0 + chunk : n;
+  const double inv_ls = exp(-(double)log_ls[0]), var = exp((double)log_var[0]);
+  double z[D], g[D], gls = 0, gvar = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) { z[d] = (double)Z[m * D + d]; g[d] = 0; }
+  for (long r = r0 + lane; r < r1; r += 32) {
+    double dd[D], r2 = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      dd[d] = z[d] - (double)X[r * D + d];
+      r2 += dd[d] * dd[d];
+    }
+    double k, coef, dls;
+    if (KIND == GPSA_KIND_RBF) {
+      k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
+      coef = k * inv_ls * inv_ls;
+      dls = coef * r2;
+    } else {
+      const double t = sqrt(r2 + 1e-10);
+      k = var * exp(-0.5 * t * inv_ls);
+      coef = 0.5 * k * inv_ls / t;
+      dls = 0.5 * k * t * inv_ls;
+    }
+    const double kb = Bbar[(long)m * n + r];
+    const double w = -kb * coef;
+#pragma unroll
+    for (int d = 0; d < D; ++d) g[d] += w * dd[d];
+    gls += kb * dls;
+    gvar += kb * k;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) g[d] = warp_sum(g[d]);
+  gls = warp_sum(gls);
+  gvar = warp_sum(gvar);
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) atomicAdd(&acc_Z[m * D + d], g[d]);
+    atomicAdd(&acc_hyp[0], gls);
+    atomicAdd(&acc_hyp[1], gvar);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cvt_kernel(long n, const TS* __restrict__ src, TD* __restrict__ dst) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    dst[i] = (float)src[i];
+    dst[i] = (TD)src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
 // small elementwise / reduction kernels
 // ------------------------------------------------------------------------------------------------
 // y += alpha * (*alpha_dev) * x
-__global__ void axpy_dev_kernel(long n, float alpha, const float* __restrict__ alpha_dev, const float* __restrict__ x,
-                                float* __restrict__ y) {
-  const float a = alpha * (alpha_dev ? alpha_dev[0] : 1.f);
+template <typename TX, typename TY>
+__global__ void axpy_dev_kernel(long n, double alpha, const float* __restrict__ alpha_dev, const TX* __restrict__ x,
+                                TY* __restrict__ y) {
+  const double a = alpha * (alpha_dev ? (double)alpha_dev[0] : 1.0);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    y[i] = fmaf(a, x[i], y[i]);
+    y[i] = (TY)((double)y[i] + a * (double)x[i]);
 }
-int axpy_dev(cudaStream_t st, long n, float alpha, const float* alpha_dev, const float* x, float* y) {
-  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  axpy_dev_kernel<<<blocks, 256, 0, st>>>(n, alpha, alpha_dev, x, y);
+template <typename TX, typename TY>
+int axpy_dev(cudaStream_t st, long n, double alpha, const float* alpha_dev, const TX* x, TY* y) {
+  axpy_dev_kernel<TX, TY><<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(n, alpha, alpha_dev, x, y);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
 
-// S[e] = sum_{b<count} X[b*stride + e]
-__global__ void sum_batch_kernel(long n, int count, long stride, const float* __restrict__ X, float* __restrict__ S) {
+// S[e] = sum_{b<count} X[b*stride + e]   (fp64 accumulate)
+__global__ void sum_batch_kernel(long n, int count, long stride, const float* __restrict__ X, double* __restrict__ S) {
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < count; ++b) s += X[(long)b * stride + e];
+  double s = 0.0;
+  for (int b = 0; b < count; ++b) s += (double)X[(long)b * stride + e];
   S[e] = s;
 }
 
-// q1[r] = sum_m A[m,r] B[m,r]
-__global__ void q1_kernel(int M, long R, const float* __restrict__ A, const float* __restrict__ B,
-                          float* __restrict__ q1) {
+// kq[r] = sigma2 - sum_m A[m,r] B[m,r]   (K_ff - a^T K a, fp64 accumulate, rounded once)
+__global__ void kq_kernel(int M, long R, const float* __restrict__ A, const float* __restrict__ B,
+                          const float* __restrict__ log_var, float* __restrict__ kq) {
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  float s = 0.f;
-  for (int m = 0; m < M; ++m) s = fmaf(A[(long)m * R + r], B[(long)m * R + r], s);
-  q1[r] = s;
+  double s = 0.0;
+  for (int m = 0; m < M; ++m) s += (double)A[(long)m * R + r] * (double)B[(long)m * R + r];
+  kq[r] = (float)(exp((double)log_var[0]) - s);
 }
 
 // out[m,r] = q[r] * X[m,r]   (accumulate = 0)   or   out[m,r] += q[r] * X[m,r]  (accumulate = 1)
-__global__ void colscale_kernel(long total, long R, const float* __restrict__ q, const float* __restrict__ X,
-                                float* __restrict__ out, int accumulate) {
+template <typename T>
+__global__ void colscale_kernel(long total, long R, const float* __restrict__ q, const T* __restrict__ X,
+                                T* __restrict__ out, int accumulate) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const float v = q[i % R] * X[i];
+    const T v = (T)q[i % R] * X[i];
     out[i] = accumulate ? out[i] + v : v;
   }
 }
-int colscale(cudaStream_t st, int M, long R, const float* q, const float* X, float* out, int accumulate) {
+template <typename T>
+int colscale(cudaStream_t st, int M, long R, const float* q, const T* X, T* out, int accumulate) {
   const long total = (long)M * R;
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  colscale_kernel<<<blocks, 256, 0, st>>>(total, R, q, X, out, accumulate);
+  colscale_kernel<T><<<grid_for(total), 256, 0, st>>>(total, R, q, X, out, accumulate);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -129,13 +283,12 @@ int colscale(cudaStream_t st, int M, long R, const float* q, const float* X, flo
 // ------------------------------------------------------------------------------------------------
 // data layer: sampling and its backward
 // ------------------------------------------------------------------------------------------------
-// in:  F = predictive mean, var = q2.   out: var = sigma2 - q1 + q2 + 2 off, F = mean + sqrt(var) eps
-__global__ void sample_fwd_kernel(long total, int L, const float* __restrict__ q1, const float* __restrict__ eps,
-                                  const float* __restrict__ log_var, float* __restrict__ F, float* __restrict__ var) {
-  const float s2 = expf(log_var[0]);
+// in:  F = predictive mean, var = q2.   out: var = (sigma2 - q1) + q2 + 2 off, F = mean + sqrt(var) eps
+__global__ void sample_fwd_kernel(long total, int L, const float* __restrict__ kq, const float* __restrict__ eps,
+                                  float* __restrict__ F, float* __restrict__ var) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / L;
-    const float v = ((s2 - q1[r]) + var[i] + GPSA_OFF) + GPSA_OFF;  // jitter twice: vgpsa.py:201,:204
+    const float v = (kq[r] + var[i] + GPSA_OFF) + GPSA_OFF;  // jitter twice: vgpsa.py:201,:204
     var[i] = v;
     F[i] = fmaf(sqrtf(v), eps[i], F[i]);
   }
@@ -153,12 +306,12 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const fl
     float s = 0.f;
     for (int p = lane; p < L; p += 32) {
       const long i = r * L + p;
-      const float g = 0.5f * Fbar[i] * eps[i] * rsqrtf(var[i]);
+      const float g = 0.5f * Fbar[i] * eps[i] / sqrtf(var[i]);
       Gm[i] = g;
       s += g;
     }
     s = warp_sum(s);
-    if (lane == 0) { q1bar[r] = -s; tot += s; }
+    if (lane == 0) { q1bar[r] = -s; tot += (double)s; }
   }
   __shared__ double red[8];
   if (lane == 0) red[warp] = tot;
@@ -166,24 +319,24 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const fl
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    atomicAdd(&acc_hyp[1], t * (double)expf(log_var[0]));
+    atomicAdd(&acc_hyp[1], t * exp((double)log_var[0]));
   }
 }
 
 // KL(q(u_p) || p(u)) summed over genes: one CTA per gene.
 //   kl_p = hldK - hldOm[p] + 0.5 (tr(K^-1 Omega_p) + delta_p^T K^-1 delta_p - M)
-__global__ void __launch_bounds__(256) kl_F_kernel(int M, int L, const float* __restrict__ Kinv,
-                                                   const float* __restrict__ Omega, const float* __restrict__ hldOm,
-                                                   const float* __restrict__ dlt, const float* __restrict__ KD,
+__global__ void __launch_bounds__(256) kl_F_kernel(int M, int L, const double* __restrict__ Kinv,
+                                                   const float* __restrict__ Omega, const double* __restrict__ hldOm,
+                                                   const float* __restrict__ dlt, const double* __restrict__ KD,
                                                    const double* __restrict__ hldK, double* kl_acc) {
   const int p = blockIdx.x;
   const float* Om = Omega + (long)p * M * M;
   double s = 0.0;
-  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += (double)Kinv[i] * (double)Om[i];
-  for (int m = threadIdx.x; m < M; m += blockDim.x) s += (double)dlt[(long)m * L + p] * (double)KD[(long)m * L + p];
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += Kinv[i] * (double)Om[i];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) s += (double)dlt[(long)m * L + p] * KD[(long)m * L + p];
   __shared__ double red[32];
   s = block_sum<double>(s, red);
-  if (threadIdx.x == 0) atomicAdd(kl_acc, hldK[0] - (double)hldOm[p] + 0.5 * (s - (double)M));
+  if (threadIdx.x == 0) atomicAdd(kl_acc, hldK[0] - hldOm[p] + 0.5 * (s - (double)M));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,63 +344,63 @@ __global__ void __launch_bounds__(256) kl_F_kernel(int M, int L, const float* __
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256) warp_predict_kernel(int M, long n, int S, const float* __restrict__ Z,
-                                                           const float* __restrict__ dlt, const float* __restrict__ A,
-                                                           const float* __restrict__ B, const float* __restrict__ T,
+                                                           const float* __restrict__ dlt, const double* __restrict__ A,
+                                                           const double* __restrict__ B, const double* __restrict__ T,
                                                            const float* __restrict__ X, const float* __restrict__ eps,
                                                            const float* __restrict__ log_var, float* __restrict__ var,
                                                            float* __restrict__ Gmean, float* __restrict__ Gs,
                                                            long gs_stride) {
-  extern __shared__ float dmz[];  // [M*D]  delta - mu_z  (mean function = identity: mu_z = Z)
-  for (int i = threadIdx.x; i < M * D; i += blockDim.x) dmz[i] = dlt[i] - Z[i];
+  extern __shared__ double dmz[];  // [M*D]  delta - mu_z  (mean function = identity: mu_z = Z)
+  for (int i = threadIdx.x; i < M * D; i += blockDim.x) dmz[i] = (double)dlt[i] - (double)Z[i];
   __syncthreads();
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  float q1 = 0.f, mu[D], q2[D];
+  double q1 = 0.0, mu[D], q2[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) { mu[d] = X[r * D + d]; q2[d] = 0.f; }
+  for (int d = 0; d < D; ++d) { mu[d] = (double)X[r * D + d]; q2[d] = 0.0; }
   for (int m = 0; m < M; ++m) {
-    const float a = A[(long)m * n + r];
-    q1 = fmaf(a, B[(long)m * n + r], q1);
+    const double a = A[(long)m * n + r];
+    q1 += a * B[(long)m * n + r];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      mu[d] = fmaf(a, dmz[m * D + d], mu[d]);
-      q2[d] = fmaf(a, T[((long)d * M + m) * n + r], q2[d]);
+      mu[d] += a * dmz[m * D + d];
+      q2[d] += a * T[((long)d * M + m) * n + r];
     }
   }
-  const float s2 = expf(log_var[0]);
+  const double kq = exp((double)log_var[0]) - q1;
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    const float v = ((s2 - q1) + q2[d] + GPSA_OFF) + GPSA_OFF;
-    var[r * D + d] = v;
-    Gmean[r * D + d] = mu[d];
+    const double v = kq + q2[d] + 2e-5;  // jitter added twice (vgpsa.py:191,:204)
+    var[r * D + d] = (float)v;
+    Gmean[r * D + d] = (float)mu[d];
     for (int s = 0; s < S; ++s)  // the reference uses the VARIANCE as the Normal scale (vgpsa.py:334-340)
-      Gs[(long)s * gs_stride + r * D + d] = fmaf(v, eps[((long)s * n + r) * D + d], mu[d]);
+      Gs[(long)s * gs_stride + r * D + d] = (float)(mu[d] + v * (double)eps[((long)s * n + r) * D + d]);
   }
 }
 
-// KL terms of view v: one CTA per spatial dim j.  Stores Ke[j,:] = K^-1 (Z_j - delta_j).
-__global__ void __launch_bounds__(256) kl_G_kernel(int M, int D, int V, int v, const float* __restrict__ Kinv,
+// KL terms of view v: one CTA per spatial dim j.  Stores Ke[j,:] = K^-1 (Z_j - delta_j) in fp64.
+__global__ void __launch_bounds__(256) kl_G_kernel(int M, int D, int V, int v, const double* __restrict__ Kinv,
                                                    const float* __restrict__ Omega_G,
-                                                   const float* __restrict__ hldOm, const float* __restrict__ Z,
+                                                   const double* __restrict__ hldOm, const float* __restrict__ Z,
                                                    const float* __restrict__ dlt, const double* __restrict__ hldK,
-                                                   float* __restrict__ Ke, double* kl_acc) {
+                                                   double* __restrict__ Ke, double* kl_acc) {
   const int j = blockIdx.x;
   const int slot = j * V + v;  // the KL uses slice j*V+v (vgpsa.py:508)
   const float* Om = Omega_G + (long)slot * M * M;
-  extern __shared__ float e[];  // [M]
-  for (int m = threadIdx.x; m < M; m += blockDim.x) e[m] = Z[m * D + j] - dlt[m * D + j];
+  extern __shared__ double e[];  // [M]
+  for (int m = threadIdx.x; m < M; m += blockDim.x) e[m] = (double)Z[m * D + j] - (double)dlt[m * D + j];
   __syncthreads();
   double s = 0.0;
-  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += (double)Kinv[i] * (double)Om[i];
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += Kinv[i] * (double)Om[i];
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
-    float t = 0.f;
-    for (int k = 0; k < M; ++k) t = fmaf(Kinv[(long)m * M + k], e[k], t);
+    double t = 0.0;
+    for (int k = 0; k < M; ++k) t += Kinv[(long)m * M + k] * e[k];
     Ke[(long)j * M + m] = t;
-    s += (double)t * (double)e[m];
+    s += t * e[m];
   }
   __shared__ double red[32];
   s = block_sum<double>(s, red);
-  if (threadIdx.x == 0) atomicAdd(kl_acc, hldK[0] - (double)hldOm[slot] + 0.5 * (s - (double)M));
+  if (threadIdx.x == 0 && kl_acc) atomicAdd(kl_acc, hldK[0] - hldOm[slot] + 0.5 * (s - (double)M));
 }
 
 template <int D>
@@ -258,7 +411,7 @@ __global__ void __launch_bounds__(256) warp_bwd_prep_kernel(long n, int S, const
                                                             float* __restrict__ mubar, float* __restrict__ varbar,
                                                             float* __restrict__ q1bar, double* acc_hyp) {
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  float tot = 0.f;
+  double tot = 0.0;
   if (r < n) {
     float q = 0.f;
 #pragma unroll
@@ -276,31 +429,31 @@ __global__ void __launch_bounds__(256) warp_bwd_prep_kernel(long n, int S, const
       q += vb;
     }
     q1bar[r] = -q;
-    tot = q;
+    tot = (double)q;
   }
-  __shared__ float red[32];
-  tot = block_sum<float>(tot, red);
-  if (threadIdx.x == 0) atomicAdd(&acc_hyp[1], (double)tot * (double)expf(log_var[0]));
+  __shared__ double red[32];
+  tot = block_sum<double>(tot, red);
+  if (threadIdx.x == 0) atomicAdd(&acc_hyp[1], tot * exp((double)log_var[0]));
 }
 
-// Abar = (delta - Z) mubar^T + q1bar o B + 2 sum_j varbar_j o T_j ;  AS_j = A o varbar_j
+// Abar = (delta - Z) mubar^T + q1bar o B + 2 sum_j varbar_j o T_j ;  AS_j = A o varbar_j   (fp64)
 template <int D>
 __global__ void warp_abar_kernel(int M, long n, const float* __restrict__ Z, const float* __restrict__ dlt,
-                                 const float* __restrict__ A, const float* __restrict__ B,
-                                 const float* __restrict__ T, const float* __restrict__ mubar,
+                                 const double* __restrict__ A, const double* __restrict__ B,
+                                 const double* __restrict__ T, const float* __restrict__ mubar,
                                  const float* __restrict__ varbar, const float* __restrict__ q1bar,
-                                 float* __restrict__ Abar, float* __restrict__ AS) {
+                                 double* __restrict__ Abar, double* __restrict__ AS) {
   const long total = (long)M * n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int m = i / n;
     const long r = i % n;
-    const float a = A[i];
-    float s = q1bar[r] * B[i];
+    const double a = A[i];
+    double s = (double)q1bar[r] * B[i];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const float vb = varbar[r * D + d];
-      s = fmaf(dlt[m * D + d] - Z[m * D + d], mubar[r * D + d], s);
-      s = fmaf(2.f * vb, T[(long)d * total + i], s);
+      const double vb = (double)varbar[r * D + d];
+      s += ((double)dlt[m * D + d] - (double)Z[m * D + d]) * (double)mubar[r * D + d];
+      s += 2.0 * vb * T[(long)d * total + i];
       AS[(long)d * total + i] = a * vb;
     }
     Abar[i] = s;
@@ -309,38 +462,38 @@ __global__ void warp_abar_kernel(int M, long n, const float* __restrict__ Z, con
 
 // d(delta - Z)[m,j] = sum_r A[m,r] mubar[r,j]:  +acc_dlt, -acc_Z.  One warp per m, column chunks on y.
 template <int D>
-__global__ void __launch_bounds__(256) warp_dmz_kernel(int M, long n, long chunk, const float* __restrict__ A,
+__global__ void __launch_bounds__(256) warp_dmz_kernel(int M, long n, long chunk, const double* __restrict__ A,
                                                        const float* __restrict__ mubar, double* acc_dlt,
                                                        double* acc_Z) {
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const long r0 = (long)blockIdx.y * chunk, r1 = (r0 + chunk < n) ? r0 + chunk : n;
-  float g[D];
+  double g[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) g[d] = 0.f;
+  for (int d = 0; d < D; ++d) g[d] = 0.0;
   for (long r = r0 + lane; r < r1; r += 32) {
-    const float a = A[(long)m * n + r];
+    const double a = A[(long)m * n + r];
 #pragma unroll
-    for (int d = 0; d < D; ++d) g[d] = fmaf(a, mubar[r * D + d], g[d]);
+    for (int d = 0; d < D; ++d) g[d] += a * (double)mubar[r * D + d];
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    const float t = warp_sum(g[d]);
+    const double t = warp_sum(g[d]);
     if (lane == 0) {
-      atomicAdd(&acc_dlt[m * D + d], (double)t);
-      atomicAdd(&acc_Z[m * D + d], -(double)t);
+      atomicAdd(&acc_dlt[m * D + d], t);
+      atomicAdd(&acc_Z[m * D + d], -t);
     }
   }
 }
 
 // e-bar_j = kl_bar * Ke_j :  acc_Z[:,j] += , acc_dlt[:,j] -=
-__global__ void kl_e_bwd_kernel(int M, int D, const float* __restrict__ Ke, const float* __restrict__ kl_bar,
+__global__ void kl_e_bwd_kernel(int M, int D, const double* __restrict__ Ke, const float* __restrict__ kl_bar,
                                 double* acc_Z, double* acc_dlt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * D) return;
   const int m = i / D, j = i % D;
-  const double g = (double)kl_bar[0] * (double)Ke[(long)j * M + m];
+  const double g = (double)kl_bar[0] * Ke[(long)j * M + m];
   acc_Z[i] += g;
   acc_dlt[i] -= g;
 }
@@ -363,7 +516,7 @@ __global__ void __launch_bounds__(256) ll_fwd_kernel(long N, int P, int S, const
   acc = block_sum<double>(acc, red);
   if (threadIdx.x == 0) {
     double v = -0.5 * acc;
-    if (blockIdx.x == 0) v -= (double)total * ((double)logf(sigma) + 0.91893853320467274178);
+    if (blockIdx.x == 0) v -= (double)total * (log((double)sigma) + 0.91893853320467274178);
     atomicAdd(ll_acc, v / (double)S);
   }
 }
@@ -394,9 +547,41 @@ __global__ void __launch_bounds__(256) ll_bwd_kernel(long N, int P, int S, const
   }
 }
 
-int grid_for(long n, int per_block = 256, int cap = 148 * 16) {
-  const long b = (n + per_block - 1) / per_block;
-  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+// prior_bwd launcher
+int prior_bwd(int kind, int D, int M, const float* Z, const float* ls, const float* var, const double* Kbar,
+              double* acc_Z, double* acc_hyp, cudaStream_t st) {
+  const int blocks = gpsa_cdiv(M, 8);
+#define PB(DD, KK) prior_bwd_kernel<DD, KK><<<blocks, 256, 0, st>>>(M, Z, ls, var, Kbar, acc_Z, acc_hyp)
+  if (kind == GPSA_KIND_RBF) {
+    if (D == 1) PB(1, GPSA_KIND_RBF); else if (D == 2) PB(2, GPSA_KIND_RBF); else PB(3, GPSA_KIND_RBF);
+  } else if (kind == GPSA_KIND_MATERN12) {
+    if (D == 1) PB(1, GPSA_KIND_MATERN12); else if (D == 2) PB(2, GPSA_KIND_MATERN12); else PB(3, GPSA_KIND_MATERN12);
+  } else {
+    return GPSA_ERR_UNSUPPORTED;
+  }
+#undef PB
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+// K-bar (fp64) of a sparse-GP layer:  Kbar = -K^-1 (Abar A^T)  [+ kl_bar * KL terms]
+//   P = Abar A^T (fp64 accumulate over R), Kbar = -Kinv P.
+template <typename TV>
+int kbar_from_solve(cudaStream_t st, int M, long R, const double* Kinv64, const TV* Abar, const TV* A, double* P,
+                    double* Kbar) {
+  TRY((gemm_nt<double, TV, TV, double>(st, M, M, R, 1.0, Abar, R, A, R, 0.0, P, M)));
+  return gemm_nn<double, double, double, double>(st, M, M, M, -1.0, Kinv64, M, P, M, 0.0, Kbar, M);
+}
+
+// chunking of a warp-per-row reduction over n columns so that the grid fills the machine
+void row_chunks(int M, long n, dim3& grid, long& chunk) {
+  const int row_ctas = gpsa_cdiv(M, 8);
+  long nchunk = (148 * 4 + row_ctas - 1) / row_ctas;
+  const long maxc = (n + 1023) / 1024;
+  if (nchunk > maxc) nchunk = maxc;
+  if (nchunk < 1) nchunk = 1;
+  chunk = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
+  grid = dim3(row_ctas, gpsa_cdiv(n, chunk));
 }
 
 }  // namespace
@@ -404,7 +589,7 @@ int grid_for(long n, int per_block = 256, int cap = 148 * 16) {
 // ================================================================================================
 // exported entry points
 // ================================================================================================
-extern "C" int gpsa_version(void) { return 100; }
+extern "C" int gpsa_version(void) { return 101; }
 
 extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA,
                              const float* B, long brs, long bcs, long sB, float beta, float* C, long ldc, long sC,
@@ -414,13 +599,12 @@ extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, 
 }
 
 extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_ls, const float* log_var,
-                                  float* Lk, float* Kinv, double* half_logdet, int* info, double* ws64,
+                                  float* Lk, float* Kinv, double* Kinv64, double* half_logdet, int* info, double* ws64,
                                   cudaStream_t st) {
   if (M <= 0 || D < 1 || D > 3) return GPSA_ERR_ARG;
   const long MM = (long)M * M;
   double* Kd = ws64;
   double* Xd = ws64 + MM;
-  double* Kinv_d = ws64 + 2 * MM;
   const int blocks = gpsa_cdiv(MM, 256);
 #define PK(DD, KK) prior_kuu_kernel<DD, KK><<<blocks, 256, 0, st>>>(M, Z, log_ls, log_var, Kd)
   if (kind == GPSA_KIND_RBF) {
@@ -435,64 +619,89 @@ extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const 
   TRY(gpsa_potrf_batched_f64(M, 1, Kd, half_logdet, info, st));
   TRY(gpsa_trtri_batched_f64(M, 1, Kd, Xd, st));
   // K^-1 = X^T X
-  TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv_d, M, 0, 1)));
-  cvt_d2f_kernel<<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
-  cvt_d2f_kernel<<<grid_for(MM), 256, 0, st>>>(MM, Kinv_d, Kinv);
+  TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv64, M, 0, 1)));
+  cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
+  if (Kinv) cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kinv64, Kinv);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
 
-extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, float* half_logdet,
-                                  int* info, cudaStream_t st) {
+extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, double* L64,
+                                  double* half_logdet, int* info, cudaStream_t st) {
   if (M <= 0 || B <= 0) return GPSA_OK;
   const long MM = (long)M * M;
-  TRY((gemm_strided<float, float, float, float>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, Omega, M, MM, B, 1,
-                                                (double)GPSA_OFF)));
-  if (cudaMemcpyAsync(Ltril, Omega, sizeof(float) * MM * B, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-    return GPSA_ERR_CUDA;
-  return gpsa_potrf_batched_f32(M, B, Ltril, half_logdet, info, st);
+  // Omega = Osq Osq^T + 1e-5 I with fp64 accumulation, kept in fp64 for the factorisation
+  TRY((gemm_strided<double, float, float, double>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, L64, M, MM, B, 1,
+                                                  (double)GPSA_OFF)));
+  cvt_kernel<double, float><<<grid_for(MM * B), 256, 0, st>>>(MM * B, L64, Omega);
+  GPSA_LAUNCH_CHECK();
+  TRY(gpsa_potrf_batched_f64(M, B, L64, half_logdet, info, st));
+  cvt_kernel<double, float><<<grid_for(MM * B), 256, 0, st>>>(MM * B, L64, Ltril);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
 }
 
-extern "C" int gpsa_omega_grad(int M, int B, const float* Osq, const float* Ltril, float* Obar, const float* coef,
-                               float* Linv, float* Osq_bar, cudaStream_t st) {
+extern "C" int gpsa_omega_grad(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
+                               double* Linv64, double* Y64, float* Osq_bar, cudaStream_t st) {
   if (M <= 0 || B <= 0) return GPSA_OK;
   const long MM = (long)M * M;
+  // Osq_bar = (Obar + Obar^T) Osq = 2 Obar Osq  (Obar symmetric) ...
+  TRY((gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
+                                                B)));
   if (coef) {
-    TRY(gpsa_trtri_batched_f32(M, B, Ltril, Linv, st));
-    // Obar[b] += coef[b] * Linv^T Linv
-    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 1.0, Linv, 1, M, MM, Linv, M, 1, MM, 1.0, Obar, M, MM, B,
-                                                  1, 0.0, 0, coef, 1)));
+    // ... + 2 coef[b] Omega^-1 Osq, Omega^-1 = Linv^T Linv, in fp64
+    TRY(gpsa_trtri_batched_f64(M, B, L64, Linv64, st));
+    TRY((gemm_strided<double, double, float, double>(st, M, M, M, 1.0, Linv64, M, 1, MM, Osq, M, 1, MM, 0.0, Y64, M, MM,
+                                                     B)));
+    TRY((gemm_strided<double, double, double, float>(st, M, M, M, 2.0, Linv64, 1, M, MM, Y64, M, 1, MM, 1.0, Osq_bar, M,
+                                                     MM, B, 1, 0.0, 0, coef, 1)));
   }
-  // Osq_bar = (Obar + Obar^T) Osq = 2 Obar Osq  (Obar symmetric)
-  return gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
-                                                  B);
+  return GPSA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
+#define DISPATCH_WARP(D, kind, CALL)                                                                        \
+  do {                                                                                                      \
+    if (kind == GPSA_KIND_RBF) {                                                                            \
+      if (D == 1) CALL(1, GPSA_KIND_RBF); else if (D == 2) CALL(2, GPSA_KIND_RBF); else CALL(3, GPSA_KIND_RBF); \
+    } else if (kind == GPSA_KIND_MATERN12) {                                                                \
+      if (D == 1) CALL(1, GPSA_KIND_MATERN12); else if (D == 2) CALL(2, GPSA_KIND_MATERN12);                \
+      else CALL(3, GPSA_KIND_MATERN12);                                                                     \
+    } else {                                                                                                \
+      return GPSA_ERR_UNSUPPORTED;                                                                          \
+    }                                                                                                       \
+  } while (0)
+
 extern "C" int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t st) {
   const int M = a->M, D = a->D;
   const long n = a->n, MM = (long)M * M;
   if (n <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  TRY(gpsa_prior_prepare(a->kind, D, M, a->Z, a->log_ls, a->log_var, a->Lk, a->Kinv, a->hld_K, a->info, a->ws64, st));
-  TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, n, a->Z, a->X, a->log_ls, a->log_var, a->B, st));
-  TRY(gemm_nn(st, M, (int)n, M, 1.0, a->Kinv, M, a->B, n, 0.0, a->A, n));
+  TRY(gpsa_prior_prepare(a->kind, D, M, a->Z, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
+                         a->ws64, st));
+  {
+    dim3 grid(gpsa_cdiv(n, 256), M < 32 ? M : 32);
+#define KF(DD, KK) kuf64_kernel<DD, KK><<<grid, 256, 0, st>>>(M, n, a->Z, a->X, a->log_ls, a->log_var, a->B)
+    DISPATCH_WARP(D, a->kind, KF);
+#undef KF
+    GPSA_LAUNCH_CHECK();
+  }
+  // A = K^-1 K_uf  (replaces torch.cholesky_solve, vgpsa.py:177)
+  TRY((gemm_nn<double, double, double, double>(st, M, (int)n, M, 1.0, a->Kinv64, M, a->B, n, 0.0, a->A, n)));
   // T_j = Omega_{v*D+j} A  -- the marginal variance uses slice v*D+j (vgpsa.py:336-339)
-  TRY((gemm_strided<float, float, float, float>(st, M, (int)n, M, 1.0, a->Omega_G + (long)a->v * D * MM, M, 1, MM, a->A,
-                                                n, 1, 0, 0.0, a->T, n, (long)M * n, D)));
-  const size_t smem = (size_t)M * D * sizeof(float);
+  TRY((gemm_strided<double, float, double, double>(st, M, (int)n, M, 1.0, a->Omega_G + (long)a->v * D * MM, M, 1, MM,
+                                                   a->A, n, 1, 0, 0.0, a->T, n, (long)M * n, D)));
+  const size_t smem = (size_t)M * D * sizeof(double);
   const int blocks = gpsa_cdiv(n, 256);
-#define WP(DD)                                                                                                       \
-  warp_predict_kernel<DD><<<blocks, 256, smem, st>>>(M, n, a->S, a->Z, a->dlt, a->A, a->B, a->T, a->X, a->eps,       \
+#define WP(DD)                                                                                                 \
+  warp_predict_kernel<DD><<<blocks, 256, smem, st>>>(M, n, a->S, a->Z, a->dlt, a->A, a->B, a->T, a->X, a->eps, \
                                                      a->log_var, a->var, a->Gmean, a->Gs, a->gs_stride)
   if (D == 1) WP(1); else if (D == 2) WP(2); else WP(3);
 #undef WP
   GPSA_LAUNCH_CHECK();
-  if (a->kl_acc) {
-    kl_G_kernel<<<D, 256, M * sizeof(float), st>>>(M, D, a->V, a->v, a->Kinv, a->Omega_G, a->hld_Omega, a->Z, a->dlt,
-                                                   a->hld_K, a->Ke, a->kl_acc);
-    GPSA_LAUNCH_CHECK();
-  }
+  kl_G_kernel<<<D, 256, M * sizeof(double), st>>>(M, D, a->V, a->v, a->Kinv64, a->Omega_G, a->hld_Omega, a->Z, a->dlt,
+                                                  a->hld_K, a->Ke, a->kl_acc);
+  GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
 
@@ -501,9 +710,12 @@ extern "C" int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t st) 
   const long n = a->n, MM = (long)M * M;
   if (n <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
+  double* Kbar = a->ws64;
+  double* P = a->ws64 + MM;
+  double* T1 = a->ws64 + 2 * MM;
   const int blocks = gpsa_cdiv(n, 256);
-#define WB(DD)                                                                                                 \
-  warp_bwd_prep_kernel<DD><<<blocks, 256, 0, st>>>(n, a->S, a->Gs_bar, a->gs_stride, a->Gm_bar, a->eps,        \
+#define WB(DD)                                                                                          \
+  warp_bwd_prep_kernel<DD><<<blocks, 256, 0, st>>>(n, a->S, a->Gs_bar, a->gs_stride, a->Gm_bar, a->eps, \
                                                    a->log_var, a->mubar, a->varbar, a->q1bar, a->acc_hyp)
   if (D == 1) WB(1); else if (D == 2) WB(2); else WB(3);
 #undef WB
@@ -515,48 +727,44 @@ extern "C" int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t st) 
   if (D == 1) WA(1); else if (D == 2) WA(2); else WA(3);
 #undef WA
   GPSA_LAUNCH_CHECK();
-  {
-    const int row_ctas = gpsa_cdiv(M, 8);
-    long nchunk = (148 * 4 + row_ctas - 1) / row_ctas;
-    const long maxc = (n + 1023) / 1024;
-    if (nchunk > maxc) nchunk = maxc;
-    if (nchunk < 1) nchunk = 1;
-    const long chunk = ((n + nchunk - 1) / nchunk + 31) / 32 * 32;
-    dim3 grid(row_ctas, gpsa_cdiv(n, chunk));
-#define WD(DD) warp_dmz_kernel<DD><<<grid, 256, 0, st>>>(M, n, chunk, a->A, a->mubar, a->acc_dlt, a->acc_Z)
-    if (D == 1) WD(1); else if (D == 2) WD(2); else WD(3);
+  dim3 rgrid;
+  long chunk;
+  row_chunks(M, n, rgrid, chunk);
+#define WD(DD) warp_dmz_kernel<DD><<<rgrid, 256, 0, st>>>(M, n, chunk, a->A, a->mubar, a->acc_dlt, a->acc_Z)
+  if (D == 1) WD(1); else if (D == 2) WD(2); else WD(3);
 #undef WD
-    GPSA_LAUNCH_CHECK();
-  }
+  GPSA_LAUNCH_CHECK();
   // Omega-bar_{v*D+j} += (A o varbar_j) A^T
   {
-    const int split = pick_split(M, M, n, D);
-    TRY((gemm_strided<float, float, float, float>(st, M, M, n, 1.0, a->AS, n, 1, (long)M * n, a->A, 1, n, 0, 1.0,
-                                                  a->Obar_G + (long)v * D * MM, M, MM, D, split)));
+    const int split = pick_split(M, M, n, D, 64);
+    TRY((gemm_strided<double, double, double, float>(st, M, M, n, 1.0, a->AS, n, 1, (long)M * n, a->A, 1, n, 0, 1.0,
+                                                     a->Obar_G + (long)v * D * MM, M, MM, D, split)));
   }
-  // C = K^-1 Abar ; Kbar = -C A^T ; Bbar = C + q1bar o A
-  TRY(gemm_nn(st, M, (int)n, M, 1.0, a->Kinv, M, a->Abar, n, 0.0, a->C, n));
-  TRY(gemm_nt(st, M, M, n, -1.0, a->C, n, a->A, n, 0.0, a->Kbar, M));
-  TRY(colscale(st, M, n, a->q1bar, a->A, a->C, 1));
+  // C = K^-1 Abar ; Kbar = -K^-1 (Abar A^T) ; Bbar = C + q1bar o A
+  TRY((gemm_nn<double, double, double, double>(st, M, (int)n, M, 1.0, a->Kinv64, M, a->Abar, n, 0.0, a->C, n)));
+  TRY(kbar_from_solve<double>(st, M, n, a->Kinv64, a->Abar, a->A, P, Kbar));
+  TRY(colscale<double>(st, M, n, a->q1bar, a->A, a->C, 1));
   if (a->kl_bar) {
     // KL_v = sum_j [hldK - hldOm_j' + 0.5 (tr(K^-1 Om_j') + e_j^T K^-1 e_j - M)],  j' = j*V+v
-    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, D, (long)V * MM, a->Omega_G + (long)v * MM, a->Som);
+    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, D, (long)V * MM, a->Omega_G + (long)v * MM, P);
     GPSA_LAUNCH_CHECK();
-    TRY(gemm_nn(st, M, M, M, 1.0, a->Kinv, M, a->Som, M, 0.0, a->T1, M));
-    TRY(gemm_nn(st, M, M, M, -0.5, a->T1, M, a->Kinv, M, 1.0, a->Kbar, M, a->kl_bar));
-    TRY((gemm_strided<float, float, float, float>(st, M, M, D, -0.5, a->Ke, 1, M, 0, a->Ke, M, 1, 0, 1.0, a->Kbar, M, 0,
-                                                  1, 1, 0.0, 0, a->kl_bar, 0)));
-    TRY(axpy_dev(st, MM, 0.5f * (float)D, a->kl_bar, a->Kinv, a->Kbar));
+    TRY((gemm_nn<double, double, double, double>(st, M, M, M, 1.0, a->Kinv64, M, P, M, 0.0, T1, M)));
+    TRY((gemm_nn<double, double, double, double>(st, M, M, M, -0.5, T1, M, a->Kinv64, M, 1.0, Kbar, M, a->kl_bar)));
+    TRY((gemm_strided<double, double, double, double>(st, M, M, D, -0.5, a->Ke, 1, M, 0, a->Ke, M, 1, 0, 1.0, Kbar, M, 0,
+                                                      1, 1, 0.0, 0, a->kl_bar, 0)));
+    TRY((axpy_dev<double, double>(st, MM, 0.5 * D, a->kl_bar, a->Kinv64, Kbar)));
     for (int j = 0; j < D; ++j)
-      TRY(axpy_dev(st, MM, 0.5f, a->kl_bar, a->Kinv, a->Obar_G + (long)(j * V + v) * MM));
+      TRY((axpy_dev<double, float>(st, MM, 0.5, a->kl_bar, a->Kinv64, a->Obar_G + (long)(j * V + v) * MM)));
     kl_e_bwd_kernel<<<gpsa_cdiv(M * D, 256), 256, 0, st>>>(M, D, a->Ke, a->kl_bar, a->acc_Z, a->acc_dlt);
     GPSA_LAUNCH_CHECK();
   }
-  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, n, a->Z, a->X, a->log_ls, a->log_var, a->C, a->acc_Z, nullptr, nullptr,
-                             a->acc_hyp, st));
-  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, M, a->Z, a->Z, a->log_ls, a->log_var, a->Kbar, a->acc_Z, nullptr, a->acc_Z,
-                             a->acc_hyp, st));
-  return GPSA_OK;
+#define KB(DD, KK)                                                                                            \
+  kuf64_bwd_kernel<DD, KK><<<rgrid, 256, 0, st>>>(M, n, chunk, a->Z, a->X, a->log_ls, a->log_var, a->C, a->acc_Z, \
+                                                  a->acc_hyp)
+  DISPATCH_WARP(D, a->kind, KB);
+#undef KB
+  GPSA_LAUNCH_CHECK();
+  return prior_bwd(a->kind, D, M, a->Z, a->log_ls, a->log_var, Kbar, a->acc_Z, a->acc_hyp, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,23 +773,24 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   const long R = a->R;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->hld_K, a->info, a->ws64, st));
+  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
+                         a->ws64, st));
   TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
-  TRY(gemm_nn(st, M, (int)R, M, 1.0, a->Kinv, M, a->B, R, 0.0, a->A, R));
-  q1_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->q1);
+  TRY((gemm_nn<double, double, float, float>(st, M, (int)R, M, 1.0, a->Kinv64, M, a->B, R, 0.0, a->A, R)));
+  kq_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->log_var, a->kq);
   GPSA_LAUNCH_CHECK();
   // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
   TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
                                                 1)));
   TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
-  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
   TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
-  sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->q1, a->eps, a->log_var, a->F, a->var);
+  sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
   GPSA_LAUNCH_CHECK();
-  // KD = K^-1 delta
-  TRY(gemm_nn(st, M, L, M, 1.0, a->Kinv, M, a->dlt, L, 0.0, a->KD, L));
+  // KD = K^-1 delta (fp64)
+  TRY((gemm_nn<double, double, float, double>(st, M, L, M, 1.0, a->Kinv64, M, a->dlt, L, 0.0, a->KD, L)));
   if (a->kl_acc) {
-    kl_F_kernel<<<L, 256, 0, st>>>(M, L, a->Kinv, a->Omega, a->hld_Omega, a->dlt, a->KD, a->hld_K, a->kl_acc);
+    kl_F_kernel<<<L, 256, 0, st>>>(M, L, a->Kinv64, a->Omega, a->hld_Omega, a->dlt, a->KD, a->hld_K, a->kl_acc);
     GPSA_LAUNCH_CHECK();
   }
   return GPSA_OK;
@@ -593,6 +802,9 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
   if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  double* Kbar = a->ws64;
+  double* P = a->ws64 + MM;
+  double* T1 = a->ws64 + 2 * MM;
   {
     long b = (R + 7) / 8;
     if (b > 148 * 8) b = 148 * 8;
@@ -601,38 +813,36 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   }
   // delta-bar = A Fbar (+ kl_bar K^-1 delta)
   {
-    const int split = pick_split(M, L, R, 1);
+    const int split = pick_split(M, L, R, 1, tile_of<float>(M, L));
     if (cudaMemsetAsync(a->dlt_bar, 0, sizeof(float) * (size_t)M * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
     TRY((gemm_strided<float, float, float, float>(st, M, L, R, 1.0, a->A, R, 1, 0, a->F_bar, L, 1, 0, 1.0, a->dlt_bar,
                                                   L, 0, 1, split)));
   }
-  if (a->kl_bar) TRY(axpy_dev(st, (long)M * L, 1.f, a->kl_bar, a->KD, a->dlt_bar));
+  if (a->kl_bar) TRY((axpy_dev<double, float>(st, (long)M * L, 1.0, a->kl_bar, a->KD, a->dlt_bar)));
   // Abar = q1bar o B + delta Fbar^T + 2 (sum_p Gm Omega_p) a
-  TRY(colscale(st, M, R, a->q1bar, a->B, a->Abar, 0));
+  TRY(colscale<float>(st, M, R, a->q1bar, a->B, a->Abar, 0));
   TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
                                                 R, 0, 1)));
   TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
   // Omega-bar = sum_r Gm a a^T (+ 0.5 kl_bar K^-1)
   TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
   TRY(gpsa_feat_unpack(M, L, a->H, a->kl_bar ? a->Kinv : nullptr, 0.5f, a->kl_bar, a->Obar, st));
-  // C = K^-1 Abar ; Kbar = -C A^T ; Bbar = C + q1bar o A
-  TRY(gemm_nn(st, M, (int)R, M, 1.0, a->Kinv, M, a->Abar, R, 0.0, a->C, R));
-  TRY(gemm_nt(st, M, M, R, -1.0, a->C, R, a->A, R, 0.0, a->Kbar, M));
-  TRY(colscale(st, M, R, a->q1bar, a->A, a->C, 1));
+  // C = K^-1 Abar ; Kbar = -K^-1 (Abar A^T) ; Bbar = C + q1bar o A
+  TRY((gemm_nn<double, double, float, float>(st, M, (int)R, M, 1.0, a->Kinv64, M, a->Abar, R, 0.0, a->C, R)));
+  TRY(kbar_from_solve<float>(st, M, R, a->Kinv64, a->Abar, a->A, P, Kbar));
+  TRY(colscale<float>(st, M, R, a->q1bar, a->A, a->C, 1));
   if (a->kl_bar) {
     // KL_F = sum_p [hldK - hldOm_p + 0.5 (tr(K^-1 Om_p) + d_p^T K^-1 d_p - M)]
-    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, L, MM, a->Omega, a->Som);
+    sum_batch_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(MM, L, MM, a->Omega, P);
     GPSA_LAUNCH_CHECK();
-    TRY(gemm_nn(st, M, M, M, 1.0, a->Kinv, M, a->Som, M, 0.0, a->T1, M));
-    TRY(gemm_nn(st, M, M, M, -0.5, a->T1, M, a->Kinv, M, 1.0, a->Kbar, M, a->kl_bar));
-    TRY(gemm_nt(st, M, M, L, -0.5, a->KD, L, a->KD, L, 1.0, a->Kbar, M, a->kl_bar));
-    TRY(axpy_dev(st, MM, 0.5f * (float)L, a->kl_bar, a->Kinv, a->Kbar));
+    TRY((gemm_nn<double, double, double, double>(st, M, M, M, 1.0, a->Kinv64, M, P, M, 0.0, T1, M)));
+    TRY((gemm_nn<double, double, double, double>(st, M, M, M, -0.5, T1, M, a->Kinv64, M, 1.0, Kbar, M, a->kl_bar)));
+    TRY((gemm_nt<double, double, double, double>(st, M, M, L, -0.5, a->KD, L, a->KD, L, 1.0, Kbar, M, a->kl_bar)));
+    TRY((axpy_dev<double, double>(st, MM, 0.5 * L, a->kl_bar, a->Kinv64, Kbar)));
   }
   TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->C, a->acc_Gt, a->G_bar, nullptr,
                              a->acc_hyp, st));
-  TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, M, a->Gt, a->Gt, a->log_ls, a->log_var, a->Kbar, a->acc_Gt, nullptr,
-                             a->acc_Gt, a->acc_hyp, st));
-  return GPSA_OK;
+  return prior_bwd(a->kind, D, M, a->Gt, a->log_ls, a->log_var, Kbar, a->acc_Gt, a->acc_hyp, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ class WarpFwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("V", I), ("v", I), ("S", I), ("n", LNG),
         ("Z", P), ("dlt", P), ("log_ls", P), ("log_var", P), ("Omega_G", P), ("hld_Omega", P), ("X", P), ("eps", P),
-        ("Lk", P), ("Kinv", P), ("hld_K", P), ("info", P),
+        ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
         ("A", P), ("B", P), ("T", P), ("Ke", P), ("var", P), ("Gmean", P), ("Gs", P), ("gs_stride", LNG),
         ("kl_acc", P), ("ws64", P),
     ]
@@ -57,11 +57,11 @@ class WarpBwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("V", I), ("v", I), ("S", I), ("n", LNG),
         ("Z", P), ("dlt", P), ("log_ls", P), ("log_var", P), ("Omega_G", P), ("X", P), ("eps", P),
-        ("Kinv", P), ("A", P), ("B", P), ("T", P), ("Ke", P),
+        ("Kinv64", P), ("A", P), ("B", P), ("T", P), ("Ke", P),
         ("Gs_bar", P), ("gs_stride", LNG), ("Gm_bar", P), ("kl_bar", P),
         ("acc_Z", P), ("acc_dlt", P), ("acc_hyp", P), ("Obar_G", P),
         ("mubar", P), ("varbar", P), ("q1bar", P), ("Abar", P), ("C", P), ("AS", P),
-        ("Kbar", P), ("Som", P), ("T1", P),
+        ("ws64", P),
     ]
 
 
@@ -69,8 +69,8 @@ class DataFwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
         ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P), ("eps", P),
-        ("Lk", P), ("Kinv", P), ("hld_K", P), ("info", P),
-        ("A", P), ("B", P), ("q1", P), ("W", P), ("KD", P), ("F", P), ("var", P),
+        ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
+        ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("F", P), ("var", P),
         ("kl_acc", P), ("ws64", P), ("engine", I),
     ]
 
@@ -79,10 +79,10 @@ class DataBwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
         ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("G", P), ("eps", P),
-        ("Kinv", P), ("A", P), ("B", P), ("W", P), ("KD", P), ("var", P),
+        ("Kinv", P), ("Kinv64", P), ("A", P), ("B", P), ("W", P), ("KD", P), ("var", P),
         ("F_bar", P), ("kl_bar", P),
         ("G_bar", P), ("acc_Gt", P), ("acc_hyp", P), ("dlt_bar", P), ("Obar", P),
-        ("Gm", P), ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("Kbar", P), ("Som", P), ("T1", P),
+        ("Gm", P), ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("ws64", P),
         ("engine", I),
     ]
 
@@ -98,9 +98,9 @@ SIGNATURES = {
     "gpsa_trtri_batched_f32": [I, I, P, P, P],
     "gpsa_trtri_batched_f64": [I, I, P, P, P],
     "gpsa_gemm_f32": [I, I, LNG, F, P, LNG, LNG, LNG, P, LNG, LNG, LNG, F, P, LNG, LNG, I, P],
-    "gpsa_prior_prepare": [I, I, I, P, P, P, P, P, P, P, P, P],
-    "gpsa_omega_prepare": [I, I, P, P, P, P, P, P],
-    "gpsa_omega_grad": [I, I, P, P, P, P, P, P, P],
+    "gpsa_prior_prepare": [I, I, I, P, P, P, P, P, P, P, P, P, P],
+    "gpsa_omega_prepare": [I, I, P, P, P, P, P, P, P],
+    "gpsa_omega_grad": [I, I, P, P, P, P, P, P, P, P],
     "gpsa_feat_count": [I],
     "gpsa_feat_pack": [I, I, P, P, P],
     "gpsa_feat_unpack": [I, I, P, P, F, P, P, P],

@@ -92,22 +92,25 @@ def kernel_matrix(kind_name, x1, x2, log_ls, log_var):
 
 # --------------------------------------------------------------------------------------------------
 def omega_prepare(Osq):
-    """Omega = Osq Osq^T + 1e-5 I, its Cholesky factor, half log-dets, info flags."""
+    """Omega = Osq Osq^T + 1e-5 I (fp32 copy), its Cholesky factor (fp32 copy and the fp64 original),
+    fp64 half log-dets, info flags."""
     B, M, _ = Osq.shape
     Omega, Ltril = _new(Osq, B, M, M), _new(Osq, B, M, M)
-    hld = _new(Osq, B)
+    L64 = _new(Osq, B, M, M, dtype=f64)
+    hld = _new(Osq, B, dtype=f64)
     info = _new(Osq, B, dtype=i32)
-    check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(hld), ptr(info, i32), stream()),
-          "omega_prepare")
-    return Omega, Ltril, hld, info
+    check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(L64, f64), ptr(hld, f64),
+                                   ptr(info, i32), stream()), "omega_prepare")
+    return Omega, Ltril, L64, hld, info
 
 
-def omega_grad(Osq, Ltril, Obar, coef):
+def omega_grad(Osq, L64, Obar, coef):
     B, M, _ = Osq.shape
-    Linv = _new(Osq, B, M, M) if coef is not None else None
+    Linv = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
+    Y = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
     out = _new(Osq, B, M, M)
-    check(lib().gpsa_omega_grad(M, B, ptr(Osq), ptr(Ltril), ptr(Obar), ptr(coef), ptr(Linv), ptr(out), stream()),
-          "omega_grad")
+    check(lib().gpsa_omega_grad(M, B, ptr(Osq), ptr(L64, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
+                                ptr(out), stream()), "omega_grad")
     return out
 
 
@@ -126,34 +129,35 @@ class WarpLayer(torch.autograd.Function):
         log_ls, log_var = _c(log_ls.detach()), _c(log_var.detach())
         V, M, D = Xtilde.shape
         S, free, kind = meta["S"], meta["free"], meta["kind"]
-        Omega_G, Ltril_G, hld_G, info_G = omega_prepare(Osq_G)
+        Omega_G, Ltril_G, L64_G, hld_G, info_G = omega_prepare(Osq_G)
         kl = _zeros(Xtilde, 1, dtype=f64)
         Lk_all = torch.full((V, M, M), float("nan"), dtype=f32, device=Xtilde.device)  # NaN rows for fixed views (:237-242)
-        ws64 = _new(Xtilde, 3 * M * M, dtype=f64)
+        ws64 = _new(Xtilde, 2 * M * M, dtype=f64)
         info = _zeros(Xtilde, V, dtype=i32)
         hldK = _zeros(Xtilde, V, dtype=f64)
         saved, outs = [], []
         for k, v in enumerate(free):
             X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
             n = X.shape[0]
-            Kinv = _new(X, M, M)
-            A, B, T = _new(X, M, n), _new(X, M, n), _new(X, D, M, n)
-            Ke, var = _new(X, D, M), _new(X, n, D)
+            Kinv = _new(X, M, M, dtype=f64)
+            A, B, T = _new(X, M, n, dtype=f64), _new(X, M, n, dtype=f64), _new(X, D, M, n, dtype=f64)
+            Ke, var = _new(X, D, M, dtype=f64), _new(X, n, D)
             Gmean, Gs = _new(X, n, D), _new(X, S, n, D)
             if n > 0:
                 a = WarpFwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
                                 Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
                                 log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v,
-                                Omega_G=ptr(Omega_G), hld_Omega=ptr(hld_G), X=ptr(X), eps=ptr(eps),
-                                Lk=ptr(Lk_all) + 4 * v * M * M, Kinv=ptr(Kinv), hld_K=ptr(hldK, f64) + 8 * v,
-                                info=ptr(info, i32) + 4 * v, A=ptr(A), B=ptr(B), T=ptr(T), Ke=ptr(Ke), var=ptr(var),
+                                Omega_G=ptr(Omega_G), hld_Omega=ptr(hld_G, f64), X=ptr(X), eps=ptr(eps),
+                                Lk=ptr(Lk_all) + 4 * v * M * M, Kinv=None, Kinv64=ptr(Kinv, f64),
+                                hld_K=ptr(hldK, f64) + 8 * v, info=ptr(info, i32) + 4 * v, A=ptr(A, f64),
+                                B=ptr(B, f64), T=ptr(T, f64), Ke=ptr(Ke, f64), var=ptr(var),
                                 Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
                                 kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64))
                 check(lib().gpsa_warp_view_fwd(C.byref(a), stream()), "warp_view_fwd")
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
         ctx.meta = meta
-        ctx.save_for_backward(Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, Ltril_G, *saved)
+        ctx.save_for_backward(Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, L64_G, *saved)
         info_all = torch.cat([info_G, info])
         ctx.mark_non_differentiable(Lk_all, Ltril_G, info_all)
         return (kl.to(f32).reshape(()), Lk_all, Ltril_G, info_all, *outs)
@@ -161,7 +165,7 @@ class WarpLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, kl_bar, _1, _2, _3, *gouts):
         meta = ctx.meta
-        Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, Ltril_G, *saved = ctx.saved_tensors
+        Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, L64_G, *saved = ctx.saved_tensors
         V, M, D = Xtilde.shape
         S, free, kind = meta["S"], meta["free"], meta["kind"]
         dev = Xtilde
@@ -170,7 +174,7 @@ class WarpLayer(torch.autograd.Function):
         acc_Z, acc_dlt = _zeros(dev, V, M, D, dtype=f64), _zeros(dev, V, M, D, dtype=f64)
         acc_hyp = _zeros(dev, V, 2, dtype=f64)
         Obar = _zeros(dev, V * D, M, M)
-        Kbar, Som, T1 = _new(dev, M, M), _new(dev, M, M), _new(dev, M, M)
+        ws64 = _new(dev, 3 * M * M, dtype=f64)
         xgrads = []
         for k, v in enumerate(free):
             X, eps, Kinv, A, B, T, Ke = saved[7 * k: 7 * k + 7]
@@ -182,23 +186,25 @@ class WarpLayer(torch.autograd.Function):
             gm = _c(gm) if gm is not None else None
             gs = _c(gs) if gs is not None else None
             mubar, varbar, q1bar = _new(dev, n, D), _new(dev, n, D), _new(dev, n)
-            Abar, Cm, AS = _new(dev, M, n), _new(dev, M, n), _new(dev, D, M, n)
+            Abar, Cm, AS = (_new(dev, M, n, dtype=f64), _new(dev, M, n, dtype=f64),
+                            _new(dev, D, M, n, dtype=f64))
             a = WarpBwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
                             Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
                             log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v, Omega_G=ptr(Omega_G),
-                            X=ptr(X), eps=ptr(eps), Kinv=ptr(Kinv), A=ptr(A), B=ptr(B), T=ptr(T), Ke=ptr(Ke),
+                            X=ptr(X), eps=ptr(eps), Kinv64=ptr(Kinv, f64), A=ptr(A, f64), B=ptr(B, f64),
+                            T=ptr(T, f64), Ke=ptr(Ke, f64),
                             Gs_bar=ptr(gs), gs_stride=n * D, Gm_bar=ptr(gm), kl_bar=ptr(klb),
                             acc_Z=ptr(acc_Z, f64) + 8 * v * M * D, acc_dlt=ptr(acc_dlt, f64) + 8 * v * M * D,
                             acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
-                            mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm),
-                            AS=ptr(AS), Kbar=ptr(Kbar), Som=ptr(Som), T1=ptr(T1))
+                            mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar, f64),
+                            C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64))
             check(lib().gpsa_warp_view_bwd(C.byref(a), stream()), "warp_view_bwd")
         coef = None
         if use_kl:
             # d(-half_logdet Omega_{j*V+v})/dOmega = -1/2 Omega^-1 on the free views' KL slices only;
             # meta["kl_mask"] holds -0.5 there and 0 elsewhere (device tensor, built once by the model)
             coef = _c(meta["kl_mask"] * klb)
-        Osq_bar = omega_grad(Osq_G, Ltril_G, Obar, coef)
+        Osq_bar = omega_grad(Osq_G, L64_G, Obar, coef)
         hyp = acc_hyp.to(f32)
         return (None, acc_Z.to(f32), acc_dlt.to(f32), Osq_bar, _c(hyp[:, 0]), _c(hyp[:, 1]), *xgrads)
 
@@ -222,25 +228,27 @@ class DataLayer(torch.autograd.Function):
         R = S * N
         kind = meta["kind"]
         pre = meta.get("omega")
-        Omega, Ltril, hld, info_O = pre if pre is not None else omega_prepare(Osq_F)
-        Lk, Kinv = _new(G, M, M), _new(G, M, M)
+        Omega, Ltril, L64, hld, info_O = pre if pre is not None else omega_prepare(Osq_F)
+        Lk, Kinv, Kinv64 = _new(G, M, M), _new(G, M, M), _new(G, M, M, dtype=f64)
         hldK = _zeros(G, 1, dtype=f64)
         info = _zeros(G, 1, dtype=i32)
-        A, B, q1 = _new(G, M, R), _new(G, M, R), _new(G, R)
+        A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, R)
         W = _new(G, _lib.feat_count(M), L)
-        KD = _new(G, M, L)
+        KD = _new(G, M, L, dtype=f64)
         Fo, var = _new(G, S, N, L), _new(G, R, L)
         kl = _zeros(G, 1, dtype=f64)
-        ws64 = _new(G, 3 * M * M, dtype=f64)
+        ws64 = _new(G, 2 * M * M, dtype=f64)
         a = DataFwdArgs(kind=kind, D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls), log_var=ptr(log_var),
-                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld), G=ptr(G), eps=ptr(eps),
-                        Lk=ptr(Lk), Kinv=ptr(Kinv), hld_K=ptr(hldK, f64), info=ptr(info, i32),
-                        A=ptr(A), B=ptr(B), q1=ptr(q1), W=ptr(W), KD=ptr(KD), F=ptr(Fo), var=ptr(var),
+                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld, f64), G=ptr(G), eps=ptr(eps),
+                        Lk=ptr(Lk), Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), hld_K=ptr(hldK, f64),
+                        info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), F=ptr(Fo),
+                        var=ptr(var),
                         kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
                         engine=ENGINE["value"])
         check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
         ctx.meta = meta
-        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, Ltril, Kinv, A, B, W, KD, var)
+        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
+                              var)
         info_all = torch.cat([info_O, info])
         ctx.mark_non_differentiable(Lk, Ltril, info_all)
         return Fo, kl.to(f32).reshape(()), Lk, Ltril, info_all
@@ -248,7 +256,8 @@ class DataLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, F_bar, kl_bar, _1, _2, _3):
         meta = ctx.meta
-        Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, Ltril, Kinv, A, B, W, KD, var = ctx.saved_tensors
+        (Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
+         var) = ctx.saved_tensors
         M, D = Gtilde.shape
         L = delta_F.shape[1]
         S, N = G.shape[0], G.shape[1]
@@ -263,17 +272,18 @@ class DataLayer(torch.autograd.Function):
         Gm, q1bar = _new(dev, R, L), _new(dev, R)
         Abar, Cm = _new(dev, M, R), _new(dev, M, R)
         H = _new(dev, W.shape[0], L)
-        Kbar, Som, T1 = _new(dev, M, M), _new(dev, M, M), _new(dev, M, M)
+        ws64 = _new(dev, 3 * M * M, dtype=f64)
         a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
                         log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G), eps=ptr(eps),
-                        Kinv=ptr(Kinv), A=ptr(A), B=ptr(B), W=ptr(W), KD=ptr(KD), var=ptr(var),
+                        Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), A=ptr(A), B=ptr(B), W=ptr(W), KD=ptr(KD, f64),
+                        var=ptr(var),
                         F_bar=ptr(F_bar), kl_bar=ptr(klb), G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
                         acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar), Gm=ptr(Gm),
-                        q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), Kbar=ptr(Kbar), Som=ptr(Som),
-                        T1=ptr(T1), engine=ENGINE["value"])
+                        q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), ws64=ptr(ws64, f64),
+                        engine=ENGINE["value"])
         check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
-        Osq_bar = omega_grad(Osq_F, Ltril, Obar, coef)
+        Osq_bar = omega_grad(Osq_F, L64, Obar, coef)
         hyp = acc_hyp.to(f32)
         return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar, None
 

@@ -180,7 +180,7 @@ class VariationalGPSA(GPSA):
 
     def get_Omega_from_Omega_sqt(self, Omega_sqt):
         """Omega_sqt Omega_sqt^T + 1e-5 I (reference :206-210)."""
-        Omega, _, _, _ = _ops.omega_prepare(Omega_sqt.detach().contiguous())
+        Omega = _ops.omega_prepare(Omega_sqt.detach().contiguous())[0]
         return Omega
 
     # ----------------------------------------------------------------------------------------------
