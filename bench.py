@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Headline benchmark: VariationalGPSA fwd + loss + bwd + Adam step (one ELBO iteration) on synthetic data
+of the shapes BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  metric = spot-samples/s = iters/s x S x N_spots (BASELINE.json);
+`value` is device-timed with inputs resident in HBM, `e2e` is the same iteration driven from pinned
+HOST buffers (H2D copy of coordinates + outputs and a D2H read of the loss every step).  `roofline`
+covers the dominant kernels (the implicit-feature quadratic-form GEMMs) timed live with CUDA events
+inside the library; `cpu_baseline` is the CPU restatement of the reference (oracle/) timed on this
+box's host cores on a bounded sample.  `--impl reference` prints that CPU arm as its own line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spatial-alignment_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# id: (V, N_v, D, P, M, S, kernel)   SURVEY.md 8 / BASELINE.md 4
+CONFIGS = {
+    "c1": dict(V=2, Nv=100, D=2, P=30, M=25, S=5, kernel="rbf", desc="grid_example as shipped (synthetic stand-in, P=30, M=25)"),
+    "c2": dict(V=2, Nv=100, D=2, P=5, M=50, S=5, kernel="matern12", desc="Matern-1/2 warp+data kernels, 2 views, P=5, M=50"),
+    "c3": dict(V=4, Nv=4000, D=2, P=2000, M=200, S=8, kernel="rbf", desc="Visium-shaped synthetic: 4 views x 4k spots x 2k genes"),
+    "c4": dict(V=8, Nv=10000, D=3, P=500, M=256, S=8, kernel="rbf", desc="3-D serial sections: 8 views x 10k spots x 500 genes"),
+    "c5": dict(V=8, Nv=50000, D=2, P=5000, M=512, S=16, kernel="rbf", desc="large-N scaling: 8 views x 50k spots x 5k genes"),
+}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic data: jittered grid on [0,10]^2, views >= 1 warped by a smooth random
+# field, outputs = random-Fourier-feature draws of an RBF GP + noise, z-scored per gene per view
+# --------------------------------------------------------------------------------------------------
+def make_data(cfg, seed, genes=None):
+    rng = np.random.default_rng(seed)
+    V, Nv, D = cfg["V"], cfg["Nv"], cfg["D"]
+    P = genes if genes is not None else cfg["P"]
+    side = int(math.ceil(math.sqrt(Nv)))
+    base = np.stack(np.meshgrid(np.linspace(0, 10, side), np.linspace(0, 10, side)), -1).reshape(-1, 2)
+    Xs, Ys = [], []
+    om_w = rng.standard_normal((16, 2)) / 5.0
+    ph_w = rng.uniform(0, 2 * np.pi, 16)
+    om_y = rng.standard_normal((64, 2))
+    ph_y = rng.uniform(0, 2 * np.pi, 64)
+    W = rng.standard_normal((64, P)).astype(np.float32) * math.sqrt(2.0 / 64)
+    for v in range(V):
+        keep = rng.permutation(base.shape[0])[:Nv]
+        x = base[np.sort(keep)] + rng.uniform(-0.3, 0.3, (Nv, 2)) * (10.0 / side)
+        feats = np.cos(x @ om_y.T + ph_y).astype(np.float32)
+        y = feats @ W + 0.03 * rng.standard_normal((Nv, P)).astype(np.float32)
+        y = (y - y.mean(0)) / (y.std(0) + 1e-6)
+        if v > 0:
+            amp = rng.standard_normal((16, 2)) * 0.3 / 4.0
+            x = x + np.cos(x @ om_w.T + ph_w + v) @ amp
+        if D == 3:
+            x = np.concatenate([x, np.full((Nv, 1), float(v))], 1)
+        elif D == 1:
+            x = x[:, :1]
+        Xs.append(x.astype(np.float32))
+        Ys.append(y.astype(np.float32))
+    return np.concatenate(Xs), np.concatenate(Ys), [Nv] * V
+
+
+def flops_iter(cfg, genes=None):
+    """F_iter of BASELINE.md 4 (algorithmic, triangular-minimum, no credit for recomputation)."""
+    V, Nv, D, M, S = cfg["V"], cfg["Nv"], cfg["D"], cfg["M"], cfg["S"]
+    L = genes if genes is not None else cfg["P"]
+    N = V * Nv
+    Vf = V - 1
+    q2 = S * N * L * M * M
+    total = 3 * (q2 + 2 * S * N * M * L + 2 * S * N * M * M + Vf * Nv * M * M * (2 + D)) + 4 * (L * M**3 + V * D * M**3)
+    return float(total), 3.0 * q2
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference on the box's host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg, seed, budget_s=25.0, log=None):
+    """Times fwd + loss + bwd of the reference's algorithm (oracle/gpsa_oracle.py, float32, materialising
+    the [S,L,N,M] tensor exactly like gpsa/models/vgpsa.py:193-196) with every host thread.  Configs whose
+    full shape cannot be materialised (C3: 205 GB) are timed at a few small gene counts and extrapolated
+    linearly in the gene count, as BASELINE.md 5 prescribes.  Returns (spot_samples_per_s, description)."""
+    import torch
+
+    from oracle import gpsa_oracle as orc
+
+    torch.set_num_threads(os.cpu_count())
+    V, Nv, D, M, S = cfg["V"], cfg["Nv"], cfg["D"], cfg["M"], cfg["S"]
+    N = V * Nv
+    full_bytes = 4.0 * S * cfg["P"] * N * M
+    small = full_bytes < 2e9
+    gene_counts = [cfg["P"]] if small else [1, 2]
+    times = []
+    t_start = time.time()
+    for Pg in gene_counts:
+        X, Y, nl = make_data(cfg, seed, genes=Pg)
+        ocfg = orc.Config(n_views=V, n_spatial_dims=D, modality_names=["expression"],
+                          n_samples_lists={"expression": nl}, m_X_per_view=M, m_G=M,
+                          kernel_warp=cfg["kernel"], kernel_data=cfg["kernel"], fixed_view_idx=0,
+                          n_latent_gps={"expression": None})
+        params = orc.init_params(ocfg, {"expression": X}, {"expression": Pg}, seed=seed, kmeans=False)
+        eps = orc.draw_noise(ocfg, S, {"expression": Pg}, seed)
+        reps = []
+        for it in range(50):
+            t0 = time.perf_counter()
+            orc.elbo_and_grads(params, ocfg, {"expression": X}, {"expression": Y}, S, eps, dtype=torch.float32,
+                               materialise=True)
+            dt = time.perf_counter() - t0
+            if it > 0 or not small:
+                reps.append(dt)
+            if (small and it >= 3 and time.time() - t_start > budget_s) or (not small and it >= 1):
+                break
+        times.append(float(np.median(reps)))
+        if log is not None:
+            log.append((Pg, times[-1]))
+    if small:
+        t_full = times[0]
+        sample = f"full {cfg['desc']}: median of {len(reps)} iterations"
+    else:
+        c = (times[1] - times[0]) / (gene_counts[1] - gene_counts[0])
+        c = max(c, 1e-6)
+        t0 = times[0] - c * gene_counts[0]
+        t_full = t0 + c * cfg["P"]
+        sample = (f"P={gene_counts} genes timed ({times[0]:.2f}s, {times[1]:.2f}s per iteration; the full shape needs a "
+                  f"{full_bytes/1e9:.0f} GB [S,P,N,M] tensor), linear extrapolation to P={cfg['P']}: {t_full:.1f} s/iter")
+    return S * N / t_full, sample
+
+
+# --------------------------------------------------------------------------------------------------
+def sample_clocks(stop, out):
+    try:
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        idx = os.environ.get("LOCAL_RANK", "0")
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", idx],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    try:
+        while not stop.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            out.append(line.strip())
+    finally:
+        p.terminate()
+
+
+def summarise_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [t.strip() for t in ln.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for nm, val in zip(names, f[3:7]):
+            if val.lower().startswith("active"):
+                reasons.add(nm)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(cfg, seed, genes_slice=None, device="cuda"):
+    """Construct the public-API model on synthetic data.  Inducing locations are initialised from a random
+    subset of the spots instead of KMeans for the large configs (init is outside the timed region)."""
+    import torch
+
+    import gpsa
+
+    X, Y, nl = make_data(cfg, seed)
+    if genes_slice is not None:
+        Y = np.ascontiguousarray(Y[:, genes_slice])
+    kern = gpsa.rbf_kernel if cfg["kernel"] == "rbf" else gpsa.matern12_kernel
+    data_dict = {"expression": {"spatial_coords": torch.from_numpy(X), "outputs": torch.from_numpy(Y), "n_samples_list": nl}}
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    use_kmeans = cfg["V"] * cfg["Nv"] <= 20000
+    model = gpsa.VariationalGPSA(data_dict, n_spatial_dims=cfg["D"], m_X_per_view=cfg["M"], m_G=cfg["M"],
+                                 data_init=use_kmeans, n_latent_gps={"expression": None},
+                                 mean_function="identity_fixed", kernel_func_warp=kern, kernel_func_data=kern,
+                                 fixed_view_idx=0)
+    if not use_kmeans:
+        rng = np.random.default_rng(seed)
+        with torch.no_grad():
+            for v in range(cfg["V"]):
+                sel = rng.choice(cfg["Nv"], cfg["M"], replace=False) + v * cfg["Nv"]
+                model.Xtilde[v] = torch.from_numpy(X[sel])
+            model.delta_G_list.copy_(model.Xtilde)
+            model.Gtilde.copy_(torch.from_numpy(X[rng.choice(X.shape[0], cfg["M"], replace=False)]))
+    model = model.to(device)
+    return model, data_dict, X, Y, nl
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", type=int, default=None, help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    S, N = cfg["S"], cfg["V"] * cfg["Nv"]
+    workload = (f"{args.config}: {cfg['desc']}, D={cfg['D']}, M_X=M_G={cfg['M']}, S={cfg['S']}, {cfg['kernel']}, "
+                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rate, sample = cpu_reference_rate(cfg, args.seed)
+        line = {
+            "impl": "reference", "metric": "spot_samples_per_s", "value": rate, "unit": "spot-samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * S * N / rate,
+            "iters_per_s": rate / (S * N), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": rate, "unit": "spot-samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "spot-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gpsa import _lib, _ops
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.engine is not None:
+        _ops.ENGINE["value"] = args.engine
+
+    # gene sharding across ranks: rank r owns a contiguous slice of the output genes
+    P = cfg["P"]
+    lo, hi = (P * rank) // world, (P * (rank + 1)) // world
+    genes_slice = slice(lo, hi) if world > 1 else None
+    model, data_dict, X, Y, nl = build_model(cfg, args.seed, genes_slice)
+    if world > 1:
+        from gpsa import parallel
+
+        parallel.shard_genes(model, world, rank)
+    data_dev = {"expression": {"spatial_coords": data_dict["expression"]["spatial_coords"].cuda(),
+                               "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
+    view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    x_dev, y_dev = data_dev["expression"]["spatial_coords"], data_dev["expression"]["outputs"]
+
+    def step(it):
+        torch.manual_seed(1000 + it)
+        _, _, _, F = model.forward({"expression": x_dev}, view_idx=view_idx, Ns=Ns, S=S)
+        loss = model.loss_fn(data_dev, F)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_shared_grads(model)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(args.warmup):
+        step(it)
+    barrier()
+
+    # ---- timed region: K steps, CUDA events, inputs resident
+    lib = _lib.lib()
+    lib.gpsa_prof_enable(1)
+    clock_lines, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clock_lines), daemon=True)
+    th.start()
+    n0 = lib.gpsa_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        loss = step(args.warmup + it)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.gpsa_launch_count() - n0
+    import ctypes as C
+
+    counts = (C.c_int * 4)()
+    tot_ms = (C.c_double * 4)()
+    lib.gpsa_prof_read(counts, tot_ms)
+    lib.gpsa_prof_enable(0)
+    stop.set()
+    th.join(timeout=2)
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_step = ms / args.steps
+    value = S * N / (ms_step * 1e-3)
+
+    # ---- e2e: same iteration from pinned host buffers + D2H read of the loss, every step
+    x_pin = data_dict["expression"]["spatial_coords"].pin_memory()
+    y_pin = data_dict["expression"]["outputs"].pin_memory()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    host_loss = 0.0
+    for it in range(args.steps):
+        x_dev.copy_(x_pin, non_blocking=True)
+        y_dev.copy_(y_pin, non_blocking=True)
+        host_loss = float(step(args.warmup + args.steps + it).item())
+    t1.record()
+    barrier()
+    te = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = S * N / (float(te) / args.steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md ~1.4 PF sustained)"
+    local_genes = (hi - lo) if world > 1 else P
+    f_iter, f_q2 = flops_iter(cfg, genes=local_genes)
+    q_ms = sum(tot_ms[i] for i in range(3))
+    q_launch = sum(counts[i] for i in range(3))
+    achieved = (f_q2 * args.steps) / (q_ms * 1e-3) / 1e12 if q_ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "implicit-feature quadratic-form GEMMs (fwd + A-bar bwd + Omega-bar bwd)",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+        "peak_source": peak_src, "traffic": None,
+        "share_of_step": q_ms / ms if ms > 0 else None, "launches": int(q_launch),
+        "ms_per_launch": {"fwd": tot_ms[0] / max(counts[0], 1), "bwd_alpha": tot_ms[1] / max(counts[1], 1),
+                          "bwd_omega": tot_ms[2] / max(counts[2], 1)},
+        "engine": "fp32 SIMT (exact fp32 accumulate)" if _ops.ENGINE["value"] == 0 else "tcgen05 split-bf16",
+        "fp32_simt_peak_tflops": 74.5, "frac_of_fp32_simt": (achieved / 74.5) if achieved else None,
+        "whole_step_tflops": f_iter / (ms_step * 1e-3) / 1e12,
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, sample = cpu_reference_rate(cfg, args.seed)
+        cpu = {"value": rate, "unit": "spot-samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+    line = {
+        "metric": "spot_samples_per_s", "value": value, "unit": "spot-samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "l2": "working set (Omega_sqt 320 MB, F/eps/var 1 GB each at c3) far exceeds the 126 MB L2",
+                   "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
+        "e2e": {"value": e2e_value, "unit": "spot-samples/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": summarise_clocks(clock_lines), "loss_last": host_loss,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,15 @@ extern "C" {
 
 int gpsa_version(void);
 
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------
+ * gpsa_launch_count: kernels this library has launched so far in this process.
+ * gpsa_prof_enable(1): record CUDA events on the launching stream around the hot kernels
+ *   (slot 0 = quadratic form forward, 1 = its A-bar backward, 2 = its Omega-bar backward).
+ * gpsa_prof_read: synchronise, return per slot the number of timed launches and their total ms. */
+long gpsa_launch_count(void);
+void gpsa_prof_enable(int on);
+int gpsa_prof_read(int* counts, double* total_ms);
+
 /* ---- covariance functions -------------------------------------------------------------------
  * K[m,r] = k(x1[m], x2[r]);  x1 [M,D], x2 [R,D], K [M,R].  log_ls / log_var: device scalars.
  * Replaces rbf_kernel / matern12_kernel (gpsa/util/util.py:8-23, :33-47) as called at

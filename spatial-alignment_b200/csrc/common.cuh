@@ -13,11 +13,21 @@
 
 #define GPSA_OFF 1e-5f  // diagonal_offset, reference gpsa/models/gpsa.py:153
 
-#define GPSA_LAUNCH_CHECK()                      \
-  do {                                           \
-    cudaError_t e__ = cudaGetLastError();        \
+// Every kernel launch of the library is followed by this check; it also counts launches so that
+// bench.py can report how many of OUR kernels ran inside a timed region (gpsa_launch_count()).
+extern long g_gpsa_launches;
+#define GPSA_LAUNCH_CHECK()                       \
+  do {                                            \
+    ++g_gpsa_launches;                            \
+    cudaError_t e__ = cudaGetLastError();         \
     if (e__ != cudaSuccess) return GPSA_ERR_CUDA; \
   } while (0)
+
+// Optional in-library timing of the hot kernels with CUDA events on the launching stream
+// (gpsa_prof_enable / gpsa_prof_read).  slot: 0 = quadform fwd, 1 = quadform bwd (A-bar), 2 = quadform bwd (Omega-bar)
+#define GPSA_PROF_SLOTS 4
+void gpsa_prof_begin(int slot, cudaStream_t st);
+void gpsa_prof_end(int slot, cudaStream_t st);
 
 static inline int gpsa_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

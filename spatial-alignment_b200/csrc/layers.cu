@@ -587,9 +587,62 @@ void row_chunks(int M, long n, dim3& grid, long& chunk) {
 }  // namespace
 
 // ================================================================================================
+// launch counter and hot-kernel event profiler
+// ================================================================================================
+long g_gpsa_launches = 0;
+
+namespace {
+constexpr int PROF_RING = 1024;
+struct ProfSlot {
+  cudaEvent_t beg[PROF_RING], end[PROF_RING];
+  int n = 0;
+  bool made = false;
+};
+ProfSlot g_prof[GPSA_PROF_SLOTS];
+int g_prof_on = 0;
+}  // namespace
+
+void gpsa_prof_begin(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfSlot& p = g_prof[slot];
+  if (!p.made) {
+    for (int i = 0; i < PROF_RING; ++i) { cudaEventCreate(&p.beg[i]); cudaEventCreate(&p.end[i]); }
+    p.made = true;
+  }
+  if (p.n < PROF_RING) cudaEventRecord(p.beg[p.n], st);
+}
+void gpsa_prof_end(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfSlot& p = g_prof[slot];
+  if (p.n < PROF_RING) { cudaEventRecord(p.end[p.n], st); ++p.n; }
+}
+
+extern "C" long gpsa_launch_count(void) { return g_gpsa_launches; }
+extern "C" void gpsa_prof_enable(int on) {
+  g_prof_on = on;
+  for (int s = 0; s < GPSA_PROF_SLOTS; ++s) g_prof[s].n = 0;
+}
+// Synchronises the device; returns per slot the number of timed launches and their total milliseconds.
+extern "C" int gpsa_prof_read(int* counts, double* total_ms) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return GPSA_ERR_CUDA;
+  for (int s = 0; s < GPSA_PROF_SLOTS; ++s) {
+    double t = 0;
+    for (int i = 0; i < g_prof[s].n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_prof[s].beg[i], g_prof[s].end[i]);
+      t += ms;
+    }
+    counts[s] = g_prof[s].n;
+    total_ms[s] = t;
+    g_prof[s].n = 0;
+  }
+  return GPSA_OK;
+}
+
+// ================================================================================================
 // exported entry points
 // ================================================================================================
-extern "C" int gpsa_version(void) { return 101; }
+extern "C" int gpsa_version(void) { return 102; }
 
 extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA,
                              const float* B, long brs, long bcs, long sB, float beta, float* C, long ldc, long sC,
@@ -621,8 +674,11 @@ extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const 
   // K^-1 = X^T X
   TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv64, M, 0, 1)));
   cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
-  if (Kinv) cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kinv64, Kinv);
   GPSA_LAUNCH_CHECK();
+  if (Kinv) {
+    cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kinv64, Kinv);
+    GPSA_LAUNCH_CHECK();
+  }
   return GPSA_OK;
 }
 
@@ -784,7 +840,9 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
                                                 1)));
   TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
+  gpsa_prof_begin(0, st);
   TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
+  gpsa_prof_end(0, st);
   sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
   GPSA_LAUNCH_CHECK();
   // KD = K^-1 delta (fp64)
@@ -823,9 +881,13 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   TRY(colscale<float>(st, M, R, a->q1bar, a->B, a->Abar, 0));
   TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
                                                 R, 0, 1)));
+  gpsa_prof_begin(1, st);
   TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
+  gpsa_prof_end(1, st);
   // Omega-bar = sum_r Gm a a^T (+ 0.5 kl_bar K^-1)
+  gpsa_prof_begin(2, st);
   TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
+  gpsa_prof_end(2, st);
   TRY(gpsa_feat_unpack(M, L, a->H, a->kl_bar ? a->Kinv : nullptr, 0.5f, a->kl_bar, a->Obar, st));
   // C = K^-1 Abar ; Kbar = -K^-1 (Abar A^T) ; Bbar = C + q1bar o A
   TRY((gemm_nn<double, double, float, float>(st, M, (int)R, M, 1.0, a->Kinv64, M, a->Abar, R, 0.0, a->C, R)));

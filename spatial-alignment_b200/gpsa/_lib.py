@@ -91,6 +91,9 @@ class DataBwdArgs(C.Structure):
 # check that every symbol of include/gpsa_b200.h is exported.
 SIGNATURES = {
     "gpsa_version": [],
+    "gpsa_launch_count": [],
+    "gpsa_prof_enable": [I],
+    "gpsa_prof_read": [P, P],
     "gpsa_kernel_matrix_fwd": [I, I, I, LNG, P, P, P, P, P, P],
     "gpsa_kernel_matrix_bwd": [I, I, I, LNG, P, P, P, P, P, P, P, P, P, P],
     "gpsa_potrf_batched_f32": [I, I, P, P, P, P],
@@ -114,7 +117,7 @@ SIGNATURES = {
     "gpsa_gaussian_ll_fwd": [LNG, I, I, P, P, P, P, P],
     "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
 }
-_RESTYPE = {"gpsa_feat_count": LNG}
+_RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None}
 
 
 def _declare(l):
