@@ -22,6 +22,8 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 #endif
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -101,6 +103,25 @@ int gpsa_quadform_bwd_omega_f32(int M, long R, int L, const float* A, const floa
                                 cudaStream_t stream);
 int gpsa_quadform_bwd_alpha_f32(int M, long R, int L, const float* A, const float* G, const float* W, float* Abar,
                                 cudaStream_t stream);
+
+/* ---- tensor-core (tcgen05) engine for the same three products ------------------------------------
+ * bf16 hi/lo split operands, three MMA passes, fp32 accumulation in TMEM (error ~2^-16 per product).
+ * The forward uses the reference's own formulation q2 = ||a^T L_p||^2 with Ltril = chol(Omega)
+ * (gpsa/models/vgpsa.py:193-196); the backward products use Omega / the packed features as above.
+ * `ws` is caller-provided device scratch of at least gpsa_quadform_tc_ws_bytes(M, R, L) bytes (bf16
+ * copies of the operands); gpsa_tc_supported(M) says whether the forward kernel covers this M
+ * (16 <= M <= 256 for now).  G [R,L] = dLoss/dq2, Abar [M,R] is ADDED to, H as for the fp32 engine. */
+int gpsa_tc_supported(int M);
+size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L);
+int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws, size_t ws_bytes,
+                         cudaStream_t stream);
+int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float* G, const float* Omega, float* Abar,
+                               void* ws, size_t ws_bytes, cudaStream_t stream);
+int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, const float* G, float* H, void* ws,
+                               size_t ws_bytes, cudaStream_t stream);
+/* Plain C [Mr,Nc] = A [Mr,K] B[Nc,K]^T through the same TMA / tcgen05 / TMEM core (unit-test hook). */
+int gpsa_tc_gemm_test(int Mr, int Nc, int K, const float* A, const float* B, float* C, int split, void* ws,
+                      size_t ws_bytes, cudaStream_t stream);
 
 /* ---- warp layer, one non-fixed view -------------------------------------------------------------
  * Replaces the body of the view loop, gpsa/models/vgpsa.py:275-351 (K_uu, K_uf, compute_mean_and_var
@@ -182,6 +203,9 @@ typedef struct {
   double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
   double* ws64;           /* 2*M*M doubles */
   int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 */
+  const float* Ltril;     /* [L,M,M] chol(Omega) from gpsa_omega_prepare (engine 1 only) */
+  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  size_t tc_ws_bytes;
 } gpsa_data_fwd_args;
 int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
 
@@ -208,6 +232,8 @@ typedef struct {
   float* H;               /* [gpsa_feat_count(M), L] */
   double* ws64;           /* 3*M*M doubles */
   int engine;
+  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  size_t tc_ws_bytes;
 } gpsa_data_bwd_args;
 int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t stream);
 

@@ -642,7 +642,7 @@ extern "C" int gpsa_prof_read(int* counts, double* total_ms) {
 // ================================================================================================
 // exported entry points
 // ================================================================================================
-extern "C" int gpsa_version(void) { return 102; }
+extern "C" int gpsa_version(void) { return 103; }
 
 extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA,
                              const float* B, long brs, long bcs, long sB, float beta, float* C, long ldc, long sC,
@@ -829,7 +829,7 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   const long R = a->R;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine != 0 && (a->engine != 1 || !gpsa_tc_supported(M) || !a->Ltril || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
   TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
                          a->ws64, st));
   TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
@@ -839,10 +839,16 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
   TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
                                                 1)));
-  TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
-  gpsa_prof_begin(0, st);
-  TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
-  gpsa_prof_end(0, st);
+  if (a->engine == 0) {
+    TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
+    gpsa_prof_begin(0, st);
+    TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
+    gpsa_prof_end(0, st);
+  } else {
+    gpsa_prof_begin(0, st);
+    TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->var, a->tc_ws, a->tc_ws_bytes, st));
+    gpsa_prof_end(0, st);
+  }
   sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
   GPSA_LAUNCH_CHECK();
   // KD = K^-1 delta (fp64)
@@ -859,7 +865,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   const long R = a->R, MM = (long)M * M;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine != 0) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine != 0 && (a->engine != 1 || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
   double* Kbar = a->ws64;
   double* P = a->ws64 + MM;
   double* T1 = a->ws64 + 2 * MM;
@@ -882,11 +888,13 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
                                                 R, 0, 1)));
   gpsa_prof_begin(1, st);
-  TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
+  if (a->engine == 0) TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
+  else TRY(gpsa_quadform_bwd_alpha_tc(M, R, L, a->A, a->Gm, a->Omega, a->Abar, a->tc_ws, a->tc_ws_bytes, st));
   gpsa_prof_end(1, st);
   // Omega-bar = sum_r Gm a a^T (+ 0.5 kl_bar K^-1)
   gpsa_prof_begin(2, st);
-  TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
+  if (a->engine == 0) TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
+  else TRY(gpsa_quadform_bwd_omega_tc(M, R, L, a->A, a->Gm, a->H, a->tc_ws, a->tc_ws_bytes, st));
   gpsa_prof_end(2, st);
   TRY(gpsa_feat_unpack(M, L, a->H, a->kl_bar ? a->Kinv : nullptr, 0.5f, a->kl_bar, a->Obar, st));
   // C = K^-1 Abar ; Kbar = -K^-1 (Abar A^T) ; Bbar = C + q1bar o A

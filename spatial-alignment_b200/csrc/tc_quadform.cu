@@ -1,0 +1,883 @@
+// tcgen05 engine for the hot contraction of the path: the per-gene marginal-variance quadratic form
+//     q2[r,p] = a_r^T Omega_p a_r          (reference gpsa/models/vgpsa.py:193-196, the [S,L,N,M] bmm)
+// and its two backward products.  All three run on the 5th-generation tensor cores as bf16 x bf16 -> fp32
+// MMAs with every fp32 operand split into bf16 (hi, lo) and three passes (hi*hi + lo*hi + hi*lo), which
+// reproduces an fp32 product to ~2^-16 while keeping fp32 accumulation in TMEM.
+//
+//   forward      T_p = A_tile^T L_p  (L_p = chol(Omega_p), the reference's own formulation ||a^T L||^2):
+//                the 128-row A tile stays resident in shared memory, the transposed factor of each gene is
+//                streamed by TMA in reverse K order so that lower-triangular zeros are never multiplied
+//                (tcgen05.mma N shrinks with K), sum of squares in the epilogue straight out of TMEM.
+//   A-bar        Psi = G W^T over the packed symmetric features of Omega (feat.cu ordering), contracted with
+//                a_r in the epilogue:  Abar[:, r] += 2 (sum_p G[r,p] Omega_p) a_r.
+//   Omega-bar    H = Phi^T G with the feature operand Phi[r,(i,j)] = a_r[i] a_r[j] generated on the fly into
+//                swizzled shared memory by four generator warps (never stored), G^T streamed by TMA.
+//
+// Kernel anatomy (all three): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4), [warps 8-11 = operand generators];
+// persistent CTAs, one per SM, mbarrier full/empty rings for shared memory and for the two TMEM
+// accumulator stages.
+#include "common.cuh"
+#include "gpsa_b200.h"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int FB = 8, FBK = 64;  // feature blocks, identical to feat.cu
+__host__ __device__ inline int feat_nb(int M) { return (M + FB - 1) / FB; }
+__host__ __device__ inline long feat_nblk(int M) { const long nb = feat_nb(M); return nb * (nb + 1) / 2; }
+__device__ __forceinline__ void decode_block(int b, int nb, int& I, int& J) {
+  int i = 0, rem = b;
+  while (rem >= nb - i) { rem -= nb - i; ++i; }
+  I = i; J = i + rem;
+}
+
+constexpr int TM = 128;                       // rows of one accumulator = TMEM lanes
+constexpr int TN = 256;                       // columns of one accumulator
+constexpr int A_TILE_BYTES = TM * ROW_BYTES;  // 16 KB
+constexpr int B_TILE_BYTES = TN * ROW_BYTES;  // 32 KB
+constexpr int NSTAGE = 2;
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
+constexpr int GEMM_SMEM = NSTAGE * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+
+enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2 };
+
+struct GemmParams {
+  int n_mt, n_nt, group_m, n_split, kblocks, kb_per;
+  long Mrows, Ncols;  // logical output extent
+  float* C;           // TEST: C [Mrows, Ncols];  OMEGA: H [NF, L]
+  long ldc;
+  int accumulate;     // OMEGA/TEST: 1 = atomicAdd (split-K), 0 = plain store
+  const float* Amat;  // ALPHA/OMEGA: A [Mind, R]
+  long R;
+  int Mind, nb, nblk;
+  float* Abar;        // ALPHA: [Mind, R], added to
+};
+
+__device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& ks) {
+  const int per_split = p.n_mt * p.n_nt;
+  ks = item / per_split;
+  int w = item - ks * per_split;
+  const int gfull = p.group_m * p.n_nt;
+  const int g = w / gfull;
+  const int m0 = g * p.group_m;
+  const int gm = min(p.group_m, p.n_mt - m0);
+  w -= g * gfull;
+  nt = w / gm;
+  mt = m0 + w % gm;
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic 128 x 256 x K tile GEMM, C = (A_hi + A_lo)(B_hi + B_lo)^T in three bf16 passes
+// -------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(MODE == MODE_OMEGA ? 384 : 256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* full = bars;            // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
+  uint64_t* tfull = bars + 2 * NSTAGE;      // [2]
+  uint64_t* tempty = bars + 2 * NSTAGE + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    if (MODE != MODE_OMEGA) { prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); }
+    prefetch_tmap(&tmB_hi);
+    prefetch_tmap(&tmB_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], MODE == MODE_OMEGA ? 5 : 1);  // TMA expect_tx arrive (+ 4 generator warps)
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = p.n_mt * p.n_nt * p.n_split;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int mt, nt, ks;
+        decode_item(p, item, mt, nt, ks);
+        const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], MODE == MODE_OMEGA ? 2 * B_TILE_BYTES : STAGE_BYTES);
+          if (MODE != MODE_OMEGA) {
+            tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
+            tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
+          }
+          tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, TN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int mt, nt, ks;
+        decode_item(p, item, mt, nt, ks);
+        const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * TN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_hi = make_desc_sw128(smem_u32(st));
+          const uint64_t a_lo = make_desc_sw128(smem_u32(st + A_TILE_BYTES));
+          const uint64_t b_hi = make_desc_sw128(smem_u32(st + 2 * A_TILE_BYTES));
+          const uint64_t b_lo = make_desc_sw128(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t off = k * UMMA_K * 2;
+            umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_hi, off), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(d, desc_advance(a_lo, off), desc_advance(b_hi, off), idesc, 1u);
+            umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_lo, off), idesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int mt, nt, ks;
+      decode_item(p, item, mt, nt, ks);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+      const long row = (long)mt * TM + q * 32 + lane;
+      if (MODE == MODE_TEST || MODE == MODE_OMEGA) {
+#pragma unroll 1
+        for (int c = 0; c < TN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (row < p.Mrows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long col = (long)nt * TN + c * 32 + j;
+              if (col < p.Ncols) {
+                float* dst = p.C + row * p.ldc + col;
+                if (p.accumulate) atomicAdd(dst, __uint_as_float(v[j]));
+                else *dst = __uint_as_float(v[j]);
+              }
+            }
+          }
+        }
+      } else {  // MODE_ALPHA: Abar[:, r] += contraction of Psi[r, (i,j)] with a_r
+        const bool valid = row < p.R;
+#pragma unroll 1
+        for (int bb = 0; bb < TN / FBK; ++bb) {
+          const int b = nt * (TN / FBK) + bb;
+          if (b >= p.nblk) break;
+          int I, J;
+          decode_block(b, p.nb, I, J);
+          uint32_t v[64];
+          tmem_ld32(taddr + bb * FBK, v);
+          tmem_ld32(taddr + bb * FBK + 32, v + 32);
+          tmem_ld_wait();
+          float aI[FB], aJ[FB], sJ[FB];
+#pragma unroll
+          for (int t = 0; t < FB; ++t) {
+            const int mi = I * FB + t, mj = J * FB + t;
+            aI[t] = (valid && mi < p.Mind) ? __ldg(&p.Amat[(long)mi * p.R + row]) : 0.f;
+            aJ[t] = (valid && mj < p.Mind) ? __ldg(&p.Amat[(long)mj * p.R + row]) : 0.f;
+            sJ[t] = 0.f;
+          }
+          const bool diag = (I == J);
+#pragma unroll
+          for (int il = 0; il < FB; ++il) {
+            float si = 0.f;
+#pragma unroll
+            for (int jl = 0; jl < FB; ++jl) {
+              const float psi = __uint_as_float(v[il * FB + jl]);
+              si = fmaf(psi, aJ[jl], si);
+              sJ[jl] = fmaf(psi, aI[il], sJ[jl]);
+            }
+            const int mi = I * FB + il;
+            if (valid && mi < p.Mind) atomicAdd(&p.Abar[(long)mi * p.R + row], diag ? 2.f * si : si);
+          }
+          if (!diag) {
+#pragma unroll
+            for (int jl = 0; jl < FB; ++jl) {
+              const int mj = J * FB + jl;
+              if (valid && mj < p.Mind) atomicAdd(&p.Abar[(long)mj * p.R + row], sJ[jl]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (MODE == MODE_OMEGA && warp >= 8) {
+    // ===== feature-operand generators: A-operand row t = feature (i,j), columns = 64 consecutive r =====
+    const int t = threadIdx.x - 256;
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool vec_ok = (p.R % 4 == 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int mt, nt, ks;
+      decode_item(p, item, mt, nt, ks);
+      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      const long f = (long)mt * TM + t;
+      const int b = (int)(f / FBK);
+      bool fvalid = b < p.nblk;
+      int I = 0, J = 0;
+      if (fvalid) decode_block(b, p.nb, I, J);
+      const int mi = I * FB + (int)(f % FBK) / FB, mj = J * FB + (int)(f % FB);
+      fvalid = fvalid && mi < p.Mind && mj < p.Mind;
+      const float* ai = p.Amat + (long)mi * p.R;
+      const float* aj = p.Amat + (long)mj * p.R;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        mbar_wait(&empty[stage], phase ^ 1);
+        const long r0 = (long)kb * BK;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float x[8];
+          const long r = r0 + c * 8;
+          if (!fvalid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = 0.f;
+          } else if (vec_ok && r + 8 <= p.R) {
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ai + r));
+            const float4 u1 = __ldg(reinterpret_cast<const float4*>(ai + r + 4));
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(aj + r));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(aj + r + 4));
+            x[0] = u0.x * w0.x; x[1] = u0.y * w0.y; x[2] = u0.z * w0.z; x[3] = u0.w * w0.w;
+            x[4] = u1.x * w1.x; x[5] = u1.y * w1.y; x[6] = u1.z * w1.z; x[7] = u1.w * w1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = (r + e < p.R) ? __ldg(ai + r + e) * __ldg(aj + r + e) : 0.f;
+          }
+          uint4 hi, lo;
+          split_pair(x[0], x[1], hi.x, lo.x);
+          split_pair(x[2], x[3], hi.y, lo.y);
+          split_pair(x[4], x[5], hi.z, lo.z);
+          split_pair(x[6], x[7], hi.w, lo.w);
+          const uint32_t off = sw128_offset(t, c);
+          *reinterpret_cast<uint4*>(st + off) = hi;
+          *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward: q2[r,p] = || A_tile[r,:] L_p ||^2, A tile resident, L_p^T streamed in reverse K order
+// -------------------------------------------------------------------------------------------------
+constexpr int FWD_MAXSLOT = 4;
+struct FwdParams {
+  int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes;
+  long R;
+  float* q2;
+};
+
+__global__ void __launch_bounds__(256, 1)
+tc_qf_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB64_hi, const __grid_constant__ CUtensorMap tmB64_lo,
+                 const __grid_constant__ CUtensorMap tmB16_hi, const __grid_constant__ CUtensorMap tmB16_lo,
+                 const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA_hi = smem;                               // [nkb][128 x 64]
+  uint8_t* sA_lo = smem + p.nkb * A_TILE_BYTES;        // [nkb][128 x 64]
+  uint8_t* ring = smem + 2 * p.nkb * A_TILE_BYTES;     // [nslot][Mp x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.nslot * p.slot_bytes);
+  uint64_t* full = bars;                    // [FWD_MAXSLOT]
+  uint64_t* empty = bars + FWD_MAXSLOT;     // [FWD_MAXSLOT]
+  uint64_t* tfull = bars + 2 * FWD_MAXSLOT; // [2]
+  uint64_t* tempty = tfull + 2;             // [2]
+  uint64_t* a_full = tempty + 2;
+  uint64_t* a_empty = a_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo);
+    prefetch_tmap(&tmB64_hi); prefetch_tmap(&tmB64_lo);
+    prefetch_tmap(&tmB16_hi); prefetch_tmap(&tmB16_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = p.n_rt * p.gsplit;
+  const int Mp = p.Mp, nkb = p.nkb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t sphase = 0, aphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rt = item % p.n_rt, gs = item / p.n_rt;
+        const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+        mbar_wait(a_empty, aphase ^ 1);
+        mbar_arrive_expect_tx(a_full, 2 * nkb * A_TILE_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) {
+          tma_load_2d(sA_hi + kb * A_TILE_BYTES, &tmA_hi, a_full, kb * BK, rt * TM);
+          tma_load_2d(sA_lo + kb * A_TILE_BYTES, &tmA_lo, a_full, kb * BK, rt * TM);
+        }
+        aphase ^= 1;
+        for (int g = g0; g < g1; ++g) {
+          for (int kb = nkb - 1; kb >= 0; --kb) {
+            const int nrows = min(BK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
+            for (int half = 0; half < 2; ++half) {
+              uint8_t* dst = ring + slot * p.slot_bytes;
+              mbar_wait(&empty[slot], sphase ^ 1);
+              mbar_arrive_expect_tx(&full[slot], nrows * ROW_BYTES);
+              int row = 0;
+              for (; row + 64 <= nrows; row += 64)
+                tma_load_3d(dst + row * ROW_BYTES, half ? &tmB64_lo : &tmB64_hi, &full[slot], kb * BK, row, g);
+              for (; row < nrows; row += 16)
+                tma_load_3d(dst + row * ROW_BYTES, half ? &tmB16_lo : &tmB16_hi, &full[slot], kb * BK, row, g);
+              if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int slot = 0, acc = 0;
+      uint32_t sphase = 0, acc_phase = 0, aphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int gs = item / p.n_rt;
+        const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+        mbar_wait(a_full, aphase);
+        aphase ^= 1;
+        tc_fence_after();
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)acc * TN;
+          uint32_t accum = 0;  // the first MMA of a gene has N = Mp and initialises every column
+          for (int kb = nkb - 1; kb >= 0; --kb) {
+            const uint64_t a_hi = make_desc_sw128(smem_u32(sA_hi + kb * A_TILE_BYTES));
+            const uint64_t a_lo = make_desc_sw128(smem_u32(sA_lo + kb * A_TILE_BYTES));
+            // B_hi block: passes hi*hi and lo*hi
+            mbar_wait(&full[slot], sphase);
+            tc_fence_after();
+            const uint64_t b_hi = make_desc_sw128(smem_u32(ring + slot * p.slot_bytes));
+            for (int k = BK / UMMA_K - 1; k >= 0; --k) {
+              const int k0 = kb * BK + k * UMMA_K;
+              if (k0 >= Mp) continue;
+              const uint32_t idesc = make_idesc_bf16(TM, k0 + UMMA_K);
+              const uint32_t off = k * UMMA_K * 2;
+              umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_hi, off), idesc, accum);
+              accum = 1;
+              umma_bf16(d, desc_advance(a_lo, off), desc_advance(b_hi, off), idesc, 1u);
+            }
+            umma_commit(&empty[slot]);
+            if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+            // B_lo block: pass hi*lo
+            mbar_wait(&full[slot], sphase);
+            tc_fence_after();
+            const uint64_t b_lo = make_desc_sw128(smem_u32(ring + slot * p.slot_bytes));
+            for (int k = BK / UMMA_K - 1; k >= 0; --k) {
+              const int k0 = kb * BK + k * UMMA_K;
+              if (k0 >= Mp) continue;
+              const uint32_t idesc = make_idesc_bf16(TM, k0 + UMMA_K);
+              const uint32_t off = k * UMMA_K * 2;
+              umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_lo, off), idesc, 1u);
+            }
+            umma_commit(&empty[slot]);
+            if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+          }
+          umma_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rt = item % p.n_rt, gs = item / p.n_rt;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      const long row = (long)rt * TM + q * 32 + lane;
+      for (int g = g0; g < g1; ++g) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
+            s0 = fmaf(x, x, s0);
+            s1 = fmaf(y, y, s1);
+          }
+        }
+        if (rem16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + n32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
+            s0 = fmaf(x, x, s0);
+            s1 = fmaf(y, y, s1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (row < p.R) p.q2[row * p.L + g] = s0 + s1;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// operand packing (HBM-bound pre-passes): fp32 -> bf16 (hi, lo), K-major, zero padded
+// -------------------------------------------------------------------------------------------------
+// out[r, i] = A[i, r]     A [M, R] -> [R, Kp]
+__global__ void pack_At_kernel(int M, long R, int Kp, const float* __restrict__ A, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const long r0 = (long)blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32;
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const int i = i0 + yy;
+    const long r = r0 + threadIdx.x;
+    t[yy][threadIdx.x] = (i < M && r < R) ? A[(long)i * R + r] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const long r = r0 + yy;
+    const int i = i0 + threadIdx.x;
+    if (r < R && i < Kp) {
+      __nv_bfloat16 h, l;
+      split_one(t[threadIdx.x][yy], h, l);
+      hi[r * Kp + i] = h;
+      lo[r * Kp + i] = l;
+    }
+  }
+}
+
+// out[p, k, i] = Ltril[p, i, k]   [L, M, M] -> [L, Mp, Kp]
+__global__ void pack_Lt_kernel(int M, int Mp, int Kp, const float* __restrict__ Ltril, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const int p = blockIdx.z;
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const float* src = Ltril + (long)p * M * M;
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const int i = i0 + yy, k = k0 + threadIdx.x;
+    t[yy][threadIdx.x] = (i < M && k < M) ? src[(long)i * M + k] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const int k = k0 + yy, i = i0 + threadIdx.x;
+    if (k < Mp && i < Kp) {
+      __nv_bfloat16 h, l;
+      split_one(t[threadIdx.x][yy], h, l);
+      const long o = ((long)p * Mp + k) * Kp + i;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
+// Wt[(b, il, jl), p] = c_b Omega[p, i, j]   (c = 1 on diagonal blocks, 2 above; same ordering as feat.cu)
+__global__ void __launch_bounds__(256) pack_Wt_kernel(int M, int L, int Lp, const float* __restrict__ Omega,
+                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int nb = feat_nb(M);
+  const int b = blockIdx.x;
+  int I, J;
+  decode_block(b, nb, I, J);
+  const float c = (I == J) ? 1.f : 2.f;
+  for (int p0 = blockIdx.y * 32; p0 < L; p0 += gridDim.y * 32) {
+    for (int idx = threadIdx.x; idx < FBK * 32; idx += blockDim.x) {
+      const int pl = idx % 32, f = idx / 32;
+      const int p = p0 + pl;
+      if (p >= L) continue;
+      const int i = I * FB + f / FB, j = J * FB + f % FB;
+      const float v = (i < M && j < M) ? c * Omega[((long)p * M + i) * M + j] : 0.f;
+      __nv_bfloat16 h, l;
+      split_one(v, h, l);
+      const long o = ((long)b * FBK + f) * Lp + p;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
+// row-major split: out[r, p] = G[r, p], pitch Lp
+__global__ void pack_G_kernel(long R, int L, int Lp, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
+                              __nv_bfloat16* __restrict__ lo) {
+  const long total = R * L;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / L;
+    const int pp = (int)(idx - r * L);
+    __nv_bfloat16 h, l;
+    split_one(G[idx], h, l);
+    hi[r * Lp + pp] = h;
+    lo[r * Lp + pp] = l;
+  }
+}
+
+// transposed split: out[p, r] = G[r, p], pitch Rp
+__global__ void pack_Gt_kernel(long R, int L, long Rp, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const long r0 = (long)blockIdx.x * 32;
+  const int p0 = blockIdx.y * 32;
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const long r = r0 + yy;
+    const int pp = p0 + threadIdx.x;
+    t[yy][threadIdx.x] = (r < R && pp < L) ? G[r * L + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const int pp = p0 + yy;
+    const long r = r0 + threadIdx.x;
+    if (pp < L && r < R) {
+      __nv_bfloat16 h, l;
+      split_one(t[threadIdx.x][yy], h, l);
+      hi[(long)pp * Rp + r] = h;
+      lo[(long)pp * Rp + r] = l;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// bf16 tensor, innermost dimension contiguous, 128-byte swizzle, out-of-bounds elements read as zero
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return GPSA_ERR_CUDA;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3];
+  for (int d = 0; d < rank; ++d) { gdim[d] = dims[d]; bx[d] = box[d]; es[d] = 1; }
+  for (int d = 0; d + 1 < rank; ++d) gstr[d] = strides_bytes[d];
+  const CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? GPSA_OK : GPSA_ERR_CUDA;
+}
+int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_rows) {
+  const uint64_t dims[2] = {inner, outer}, str[1] = {pitch_elems * 2};
+  const uint32_t box[2] = {(uint32_t)BK, box_rows};
+  return make_tmap(tm, base, 2, dims, str, box);
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline long rup(long x, long m) { return (x + m - 1) / m * m; }
+
+struct FwdLayout { int Mp, Kp, nkb; size_t at, lt, total; };
+FwdLayout fwd_layout(int M, long R, int L) {
+  FwdLayout f;
+  f.Mp = (int)rup(M, 16);
+  f.nkb = (f.Mp + BK - 1) / BK;
+  f.Kp = f.nkb * BK;
+  f.at = al256((size_t)R * f.Kp * 2);
+  f.lt = al256((size_t)L * f.Mp * f.Kp * 2);
+  f.total = 2 * f.at + 2 * f.lt;
+  return f;
+}
+struct AlphaLayout { int Lp; long NF; size_t g, w, total; };
+AlphaLayout alpha_layout(int M, long R, int L) {
+  AlphaLayout a;
+  a.Lp = (int)rup(L, 8);
+  a.NF = feat_nblk(M) * FBK;
+  a.g = al256((size_t)R * a.Lp * 2);
+  a.w = al256((size_t)a.NF * a.Lp * 2);
+  a.total = 2 * a.g + 2 * a.w;
+  return a;
+}
+struct OmegaLayout { long Rp; size_t gt, total; };
+OmegaLayout omega_layout(int M, long R, int L) {
+  OmegaLayout o;
+  o.Rp = rup(R, 8);
+  o.gt = al256((size_t)L * o.Rp * 2);
+  o.total = 2 * o.gt;
+  return o;
+}
+
+template <int MODE>
+int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+      return GPSA_ERR_CUDA;
+    attr_set = true;
+  }
+  const int n_items = p.n_mt * p.n_nt * p.n_split;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  tc_gemm_kernel<MODE><<<grid, MODE == MODE_OMEGA ? 384 : 256, GEMM_SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+void set_split(GemmParams& p, int want_split) {
+  if (want_split < 1) want_split = 1;
+  if (want_split > p.kblocks) want_split = p.kblocks;
+  p.kb_per = (p.kblocks + want_split - 1) / want_split;
+  p.n_split = (p.kblocks + p.kb_per - 1) / p.kb_per;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported entry points
+// =================================================================================================
+extern "C" int gpsa_tc_supported(int M) { return (M >= 16 && M <= 256) ? 1 : 0; }
+
+extern "C" size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L) {
+  if (M <= 0 || R <= 0 || L <= 0) return 0;
+  size_t a = fwd_layout(M, R, L).total, b = alpha_layout(M, R, L).total, c = omega_layout(M, R, L).total;
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
+}
+
+// C [Mr, Nc] = A [Mr, K] B[Nc, K]^T with A, B fp32 row-major: split to bf16 in `ws`, then the tcgen05 GEMM core.
+// Exists so that the descriptor / TMA / TMEM plumbing can be unit-tested in isolation.
+extern "C" int gpsa_tc_gemm_test(int Mr, int Nc, int K, const float* A, const float* B, float* C, int split, void* ws,
+                                 size_t ws_bytes, cudaStream_t st) {
+  if (Mr <= 0 || Nc <= 0 || K <= 0) return GPSA_ERR_ARG;
+  const int Kp = (int)rup(K, 8);
+  const size_t sa = al256((size_t)Mr * Kp * 2), sb = al256((size_t)Nc * Kp * 2);
+  if (ws_bytes < 2 * sa + 2 * sb) return GPSA_ERR_ARG;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *a_hi = (__nv_bfloat16*)w, *a_lo = (__nv_bfloat16*)(w + sa), *b_hi = (__nv_bfloat16*)(w + 2 * sa),
+                *b_lo = (__nv_bfloat16*)(w + 2 * sa + sb);
+  pack_G_kernel<<<148 * 4, 256, 0, st>>>(Mr, K, Kp, A, a_hi, a_lo);
+  GPSA_LAUNCH_CHECK();
+  pack_G_kernel<<<148 * 4, 256, 0, st>>>(Nc, K, Kp, B, b_hi, b_lo);
+  GPSA_LAUNCH_CHECK();
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (make_tmap_2d(&ta_hi, a_hi, K, Mr, Kp, TM) || make_tmap_2d(&ta_lo, a_lo, K, Mr, Kp, TM) ||
+      make_tmap_2d(&tb_hi, b_hi, K, Nc, Kp, TN) || make_tmap_2d(&tb_lo, b_lo, K, Nc, Kp, TN))
+    return GPSA_ERR_CUDA;
+  GemmParams p = {};
+  p.n_mt = gpsa_cdiv(Mr, TM);
+  p.n_nt = gpsa_cdiv(Nc, TN);
+  p.group_m = p.n_mt;
+  p.kblocks = gpsa_cdiv(K, BK);
+  set_split(p, split);
+  p.Mrows = Mr; p.Ncols = Nc; p.C = C; p.ldc = Nc;
+  p.accumulate = p.n_split > 1;
+  if (p.accumulate && cudaMemsetAsync(C, 0, sizeof(float) * (size_t)Mr * Nc, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  return launch_gemm<MODE_TEST>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+}
+
+extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws,
+                                    size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
+  if (!gpsa_tc_supported(M)) return GPSA_ERR_UNSUPPORTED;
+  const FwdLayout f = fwd_layout(M, R, L);
+  if (ws_bytes < f.total) return GPSA_ERR_ARG;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *at_hi = (__nv_bfloat16*)w, *at_lo = (__nv_bfloat16*)(w + f.at), *lt_hi = (__nv_bfloat16*)(w + 2 * f.at),
+                *lt_lo = (__nv_bfloat16*)(w + 2 * f.at + f.lt);
+  {
+    dim3 grid(gpsa_cdiv(R, 32), f.Kp / 32), block(32, 8);
+    pack_At_kernel<<<grid, block, 0, st>>>(M, R, f.Kp, A, at_hi, at_lo);
+    GPSA_LAUNCH_CHECK();
+    dim3 grid2(f.Kp / 32, gpsa_cdiv(f.Mp, 32), L);
+    pack_Lt_kernel<<<grid2, block, 0, st>>>(M, f.Mp, f.Kp, Ltril, lt_hi, lt_lo);
+    GPSA_LAUNCH_CHECK();
+  }
+  CUtensorMap ta_hi, ta_lo, tb64_hi, tb64_lo, tb16_hi, tb16_lo;
+  if (make_tmap_2d(&ta_hi, at_hi, f.Mp, R, f.Kp, TM) || make_tmap_2d(&ta_lo, at_lo, f.Mp, R, f.Kp, TM)) return GPSA_ERR_CUDA;
+  {
+    const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
+    const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
+    const uint32_t box64[3] = {(uint32_t)BK, 64, 1}, box16[3] = {(uint32_t)BK, 16, 1};
+    if (make_tmap(&tb64_hi, lt_hi, 3, dims, str, box64) || make_tmap(&tb64_lo, lt_lo, 3, dims, str, box64) ||
+        make_tmap(&tb16_hi, lt_hi, 3, dims, str, box16) || make_tmap(&tb16_lo, lt_lo, 3, dims, str, box16))
+      return GPSA_ERR_CUDA;
+  }
+  FwdParams p = {};
+  p.Mp = f.Mp; p.nkb = f.nkb; p.L = L; p.R = R; p.q2 = q2;
+  p.n_rt = gpsa_cdiv(R, TM);
+  // split the gene range when there are too few row tiles to fill the machine
+  p.gsplit = 1;
+  if (p.n_rt < sm_count()) {
+    p.gsplit = (sm_count() + p.n_rt - 1) / p.n_rt;
+    if (p.gsplit > L) p.gsplit = L;
+  }
+  p.genes_per = (L + p.gsplit - 1) / p.gsplit;
+  p.gsplit = (L + p.genes_per - 1) / p.genes_per;
+  p.slot_bytes = f.Mp * ROW_BYTES;
+  const int fixed = 2 * f.nkb * A_TILE_BYTES + 1024 + 256;
+  p.nslot = (232448 - fixed) / p.slot_bytes;
+  if (p.nslot > FWD_MAXSLOT) p.nslot = FWD_MAXSLOT;
+  if (p.nslot < 2) return GPSA_ERR_UNSUPPORTED;
+  const int smem_bytes = fixed + p.nslot * p.slot_bytes;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    if (cudaFuncSetAttribute(tc_qf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return GPSA_ERR_CUDA;
+    attr_bytes = smem_bytes;
+  }
+  const int n_items = p.n_rt * p.gsplit;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  tc_qf_fwd_kernel<<<grid, 256, smem_bytes, st>>>(ta_hi, ta_lo, tb64_hi, tb64_lo, tb16_hi, tb16_lo, p);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float* G, const float* Omega,
+                                          float* Abar, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
+  const AlphaLayout a = alpha_layout(M, R, L);
+  if (ws_bytes < a.total) return GPSA_ERR_ARG;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *g_hi = (__nv_bfloat16*)w, *g_lo = (__nv_bfloat16*)(w + a.g), *w_hi = (__nv_bfloat16*)(w + 2 * a.g),
+                *w_lo = (__nv_bfloat16*)(w + 2 * a.g + a.w);
+  pack_G_kernel<<<148 * 8, 256, 0, st>>>(R, L, a.Lp, G, g_hi, g_lo);
+  GPSA_LAUNCH_CHECK();
+  {
+    dim3 grid((unsigned)feat_nblk(M), (unsigned)((L + 31) / 32 < 64 ? (L + 31) / 32 : 64));
+    pack_Wt_kernel<<<grid, 256, 0, st>>>(M, L, a.Lp, Omega, w_hi, w_lo);
+    GPSA_LAUNCH_CHECK();
+  }
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (make_tmap_2d(&ta_hi, g_hi, L, R, a.Lp, TM) || make_tmap_2d(&ta_lo, g_lo, L, R, a.Lp, TM) ||
+      make_tmap_2d(&tb_hi, w_hi, L, a.NF, a.Lp, TN) || make_tmap_2d(&tb_lo, w_lo, L, a.NF, a.Lp, TN))
+    return GPSA_ERR_CUDA;
+  GemmParams p = {};
+  p.n_mt = gpsa_cdiv(R, TM);
+  p.n_nt = gpsa_cdiv(a.NF, TN);
+  p.group_m = 32;  // 32 row tiles of G (hi+lo) stay L2-resident while the feature chunks sweep past
+  if (p.group_m > p.n_mt) p.group_m = p.n_mt;
+  p.kblocks = gpsa_cdiv(L, BK);
+  set_split(p, 1);
+  p.Mrows = R; p.Ncols = a.NF;
+  p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M); p.Abar = Abar;
+  return launch_gemm<MODE_ALPHA>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+}
+
+extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, const float* G, float* H, void* ws,
+                                          size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
+  const OmegaLayout o = omega_layout(M, R, L);
+  if (ws_bytes < o.total) return GPSA_ERR_ARG;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *gt_hi = (__nv_bfloat16*)w, *gt_lo = (__nv_bfloat16*)(w + o.gt);
+  {
+    dim3 grid(gpsa_cdiv(R, 32), gpsa_cdiv(L, 32)), block(32, 8);
+    pack_Gt_kernel<<<grid, block, 0, st>>>(R, L, o.Rp, G, gt_hi, gt_lo);
+    GPSA_LAUNCH_CHECK();
+  }
+  CUtensorMap tb_hi, tb_lo;
+  if (make_tmap_2d(&tb_hi, gt_hi, R, L, o.Rp, TN) || make_tmap_2d(&tb_lo, gt_lo, R, L, o.Rp, TN)) return GPSA_ERR_CUDA;
+  const long NF = feat_nblk(M) * FBK;
+  GemmParams p = {};
+  p.n_mt = gpsa_cdiv(NF, TM);
+  p.n_nt = gpsa_cdiv(L, TN);
+  p.group_m = p.n_mt;  // all feature tiles of one gene chunk run together: the G^T slab is shared through L2
+  p.kblocks = gpsa_cdiv(R, BK);
+  // split K (spots) until the grid fills the machine a few times over
+  const int tiles = p.n_mt * p.n_nt;
+  int split = 1;
+  if (tiles < 4 * sm_count()) split = (4 * sm_count() + tiles - 1) / tiles;
+  const int max_split = p.kblocks / 16 > 0 ? p.kblocks / 16 : 1;
+  if (split > max_split) split = max_split;
+  set_split(p, split);
+  p.Mrows = NF; p.Ncols = L; p.C = H; p.ldc = L;
+  p.accumulate = p.n_split > 1;
+  if (p.accumulate && cudaMemsetAsync(H, 0, sizeof(float) * (size_t)NF * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
+  return launch_gemm<MODE_OMEGA>(tb_hi, tb_lo, tb_hi, tb_lo, p, st);
+}

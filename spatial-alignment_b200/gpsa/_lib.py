@@ -71,7 +71,7 @@ class DataFwdArgs(C.Structure):
         ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P), ("eps", P),
         ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
         ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("F", P), ("var", P),
-        ("kl_acc", P), ("ws64", P), ("engine", I),
+        ("kl_acc", P), ("ws64", P), ("engine", I), ("Ltril", P), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
     ]
 
 
@@ -83,7 +83,7 @@ class DataBwdArgs(C.Structure):
         ("F_bar", P), ("kl_bar", P),
         ("G_bar", P), ("acc_Gt", P), ("acc_hyp", P), ("dlt_bar", P), ("Obar", P),
         ("Gm", P), ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("ws64", P),
-        ("engine", I),
+        ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
     ]
 
 
@@ -110,6 +110,12 @@ SIGNATURES = {
     "gpsa_quadform_fwd_f32": [I, LNG, I, P, P, P, P],
     "gpsa_quadform_bwd_omega_f32": [I, LNG, I, P, P, P, P],
     "gpsa_quadform_bwd_alpha_f32": [I, LNG, I, P, P, P, P, P],
+    "gpsa_tc_supported": [I],
+    "gpsa_quadform_tc_ws_bytes": [I, LNG, I],
+    "gpsa_quadform_fwd_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
+    "gpsa_quadform_bwd_alpha_tc": [I, LNG, I, P, P, P, P, P, C.c_size_t, P],
+    "gpsa_quadform_bwd_omega_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
+    "gpsa_tc_gemm_test": [I, I, I, P, P, P, I, P, C.c_size_t, P],
     "gpsa_warp_view_fwd": [C.POINTER(WarpFwdArgs), P],
     "gpsa_warp_view_bwd": [C.POINTER(WarpBwdArgs), P],
     "gpsa_data_layer_fwd": [C.POINTER(DataFwdArgs), P],
@@ -117,7 +123,8 @@ SIGNATURES = {
     "gpsa_gaussian_ll_fwd": [LNG, I, I, P, P, P, P, P],
     "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
 }
-_RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None}
+_RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None,
+            "gpsa_quadform_tc_ws_bytes": C.c_size_t}
 
 
 def _declare(l):
@@ -151,3 +158,9 @@ def ptr(t, dtype=torch.float32):
 
 def feat_count(M):
     return int(lib().gpsa_feat_count(int(M)))
+
+
+def tc_workspace(M, R, L, like):
+    """Scratch for the tcgen05 engine (bf16 hi/lo copies of the operands), as a uint8 CUDA tensor."""
+    n = int(lib().gpsa_quadform_tc_ws_bytes(int(M), int(R), int(L)))
+    return torch.empty(n, dtype=torch.uint8, device=like.device)

@@ -12,8 +12,18 @@ f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
 KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12}
 
-# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16
-ENGINE = {"value": 0}
+# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16, "auto" = tcgen05 whenever the shape can
+# fill 128-row MMA tiles (the SIMT engine stays for the launch-bound toy configurations)
+ENGINE = {"value": "auto"}
+
+
+def pick_engine(M, R, L):
+    e = ENGINE["value"]
+    if e == "auto":
+        return 1 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
+    if e == 1 and not lib().gpsa_tc_supported(int(M)):
+        raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} yet (16 <= M <= 256)")
+    return int(e)
 
 
 def _c(t):
@@ -233,7 +243,9 @@ class DataLayer(torch.autograd.Function):
         hldK = _zeros(G, 1, dtype=f64)
         info = _zeros(G, 1, dtype=i32)
         A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, R)
-        W = _new(G, _lib.feat_count(M), L)
+        engine = pick_engine(M, R, L)
+        W = _new(G, _lib.feat_count(M), L) if engine == 0 else _new(G, 1)
+        tc_ws = _lib.tc_workspace(M, R, L, G) if engine == 1 else None
         KD = _new(G, M, L, dtype=f64)
         Fo, var = _new(G, S, N, L), _new(G, R, L)
         kl = _zeros(G, 1, dtype=f64)
@@ -244,9 +256,11 @@ class DataLayer(torch.autograd.Function):
                         info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), F=ptr(Fo),
                         var=ptr(var),
                         kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
-                        engine=ENGINE["value"])
+                        engine=engine, Ltril=ptr(Ltril), tc_ws=ptr(tc_ws, torch.uint8),
+                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
         check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
         ctx.meta = meta
+        ctx.engine = engine
         ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
                               var)
         info_all = torch.cat([info_O, info])
@@ -271,7 +285,9 @@ class DataLayer(torch.autograd.Function):
         dlt_bar, Obar = _new(dev, M, L), _new(dev, L, M, M)
         Gm, q1bar = _new(dev, R, L), _new(dev, R)
         Abar, Cm = _new(dev, M, R), _new(dev, M, R)
-        H = _new(dev, W.shape[0], L)
+        engine = ctx.engine
+        H = _new(dev, _lib.feat_count(M), L)
+        tc_ws = _lib.tc_workspace(M, R, L, dev) if engine == 1 else None
         ws64 = _new(dev, 3 * M * M, dtype=f64)
         a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
                         log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G), eps=ptr(eps),
@@ -280,7 +296,8 @@ class DataLayer(torch.autograd.Function):
                         F_bar=ptr(F_bar), kl_bar=ptr(klb), G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
                         acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar), Gm=ptr(Gm),
                         q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), ws64=ptr(ws64, f64),
-                        engine=ENGINE["value"])
+                        engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
+                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
         check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
         Osq_bar = omega_grad(Osq_F, L64, Obar, coef)

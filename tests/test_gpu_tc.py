@@ -1,0 +1,135 @@
+"""tcgen05 engine parity (-m gpu): the TMA / tcgen05 / TMEM GEMM core and the three quadratic-form products
+built on it, each called through the C ABI and compared with a float64 torch evaluation of the same
+expression.  Tolerance: the engine multiplies bf16 (hi, lo) splits in three passes, i.e. each product
+carries ~2^-16 relative error instead of fp32's 2^-24; sums of K such terms are checked scale-relative
+(max |err| / max |ref|) at 1e-4, the tolerance BASELINE.json's north_star states for the ELBO path."""
+import ctypes as C
+
+import pytest
+import torch
+
+from golden_io import relerr
+
+pytestmark = pytest.mark.gpu
+
+f32, f64, u8 = torch.float32, torch.float64, torch.uint8
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def L():
+    from gpsa import _lib
+
+    assert torch.cuda.is_available()
+    return _lib
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ws_for(L, M, R, Lg):
+    return L.tc_workspace(M, R, Lg, torch.empty(1, device="cuda"))
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Mr,Nc,K,split", [(128, 256, 64, 1), (128, 256, 256, 1), (300, 500, 200, 1),
+                                           (1000, 700, 1000, 3), (77, 19, 33, 1), (513, 1030, 4100, 4)])
+def test_gemm_core(L, Mr, Nc, K, split):
+    g = torch.Generator().manual_seed(Mr + Nc + K)
+    A = torch.randn(Mr, K, generator=g)
+    B = torch.randn(Nc, K, generator=g)
+    ref = A.double() @ B.double().T
+    a, b = A.cuda(), B.cuda()
+    c = torch.full((Mr, Nc), float("nan"), device="cuda")
+    ws = torch.empty(4 * (Mr + Nc) * (K + 8) + 4096, dtype=u8, device="cuda")
+    rc = L.lib().gpsa_tc_gemm_test(Mr, Nc, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), split, ws.data_ptr(), ws.numel(),
+                                   stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    err = relerr(c.cpu(), ref)
+    assert err < 2e-5, err
+
+
+def _problem(M, R, Lg, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, R, generator=g) * 0.3
+    Osq = torch.randn(Lg, M, M, generator=g) * 0.1
+    G = torch.randn(R, Lg, generator=g)
+    return A, Osq, G
+
+
+@pytest.mark.parametrize("M,R,Lg", [(64, 128, 1), (64, 1000, 5), (200, 700, 37), (256, 2049, 9), (50, 300, 3),
+                                    (100, 4096, 300)])
+def test_quadform_tc_fwd_bwd(L, M, R, Lg):
+    from gpsa import _ops
+
+    A, Osq, G = _problem(M, R, Lg, M * 7 + R)
+    Omega, Ltril, L64, hld, info = _ops.omega_prepare(Osq.cuda())
+    Ad = A.double().requires_grad_()
+    Omd = Omega.double().cpu().requires_grad_()
+    q2r = torch.einsum("mr,pmk,kr->rp", Ad, Omd, Ad)
+    (q2r * G.double()).sum().backward()
+
+    lib = L.lib()
+    assert lib.gpsa_tc_supported(M) == 1
+    a, gg = A.cuda(), G.cuda()
+    ws = ws_for(L, M, R, Lg)
+    q2 = torch.full((R, Lg), float("nan"), device="cuda")
+    assert lib.gpsa_quadform_fwd_tc(M, R, Lg, a.data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    stream()) == 0
+    torch.cuda.synchronize()
+    assert relerr(q2.cpu(), q2r.detach()) < TOL
+
+    nf = L.feat_count(M)
+    H = torch.full((nf, Lg), float("nan"), device="cuda")
+    Obar = torch.empty(Lg, M, M, device="cuda")
+    assert lib.gpsa_quadform_bwd_omega_tc(M, R, Lg, a.data_ptr(), gg.data_ptr(), H.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          stream()) == 0
+    assert lib.gpsa_feat_unpack(M, Lg, H.data_ptr(), None, 0.0, None, Obar.data_ptr(), stream()) == 0
+    torch.cuda.synchronize()
+    assert relerr(Obar.cpu(), Omd.grad) < TOL
+
+    Abar = torch.zeros(M, R, device="cuda")
+    assert lib.gpsa_quadform_bwd_alpha_tc(M, R, Lg, a.data_ptr(), gg.data_ptr(), Omega.data_ptr(), Abar.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), stream()) == 0
+    torch.cuda.synchronize()
+    assert relerr(Abar.cpu(), Ad.grad) < TOL
+
+
+def test_tc_unsupported_M(L):
+    lib = L.lib()
+    assert lib.gpsa_tc_supported(512) == 0
+    x = torch.zeros(16, device="cuda")
+    assert lib.gpsa_quadform_fwd_tc(512, 128, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, stream()) == 3
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern12"])
+def test_data_layer_engines_agree(L, kind):
+    """The whole data layer (forward samples, KL, every gradient) with the tcgen05 engine against the fp32
+    SIMT engine on the same inputs."""
+    from gpsa import _ops
+
+    g = torch.Generator().manual_seed(11)
+    M, D, Lg, S, N = 64, 2, 24, 2, 1500
+    Gt = torch.rand(M, D, generator=g) * 10
+    G = torch.rand(S, N, D, generator=g) * 10
+    Osq = torch.randn(Lg, M, M, generator=g) * 0.1
+    dlt = torch.randn(M, Lg, generator=g)
+    eps = torch.randn(S, N, Lg, generator=g)
+    Fbar = torch.randn(S, N, Lg, generator=g)
+    ls, var = torch.tensor([0.3]), torch.tensor([0.1])
+    outs = {}
+    for engine in (0, 1):
+        _ops.ENGINE["value"] = engine
+        try:
+            leaves = [t.clone().cuda().requires_grad_() for t in (Gt, ls, var, dlt, Osq, G)]
+            F, kl, Lk, Ltril, info = _ops.DataLayer.apply({"kind": _ops.KINDS[kind], "with_kl": True}, *leaves[:5],
+                                                          leaves[5], eps.cuda())
+            ((F * Fbar.cuda()).sum() + kl).backward()
+            outs[engine] = [F.detach().cpu(), kl.detach().cpu()] + [t.grad.cpu() for t in leaves]
+        finally:
+            _ops.ENGINE["value"] = "auto"
+    names = ["F", "kl", "Gtilde", "log_ls", "log_var", "delta", "Omega_sqt", "G"]
+    for name, x0, x1 in zip(names, outs[0], outs[1]):
+        assert relerr(x1, x0) < 2e-4, name

@@ -116,7 +116,7 @@ def test_library_exports_every_declared_symbol():
     from gpsa import _lib
 
     header = open(os.path.join(ROOT, "include", "gpsa_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|long|void)\s+(gpsa_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|long|void|size_t)\s+(gpsa_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     if not os.path.exists(_lib.LIB_PATH):
         pytest.skip("library not built (run __graft_entry__.build())")
