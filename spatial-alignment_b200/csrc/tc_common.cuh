@@ -146,6 +146,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)LAYOUT_SW128 << 61;
   return d;
 }
+// same for the 64-byte swizzle: rows of 32 bf16 (64 B), 16-byte chunk index XOR ((row >> 1) & 3), 8-row groups 512 B apart
+constexpr uint32_t LAYOUT_SW64 = 4;
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)LAYOUT_SW64 << 61;
+  return d;
+}
 // advance a descriptor by `bytes` inside the tile (K-step of 16 elements = 32 bytes; 8-row groups = 1024 bytes)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 

@@ -11,15 +11,18 @@
 //   A-bar        Psi = G W^T over the packed symmetric features of Omega (feat.cu ordering), contracted with
 //                a_r in the epilogue:  Abar[:, r] += 2 (sum_p G[r,p] Omega_p) a_r.
 //   Omega-bar    H = Phi^T G with the feature operand Phi[r,(i,j)] = a_r[i] a_r[j] generated on the fly into
-//                swizzled shared memory by four generator warps (never stored), G^T streamed by TMA.
+//                swizzled shared memory by eight generator warps (never stored) from TMA-staged rows of A,
+//                G^T streamed by TMA.
 //
 // Kernel anatomy (all three): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4), [warps 8-11 = operand generators];
+// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4), [warps 8-15 = operand generators];
 // persistent CTAs, one per SM, mbarrier full/empty rings for shared memory and for the two TMEM
 // accumulator stages.
 #include "common.cuh"
 #include "gpsa_b200.h"
 #include "tc_common.cuh"
+
+#include <stdlib.h>
 
 using namespace tc;
 
@@ -39,10 +42,14 @@ constexpr int TN = 256;                       // columns of one accumulator
 constexpr int A_TILE_BYTES = TM * ROW_BYTES;  // 16 KB
 constexpr int B_TILE_BYTES = TN * ROW_BYTES;  // 32 KB
 constexpr int NSTAGE = 2;
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
-constexpr int GEMM_SMEM = NSTAGE * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int OPER_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
+constexpr int RAW_BYTES = 8192;  // Omega-bar only: 4 row groups x 2 halves of [8 rows x 32 r] fp32, 128B-swizzled
 
 enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2 };
+constexpr int N_GEN_WARPS = 8;
+__host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode == MODE_OMEGA ? RAW_BYTES : 0); }
+__host__ __device__ constexpr int gemm_smem(int mode) { return NSTAGE * stage_bytes(mode) + 1024 /*alignment*/ + 256 /*barriers*/; }
+__host__ __device__ constexpr int gemm_threads(int mode) { return mode == MODE_OMEGA ? 256 + 32 * N_GEN_WARPS : 256; }
 
 struct GemmParams {
   int n_mt, n_nt, group_m, n_split, kblocks, kb_per;
@@ -72,11 +79,13 @@ __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& 
 // -------------------------------------------------------------------------------------------------
 // generic 128 x 256 x K tile GEMM, C = (A_hi + A_lo)(B_hi + B_lo)^T in three bf16 passes
 // -------------------------------------------------------------------------------------------------
+// In MODE_OMEGA tmA_hi is the fp32 map of A [M, R] (box 32 r x 8 rows) the generators read from; tmA_lo is unused.
 template <int MODE>
-__global__ void __launch_bounds__(MODE == MODE_OMEGA ? 384 : 256, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const GemmParams p) {
+  constexpr int STAGE_BYTES = stage_bytes(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
@@ -84,18 +93,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
   uint64_t* tfull = bars + 2 * NSTAGE;      // [2]
   uint64_t* tempty = bars + 2 * NSTAGE + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  uint64_t* rawfull = bars + 2 * NSTAGE + 4; // [NSTAGE]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NSTAGE + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    if (MODE != MODE_OMEGA) { prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); }
+    prefetch_tmap(&tmA_hi);
+    if (MODE != MODE_OMEGA) prefetch_tmap(&tmA_lo);
     prefetch_tmap(&tmB_hi);
     prefetch_tmap(&tmB_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], MODE == MODE_OMEGA ? 5 : 1);  // TMA expect_tx arrive (+ 4 generator warps)
+      mbar_init(&full[s], MODE == MODE_OMEGA ? 1 + N_GEN_WARPS : 1);  // TMA expect_tx arrive (+ generator warps)
       mbar_init(&empty[s], 1);
+      mbar_init(&rawfull[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
@@ -107,64 +119,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = p.n_mt * p.n_nt * p.n_split;
 
+  // Producer and MMA warps run converged (all lanes wait on the barriers, loop state is warp-uniform); only the
+  // TMA / MMA issue is predicated on elect.sync, which keeps the single issuing thread's instruction stream short.
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int mt, nt, ks;
-        decode_item(p, item, mt, nt, ks);
-        const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], MODE == MODE_OMEGA ? 2 * B_TILE_BYTES : STAGE_BYTES);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int mt, nt, ks;
+      decode_item(p, item, mt, nt, ks);
+      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      int grow[4] = {0, 0, 0, 0};  // MODE_OMEGA: first A row of the (I, J) index groups of the tile's two feature blocks
+      if (MODE == MODE_OMEGA) {
+        for (int q = 0; q < 2; ++q) {
+          const int b = mt * (TM / FBK) + q;
+          int I = p.nb, J = p.nb;  // out of range -> rows >= M -> zero filled
+          if (b < p.nblk) decode_block(b, p.nb, I, J);
+          grow[2 * q] = I * FB;
+          grow[2 * q + 1] = J * FB;
+        }
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], MODE == MODE_OMEGA ? 2 * B_TILE_BYTES : OPER_BYTES);
           if (MODE != MODE_OMEGA) {
             tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
             tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
+          } else {
+            mbar_arrive_expect_tx(&rawfull[stage], RAW_BYTES);
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                tma_load_2d(st + OPER_BYTES + (gq * 2 + h) * 1024, &tmA_hi, &rawfull[stage], kb * BK + h * 32, grow[gq]);
           }
           tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
           tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(TM, TN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int mt, nt, ks;
-        decode_item(p, item, mt, nt, ks);
-        const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    const uint32_t idesc = make_idesc_bf16(TM, TN);
+    const uint64_t desc0 = make_desc_sw128(smem_u32(smem));
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int mt, nt, ks;
+      decode_item(p, item, mt, nt, ks);
+      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)acc * TN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)acc * TN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t a_hi = make_desc_sw128(smem_u32(st));
-          const uint64_t a_lo = make_desc_sw128(smem_u32(st + A_TILE_BYTES));
-          const uint64_t b_hi = make_desc_sw128(smem_u32(st + 2 * A_TILE_BYTES));
-          const uint64_t b_lo = make_desc_sw128(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES));
+        if (elect_one()) {
+          const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
+          const uint64_t a_lo = a_hi + (A_TILE_BYTES >> 4);
+          const uint64_t b_hi = a_hi + (2 * A_TILE_BYTES >> 4);
+          const uint64_t b_lo = b_hi + (B_TILE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t off = k * UMMA_K * 2;
-            umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_hi, off), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_bf16(d, desc_advance(a_lo, off), desc_advance(b_hi, off), idesc, 1u);
-            umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_lo, off), idesc, 1u);
+            const uint32_t off = (k * UMMA_K * 2) >> 4;
+            umma_bf16(d, a_hi + off, b_hi + off, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(d, a_lo + off, b_hi + off, idesc, 1u);
+            umma_bf16(d, a_hi + off, b_lo + off, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue =====
@@ -245,52 +279,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (MODE == MODE_OMEGA && warp >= 8) {
-    // ===== feature-operand generators: A-operand row t = feature (i,j), columns = 64 consecutive r =====
-    const int t = threadIdx.x - 256;
+    // ===== feature-operand generators =====
+    // A-operand row t = feature (i, j) of the tile, columns = 64 consecutive r:  phi = a_i[r] a_j[r], split to bf16
+    // (hi, lo) and written in the swizzled K-major layout.  The raw a rows arrive by TMA (128B-swizzled
+    // [8 rows x 32 r] fp32 boxes, so the 8 rows a quarter-warp reads at one column land in 8 different bank groups).
+    const int gt = threadIdx.x - 256;
+    const int t = gt & (TM - 1);   // feature row of the tile
+    const int h = gt >> 7;         // which half of the 64 r of a K block
+    const int bq = t / FBK, il = (t % FBK) / FB, jl = t % FB;
+    const uint32_t raw_i = OPER_BYTES + ((2 * bq) * 2 + h) * 1024 + il * 128;
+    const uint32_t raw_j = OPER_BYTES + ((2 * bq + 1) * 2 + h) * 1024 + jl * 128;
     int stage = 0;
     uint32_t phase = 0;
-    const bool vec_ok = (p.R % 4 == 0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
       const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
-      const long f = (long)mt * TM + t;
-      const int b = (int)(f / FBK);
-      bool fvalid = b < p.nblk;
-      int I = 0, J = 0;
-      if (fvalid) decode_block(b, p.nb, I, J);
-      const int mi = I * FB + (int)(f % FBK) / FB, mj = J * FB + (int)(f % FB);
-      fvalid = fvalid && mi < p.Mind && mj < p.Mind;
-      const float* ai = p.Amat + (long)mi * p.R;
-      const float* aj = p.Amat + (long)mj * p.R;
       for (int kb = kb0; kb < kb1; ++kb) {
         uint8_t* st = smem + stage * STAGE_BYTES;
-        mbar_wait(&empty[stage], phase ^ 1);
-        const long r0 = (long)kb * BK;
+        mbar_wait(&rawfull[stage], phase);  // armed only after the MMA released this stage
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float x[8];
-          const long r = r0 + c * 8;
-          if (!fvalid) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.f;
-          } else if (vec_ok && r + 8 <= p.R) {
-            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ai + r));
-            const float4 u1 = __ldg(reinterpret_cast<const float4*>(ai + r + 4));
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(aj + r));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(aj + r + 4));
-            x[0] = u0.x * w0.x; x[1] = u0.y * w0.y; x[2] = u0.z * w0.z; x[3] = u0.w * w0.w;
-            x[4] = u1.x * w1.x; x[5] = u1.y * w1.y; x[6] = u1.z * w1.z; x[7] = u1.w * w1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = (r + e < p.R) ? __ldg(ai + r + e) * __ldg(aj + r + e) : 0.f;
-          }
+        for (int c = 0; c < 4; ++c) {  // output chunk 4h + c = 8 consecutive r = raw chunks 2c, 2c+1 of this half
+          const float4 u0 = *reinterpret_cast<const float4*>(st + raw_i + (((2 * c) ^ il) << 4));
+          const float4 u1 = *reinterpret_cast<const float4*>(st + raw_i + (((2 * c + 1) ^ il) << 4));
+          const float4 w0 = *reinterpret_cast<const float4*>(st + raw_j + (((2 * c) ^ jl) << 4));
+          const float4 w1 = *reinterpret_cast<const float4*>(st + raw_j + (((2 * c + 1) ^ jl) << 4));
           uint4 hi, lo;
-          split_pair(x[0], x[1], hi.x, lo.x);
-          split_pair(x[2], x[3], hi.y, lo.y);
-          split_pair(x[4], x[5], hi.z, lo.z);
-          split_pair(x[6], x[7], hi.w, lo.w);
-          const uint32_t off = sw128_offset(t, c);
+          split_pair(u0.x * w0.x, u0.y * w0.y, hi.x, lo.x);
+          split_pair(u0.z * w0.z, u0.w * w0.w, hi.y, lo.y);
+          split_pair(u1.x * w1.x, u1.y * w1.y, hi.z, lo.z);
+          split_pair(u1.z * w1.z, u1.w * w1.w, hi.w, lo.w);
+          const uint32_t off = sw128_offset(t, 4 * h + c);
           *reinterpret_cast<uint4*>(st + off) = hi;
           *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off) = lo;
         }
@@ -312,23 +331,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // -------------------------------------------------------------------------------------------------
 // forward: q2[r,p] = || A_tile[r,:] L_p ||^2, A tile resident, L_p^T streamed in reverse K order
 // -------------------------------------------------------------------------------------------------
-constexpr int FWD_MAXSLOT = 4;
+// This kernel uses the 64-byte swizzle (K blocks of 32): the triangular factor is trimmed at 32-column
+// granularity (25 % less L2 -> shared traffic than 64-column blocks) and the ring has 6-8 slots, enough bytes in
+// flight to cover the TMA latency with the 112-128 KB resident A tile next to it.
+constexpr int FK = 32;                 // K elements per block
+constexpr int FROW = 64;               // bytes per operand row
+constexpr int FA_BYTES = TM * FROW;    // one A slab: 8 KB
+constexpr int FWD_MAXSLOT = 8;
 struct FwdParams {
   int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes;
   long R;
   float* q2;
+  int dbg;  // timing experiments only (GPSA_TC_DBG): 1 = dense N, 2 = no epilogue TMEM reads, 4 = no B loads
+};
+struct FwdMaps {
+  CUtensorMap a_hi, a_lo;    // At [R, Kp], box 32 x 128
+  CUtensorMap b_hi[4], b_lo[4];  // Lt [L, Mp, Kp], boxes 32 x {128, 64, 32, 16} x 1
 };
 
-__global__ void __launch_bounds__(256, 1)
-tc_qf_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmB64_hi, const __grid_constant__ CUtensorMap tmB64_lo,
-                 const __grid_constant__ CUtensorMap tmB16_hi, const __grid_constant__ CUtensorMap tmB16_lo,
-                 const FwdParams p) {
+__global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA_hi = smem;                               // [nkb][128 x 64]
-  uint8_t* sA_lo = smem + p.nkb * A_TILE_BYTES;        // [nkb][128 x 64]
-  uint8_t* ring = smem + 2 * p.nkb * A_TILE_BYTES;     // [nslot][Mp x 64]
+  uint8_t* sA_hi = smem;                           // [nkb][128 x 32]
+  uint8_t* sA_lo = smem + p.nkb * FA_BYTES;        // [nkb][128 x 32]
+  uint8_t* ring = smem + 2 * p.nkb * FA_BYTES;     // [nslot][hi: Mp x 32 | lo: Mp x 32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.nslot * p.slot_bytes);
   uint64_t* full = bars;                    // [FWD_MAXSLOT]
   uint64_t* empty = bars + FWD_MAXSLOT;     // [FWD_MAXSLOT]
@@ -340,9 +366,9 @@ tc_qf_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo);
-    prefetch_tmap(&tmB64_hi); prefetch_tmap(&tmB64_lo);
-    prefetch_tmap(&tmB16_hi); prefetch_tmap(&tmB16_lo);
+    prefetch_tmap(&tm.a_hi);
+    prefetch_tmap(&tm.a_lo);
+    for (int i = 0; i < 4; ++i) { prefetch_tmap(&tm.b_hi[i]); prefetch_tmap(&tm.b_lo[i]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -359,91 +385,102 @@ tc_qf_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int n_items = p.n_rt * p.gsplit;
   const int Mp = p.Mp, nkb = p.nkb;
 
+  // Producer and MMA warps run their loops CONVERGED (every lane waits on the barriers, all loop state is
+  // warp-uniform) and only the issue itself is predicated on elect.sync: the issuing thread of this kernel
+  // has ~60 cycles per MMA, so its instruction stream has to stay short.
   if (warp == 0) {
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t sphase = 0, aphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rt = item % p.n_rt, gs = item / p.n_rt;
-        const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-        mbar_wait(a_empty, aphase ^ 1);
-        mbar_arrive_expect_tx(a_full, 2 * nkb * A_TILE_BYTES);
+    int slot = 0;
+    uint32_t sphase = 0, aphase = 0;
+    const int half_bytes = p.slot_bytes >> 1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rt = item % p.n_rt, gs = item / p.n_rt;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      mbar_wait(a_empty, aphase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(a_full, 2 * nkb * FA_BYTES);
         for (int kb = 0; kb < nkb; ++kb) {
-          tma_load_2d(sA_hi + kb * A_TILE_BYTES, &tmA_hi, a_full, kb * BK, rt * TM);
-          tma_load_2d(sA_lo + kb * A_TILE_BYTES, &tmA_lo, a_full, kb * BK, rt * TM);
+          tma_load_2d(sA_hi + kb * FA_BYTES, &tm.a_hi, a_full, kb * FK, rt * TM);
+          tma_load_2d(sA_lo + kb * FA_BYTES, &tm.a_lo, a_full, kb * FK, rt * TM);
         }
-        aphase ^= 1;
-        for (int g = g0; g < g1; ++g) {
-          for (int kb = nkb - 1; kb >= 0; --kb) {
-            const int nrows = min(BK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
-            for (int half = 0; half < 2; ++half) {
-              uint8_t* dst = ring + slot * p.slot_bytes;
-              mbar_wait(&empty[slot], sphase ^ 1);
-              mbar_arrive_expect_tx(&full[slot], nrows * ROW_BYTES);
+      }
+      __syncwarp();
+      aphase ^= 1;
+      for (int g = g0; g < g1; ++g) {
+        for (int kb = nkb - 1; kb >= 0; --kb) {
+          const int nrows = min(FK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
+          mbar_wait(&empty[slot], sphase ^ 1);
+          if (elect_one()) {
+            uint8_t* dst = ring + slot * p.slot_bytes;
+            if (p.dbg & 4) {
+              mbar_arrive(&full[slot]);
+            } else {
+              mbar_arrive_expect_tx(&full[slot], 2 * nrows * FROW);
               int row = 0;
-              for (; row + 64 <= nrows; row += 64)
-                tma_load_3d(dst + row * ROW_BYTES, half ? &tmB64_lo : &tmB64_hi, &full[slot], kb * BK, row, g);
-              for (; row < nrows; row += 16)
-                tma_load_3d(dst + row * ROW_BYTES, half ? &tmB16_lo : &tmB16_hi, &full[slot], kb * BK, row, g);
-              if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+#pragma unroll
+              for (int hsel = 0; hsel < 4; ++hsel) {
+                const int hgt = 128 >> hsel;
+                for (; row + hgt <= nrows; row += hgt) {
+                  tma_load_3d(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g);
+                  tma_load_3d(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g);
+                }
+              }
             }
           }
+          __syncwarp();
+          if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int slot = 0, acc = 0;
-      uint32_t sphase = 0, acc_phase = 0, aphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int gs = item / p.n_rt;
-        const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-        mbar_wait(a_full, aphase);
-        aphase ^= 1;
+    int slot = 0, acc = 0;
+    uint32_t sphase = 0, acc_phase = 0, aphase = 0;
+    const uint32_t half16 = (uint32_t)(p.slot_bytes >> 1) >> 4;  // hi -> lo block, in descriptor units
+    const uint64_t a_hi0 = make_desc_sw64(smem_u32(sA_hi));
+    const uint64_t a_lo0 = make_desc_sw64(smem_u32(sA_lo));
+    const uint64_t ring0 = make_desc_sw64(smem_u32(ring));
+    const uint32_t idesc0 = make_idesc_bf16(TM, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int gs = item / p.n_rt;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      mbar_wait(a_full, aphase);
+      aphase ^= 1;
+      tc_fence_after();
+      for (int g = g0; g < g1; ++g) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        for (int g = g0; g < g1; ++g) {
-          mbar_wait(&tempty[acc], acc_phase ^ 1);
+        const uint32_t d = tmem_base + (uint32_t)acc * TN;
+        uint32_t accum = 0;  // the first MMA of a gene has N = Mp and initialises every column
+        for (int kb = nkb - 1; kb >= 0; --kb) {
+          mbar_wait(&full[slot], sphase);
           tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)acc * TN;
-          uint32_t accum = 0;  // the first MMA of a gene has N = Mp and initialises every column
-          for (int kb = nkb - 1; kb >= 0; --kb) {
-            const uint64_t a_hi = make_desc_sw128(smem_u32(sA_hi + kb * A_TILE_BYTES));
-            const uint64_t a_lo = make_desc_sw128(smem_u32(sA_lo + kb * A_TILE_BYTES));
-            // B_hi block: passes hi*hi and lo*hi
-            mbar_wait(&full[slot], sphase);
-            tc_fence_after();
-            const uint64_t b_hi = make_desc_sw128(smem_u32(ring + slot * p.slot_bytes));
-            for (int k = BK / UMMA_K - 1; k >= 0; --k) {
-              const int k0 = kb * BK + k * UMMA_K;
+          if (elect_one()) {
+            const uint64_t b_hi = ring0 + (uint64_t)((uint32_t)(slot * p.slot_bytes) >> 4);
+            const uint64_t a_hi = a_hi0 + (uint64_t)((uint32_t)(kb * FA_BYTES) >> 4);
+            const uint64_t a_lo = a_lo0 + (uint64_t)((uint32_t)(kb * FA_BYTES) >> 4);
+#pragma unroll
+            for (int k = FK / UMMA_K - 1; k >= 0; --k) {
+              const int k0 = kb * FK + k * UMMA_K;
               if (k0 >= Mp) continue;
-              const uint32_t idesc = make_idesc_bf16(TM, k0 + UMMA_K);
-              const uint32_t off = k * UMMA_K * 2;
-              umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_hi, off), idesc, accum);
+              const uint32_t idesc = idesc0 | ((uint32_t)(((p.dbg >> 4) ? 16 * (p.dbg >> 4) : (p.dbg & 1) ? Mp : k0 + UMMA_K) >> 3) << 17);
+              const uint32_t off = (k * UMMA_K * 2) >> 4;
+              umma_bf16(d, a_hi + off, b_hi + off, idesc, accum);
+              umma_bf16(d, a_lo + off, b_hi + off, idesc, 1u);
+              umma_bf16(d, a_hi + off, b_hi + half16 + off, idesc, 1u);
               accum = 1;
-              umma_bf16(d, desc_advance(a_lo, off), desc_advance(b_hi, off), idesc, 1u);
             }
             umma_commit(&empty[slot]);
-            if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
-            // B_lo block: pass hi*lo
-            mbar_wait(&full[slot], sphase);
-            tc_fence_after();
-            const uint64_t b_lo = make_desc_sw128(smem_u32(ring + slot * p.slot_bytes));
-            for (int k = BK / UMMA_K - 1; k >= 0; --k) {
-              const int k0 = kb * BK + k * UMMA_K;
-              if (k0 >= Mp) continue;
-              const uint32_t idesc = make_idesc_bf16(TM, k0 + UMMA_K);
-              const uint32_t off = k * UMMA_K * 2;
-              umma_bf16(d, desc_advance(a_hi, off), desc_advance(b_lo, off), idesc, 1u);
-            }
-            umma_commit(&empty[slot]);
-            if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
           }
-          umma_commit(&tfull[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          __syncwarp();
+          accum = 1;
+          if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
-        umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
+      if (elect_one()) umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
@@ -460,7 +497,7 @@ tc_qf_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < n32; ++c) {
+        for (int c = 0; c < ((p.dbg & 2) ? 0 : n32); ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -631,15 +668,16 @@ EncodeTiledFn encode_fn() {
 
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, out-of-bounds elements read as zero
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+              const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GPSA_ERR_CUDA;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], es[3];
   for (int d = 0; d < rank; ++d) { gdim[d] = dims[d]; bx[d] = box[d]; es[d] = 1; }
   for (int d = 0; d + 1 < rank; ++d) gstr[d] = strides_bytes[d];
-  const CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
-                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult rc = fn(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? GPSA_OK : GPSA_ERR_CUDA;
 }
@@ -666,8 +704,8 @@ struct FwdLayout { int Mp, Kp, nkb; size_t at, lt, total; };
 FwdLayout fwd_layout(int M, long R, int L) {
   FwdLayout f;
   f.Mp = (int)rup(M, 16);
-  f.nkb = (f.Mp + BK - 1) / BK;
-  f.Kp = f.nkb * BK;
+  f.nkb = (f.Mp + FK - 1) / FK;
+  f.Kp = (int)rup(f.Mp, 64);  // 128-byte row pitch
   f.at = al256((size_t)R * f.Kp * 2);
   f.lt = al256((size_t)L * f.Mp * f.Kp * 2);
   f.total = 2 * f.at + 2 * f.lt;
@@ -683,12 +721,13 @@ AlphaLayout alpha_layout(int M, long R, int L) {
   a.total = 2 * a.g + 2 * a.w;
   return a;
 }
-struct OmegaLayout { long Rp; size_t gt, total; };
+struct OmegaLayout { long Rp; size_t gt, apad, total; };
 OmegaLayout omega_layout(int M, long R, int L) {
   OmegaLayout o;
   o.Rp = rup(R, 8);
   o.gt = al256((size_t)L * o.Rp * 2);
-  o.total = 2 * o.gt;
+  o.apad = (R % 4 == 0) ? 0 : al256((size_t)M * rup(R, 4) * 4);  // TMA needs a 16-byte row pitch: padded copy of A
+  o.total = 2 * o.gt + o.apad;
   return o;
 }
 
@@ -697,13 +736,14 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
                 const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE)) !=
+        cudaSuccess)
       return GPSA_ERR_CUDA;
     attr_set = true;
   }
   const int n_items = p.n_mt * p.n_nt * p.n_split;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  tc_gemm_kernel<MODE><<<grid, MODE == MODE_OMEGA ? 384 : 256, GEMM_SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  tc_gemm_kernel<MODE><<<grid, gemm_threads(MODE), gemm_smem(MODE), st>>>(a_hi, a_lo, b_hi, b_lo, p);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -777,18 +817,30 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
     pack_Lt_kernel<<<grid2, block, 0, st>>>(M, f.Mp, f.Kp, Ltril, lt_hi, lt_lo);
     GPSA_LAUNCH_CHECK();
   }
-  CUtensorMap ta_hi, ta_lo, tb64_hi, tb64_lo, tb16_hi, tb16_lo;
-  if (make_tmap_2d(&ta_hi, at_hi, f.Mp, R, f.Kp, TM) || make_tmap_2d(&ta_lo, at_lo, f.Mp, R, f.Kp, TM)) return GPSA_ERR_CUDA;
+  FwdMaps maps;
+  {
+    const uint64_t dims[2] = {(uint64_t)f.Mp, (uint64_t)R}, str[1] = {(uint64_t)f.Kp * 2};
+    const uint32_t box[2] = {(uint32_t)FK, (uint32_t)TM};
+    if (make_tmap(&maps.a_hi, at_hi, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) ||
+        make_tmap(&maps.a_lo, at_lo, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
+      return GPSA_ERR_CUDA;
+  }
   {
     const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
     const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
-    const uint32_t box64[3] = {(uint32_t)BK, 64, 1}, box16[3] = {(uint32_t)BK, 16, 1};
-    if (make_tmap(&tb64_hi, lt_hi, 3, dims, str, box64) || make_tmap(&tb64_lo, lt_lo, 3, dims, str, box64) ||
-        make_tmap(&tb16_hi, lt_hi, 3, dims, str, box16) || make_tmap(&tb16_lo, lt_lo, 3, dims, str, box16))
-      return GPSA_ERR_CUDA;
+    for (int hsel = 0; hsel < 4; ++hsel) {
+      const uint32_t box[3] = {(uint32_t)FK, (uint32_t)(128 >> hsel), 1};
+      if (make_tmap(&maps.b_hi[hsel], lt_hi, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) ||
+          make_tmap(&maps.b_lo[hsel], lt_lo, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
+        return GPSA_ERR_CUDA;
+    }
   }
   FwdParams p = {};
   p.Mp = f.Mp; p.nkb = f.nkb; p.L = L; p.R = R; p.q2 = q2;
+  {
+    static const int dbg = [] { const char* e = getenv("GPSA_TC_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
+  }
   p.n_rt = gpsa_cdiv(R, TM);
   // split the gene range when there are too few row tiles to fill the machine
   p.gsplit = 1;
@@ -798,8 +850,8 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   }
   p.genes_per = (L + p.gsplit - 1) / p.gsplit;
   p.gsplit = (L + p.genes_per - 1) / p.genes_per;
-  p.slot_bytes = f.Mp * ROW_BYTES;
-  const int fixed = 2 * f.nkb * A_TILE_BYTES + 1024 + 256;
+  p.slot_bytes = 2 * f.Mp * FROW;  // one K block: hi rows, then lo rows
+  const int fixed = 2 * f.nkb * FA_BYTES + 1024 + 256;
   p.nslot = (232448 - fixed) / p.slot_bytes;
   if (p.nslot > FWD_MAXSLOT) p.nslot = FWD_MAXSLOT;
   if (p.nslot < 2) return GPSA_ERR_UNSUPPORTED;
@@ -812,7 +864,7 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   }
   const int n_items = p.n_rt * p.gsplit;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  tc_qf_fwd_kernel<<<grid, 256, smem_bytes, st>>>(ta_hi, ta_lo, tb64_hi, tb64_lo, tb16_hi, tb16_lo, p);
+  tc_qf_fwd_kernel<<<grid, 256, smem_bytes, st>>>(maps, p);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -860,8 +912,22 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
     pack_Gt_kernel<<<grid, block, 0, st>>>(R, L, o.Rp, G, gt_hi, gt_lo);
     GPSA_LAUNCH_CHECK();
   }
-  CUtensorMap tb_hi, tb_lo;
+  CUtensorMap tb_hi, tb_lo, ta_raw;
   if (make_tmap_2d(&tb_hi, gt_hi, R, L, o.Rp, TN) || make_tmap_2d(&tb_lo, gt_lo, R, L, o.Rp, TN)) return GPSA_ERR_CUDA;
+  {
+    const float* Asrc = A;
+    long pitch = R;
+    if (o.apad) {
+      pitch = rup(R, 4);
+      float* Ap = reinterpret_cast<float*>(w + 2 * o.gt);
+      if (cudaMemcpy2DAsync(Ap, pitch * 4, A, R * 4, R * 4, M, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return GPSA_ERR_CUDA;
+      Asrc = Ap;
+    }
+    const uint64_t dims[2] = {(uint64_t)R, (uint64_t)M}, str[1] = {(uint64_t)pitch * 4};
+    const uint32_t box[2] = {32, 8};
+    if (make_tmap(&ta_raw, Asrc, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return GPSA_ERR_CUDA;
+  }
   const long NF = feat_nblk(M) * FBK;
   GemmParams p = {};
   p.n_mt = gpsa_cdiv(NF, TM);
@@ -879,5 +945,5 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
   p.accumulate = p.n_split > 1;
   if (p.accumulate && cudaMemsetAsync(H, 0, sizeof(float) * (size_t)NF * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
   p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
-  return launch_gemm<MODE_OMEGA>(tb_hi, tb_lo, tb_hi, tb_lo, p, st);
+  return launch_gemm<MODE_OMEGA>(ta_raw, ta_raw, tb_hi, tb_lo, p, st);
 }
