@@ -152,6 +152,7 @@ class VariationalGPSA(GPSA):
         self.register_buffer("_kl_mask", kl_mask, persistent=False)
         self._idx_cache = {}
         self._kl = None
+        self._kl_G_scale = 1.0  # 1/world under gene sharding (gpsa.parallel), so that local losses SUM to the ELBO
 
     # ----------------------------------------------------------------------------------------------
     def _is_fixed(self, vv):
@@ -275,7 +276,7 @@ class VariationalGPSA(GPSA):
         self.F_latent_samples, self.F_observed_samples = {}, {}
         if G_test is not None:
             self.F_latent_samples_test, self.F_observed_samples_test = {}, {}
-        kl = kl_G
+        kl = kl_G if self._kl_G_scale == 1.0 else kl_G * self._kl_G_scale
         infos = [info_G]
         kind_d = _ops.KINDS[self._kind_data]
         for mod in mods:

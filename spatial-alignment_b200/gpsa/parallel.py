@@ -1,0 +1,106 @@
+"""One-process-per-GPU execution of the ELBO iteration: gene sharding.
+
+Given the warped coordinates, the data GP is independent across output genes: gene p owns its own
+Omega_sqt_F[p], delta_F[:, p], outputs[:, p] and noise draws.  Rank r therefore keeps a contiguous slice of
+the genes -- parameters, data, Adam state and the whole tcgen05 quadratic-form work for them -- and the cheap
+shared front end (warp GP of every view, K_uu / K_uf / A = K^-1 K_uf of the data GP: < 1 % of the flops) is
+replicated with identical noise, so the forward needs no collective at all.  The only exchange is one
+all-reduce (NCCL over NVLink/NVSwitch; gloo in the CPU tests) per iteration of the gradients of the shared
+parameters, which live in ONE flat buffer that autograd accumulates into directly (the parameters' .grad are
+views of it), so nothing is packed or unpacked around the collective.
+
+    model = VariationalGPSA(local_data_dict, ...)            # outputs already sliced to this rank's genes
+    sharder = GeneSharding(model, world_size, rank)           # after model.to(device)
+    loss = model.loss_fn(local_data_dict, F); sharder.zero_grad(); loss.backward(); sharder.allreduce(); opt.step()
+
+The negative ELBO decomposes as  sum_r [ -LL_r + KL_F_r + KL_G / world ]: every rank evaluates the (replicated)
+warp-GP KL and weights it by 1/world, so that the SUM over ranks of the local losses -- and of the local
+gradients of the shared parameters -- is exactly the unsharded loss / gradient.
+"""
+import torch
+import torch.distributed as dist
+
+# parameters every rank holds a full replica of (reference state_dict names)
+SHARED = ("noise_variance", "warp_kernel_variances", "warp_kernel_lengthscales", "data_kernel_lengthscale",
+          "data_kernel_variance", "Xtilde", "Gtilde", "Omega_sqt_G_list", "delta_G_list")
+
+
+def gene_range(n_genes, world, rank):
+    """Contiguous, balanced slice [lo, hi) of the genes owned by `rank` (first n_genes % world ranks get one more)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    base, extra = divmod(int(n_genes), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_data_dict(data_dict, world, rank):
+    """This rank's view of a reference-style data_dict: same coordinates, the gene slice of `outputs`."""
+    out = {}
+    for mod, d in data_dict.items():
+        lo, hi = gene_range(d["outputs"].shape[1], world, rank)
+        out[mod] = dict(d)
+        out[mod]["outputs"] = d["outputs"][:, lo:hi].contiguous()
+    return out
+
+
+def shard_state_dict(state_dict, world, rank):
+    """Slice a full (unsharded) reference/gpsa_b200 state_dict down to this rank's genes."""
+    out = {}
+    for k, v in state_dict.items():
+        if k.startswith("Omega_sqt_F_dict."):
+            lo, hi = gene_range(v.shape[0], world, rank)
+            out[k] = v[lo:hi].clone()
+        elif k.startswith("delta_F_dict."):
+            lo, hi = gene_range(v.shape[1], world, rank)
+            out[k] = v[:, lo:hi].clone()
+        elif k.startswith("W_dict."):
+            raise NotImplementedError("gene sharding with LMC loadings (n_latent_gps) mixes genes across ranks; not supported")
+        else:
+            out[k] = v.clone()
+    return out
+
+
+class GeneSharding:
+    """Owns the flat gradient buffer of the shared parameters and the per-iteration all-reduce."""
+
+    def __init__(self, model, world, rank, group=None):
+        self.model, self.world, self.rank, self.group = model, int(world), int(rank), group
+        if any(model.n_latent_gps[m] is not None for m in model.modality_names):
+            raise NotImplementedError("gene sharding with LMC loadings (n_latent_gps) is not supported")
+        named = dict(model.named_parameters())
+        self.shared = [(n, named[n]) for n in SHARED if n in named and named[n].requires_grad]
+        total = sum(p.numel() for _, p in self.shared)
+        ref = self.shared[0][1]
+        # [shared grads ..., local loss]: the trailing slot carries the scalar loss so that logging needs no second collective
+        self.flat = torch.zeros(total + 1, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for _, p in self.shared:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        model._kl_G_scale = 1.0 / self.world
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_grad(self):
+        """Zero in place (the .grad views must survive), drop the gene-local grads like optimizer.zero_grad()."""
+        self.flat.zero_()
+        shared_ids = {id(p) for _, p in self.shared}
+        for p in self.model.parameters():
+            if id(p) not in shared_ids:
+                p.grad = None
+
+    def allreduce(self, loss=None):
+        """Sum the shared-parameter gradients (and the local losses) over ranks, in place.  Returns the global loss
+        as a 0-dim tensor when `loss` is given."""
+        for _, p in self.shared:
+            if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or \
+                    p.grad.data_ptr() >= self.flat.data_ptr() + self.nbytes():
+                raise RuntimeError("a shared parameter's .grad no longer aliases the flat buffer "
+                                   "(use GeneSharding.zero_grad(), not optimizer.zero_grad(set_to_none=True))")
+        if loss is not None:
+            self.flat[-1] = loss.detach()
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat[-1].clone() if loss is not None else None

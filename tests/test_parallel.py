@@ -1,0 +1,178 @@
+"""Gene sharding (gpsa.parallel): host logic under gloo with world_size 2 on CPU, and -- marked gpu -- the sharded
+ELBO iteration against the unsharded one on the same parameters and noise (two ranks sharing cuda:0 over gloo;
+the data path has no collective, the gradient all-reduce is backend-agnostic)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from golden_io import Golden, relerr
+from test_host_api import _model_from_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_gene_range_partitions_everything():
+    from gpsa.parallel import gene_range
+
+    for n in (1, 5, 30, 2000, 2001, 5000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [gene_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        gene_range(10, 2, 2)
+
+
+def test_shard_state_and_data():
+    from gpsa.parallel import gene_range, shard_data_dict, shard_state_dict
+
+    g = Golden("c1_shipped")
+    model, data_dict = _model_from_golden(g)
+    sd = model.state_dict()
+    P = data_dict["expression"]["outputs"].shape[1]
+    parts = [shard_state_dict(sd, 4, r) for r in range(4)]
+    assert torch.equal(torch.cat([p["Omega_sqt_F_dict.expression"] for p in parts], 0), sd["Omega_sqt_F_dict.expression"])
+    assert torch.equal(torch.cat([p["delta_F_dict.expression"] for p in parts], 1), sd["delta_F_dict.expression"])
+    assert all(torch.equal(p["Xtilde"], sd["Xtilde"]) for p in parts)
+    dd = shard_data_dict(data_dict, 4, 3)
+    lo, hi = gene_range(P, 4, 3)
+    assert torch.equal(dd["expression"]["outputs"], data_dict["expression"]["outputs"][:, lo:hi])
+    assert dd["expression"]["spatial_coords"] is data_dict["expression"]["spatial_coords"]
+    g2 = Golden("lmc")
+    m2, _ = _model_from_golden(g2)
+    with pytest.raises(NotImplementedError):
+        shard_state_dict(m2.state_dict(), 2, 0)
+
+
+def _cpu_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gpsa.parallel import SHARED, GeneSharding, shard_data_dict, shard_state_dict
+
+        g = Golden("c1_shipped")
+        full, data_dict = _model_from_golden(g)
+        local_dd = shard_data_dict(data_dict, world, rank)
+        g_local, _ = None, None
+        import gpsa
+
+        np.random.seed(0)
+        torch.manual_seed(0)
+        model = gpsa.VariationalGPSA(local_dd, n_spatial_dims=2, m_X_per_view=g.cfg.m_X_per_view, m_G=g.cfg.m_G,
+                                     data_init=True, n_latent_gps=g.n_latent, fixed_view_idx=g.fixed)
+        model.load_state_dict(shard_state_dict(full.state_dict(), world, rank))
+        sh = GeneSharding(model, world, rank)
+        assert model._kl_G_scale == 1.0 / world
+        named = dict(model.named_parameters())
+        ok = True
+        for it in range(2):  # the views must survive a second iteration
+            sh.zero_grad()
+            # a stand-in loss on CPU (the ELBO needs the GPU): rank-dependent weights on shared and local parameters
+            loss = sum((rank + 1.0) * (p ** 2).sum() for n, p in named.items() if n in SHARED)
+            loss = loss + 3.0 * (named["delta_F_dict.expression"] ** 2).sum()
+            loss.backward()
+            total = sh.allreduce(loss)
+            wsum = sum(r + 1.0 for r in range(world))
+            for n, p in named.items():
+                if n in SHARED:
+                    ok &= torch.allclose(p.grad, 2 * wsum * p.detach(), rtol=1e-6)
+                    ok &= p.grad.data_ptr() >= sh.flat.data_ptr()
+            ok &= torch.allclose(named["delta_F_dict.expression"].grad, 6.0 * named["delta_F_dict.expression"].detach())
+            losses = [torch.zeros(()) for _ in range(world)]
+            dist.all_gather(losses, loss.detach())
+            ok &= bool(torch.isclose(total, sum(losses), rtol=1e-6))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_gradient_allreduce_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cpu_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+# --------------------------------------------------------------------------------------------------
+def _gpu_worker(rank, world, port, name, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gpsa
+        from gpsa.parallel import GeneSharding, gene_range, shard_data_dict, shard_state_dict
+
+        g = Golden(name)
+        full, data_dict = _model_from_golden(g)
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in g.params.items() if k not in g.fixed_params}
+        full.load_state_dict(sd, strict=True)
+        local_dd = shard_data_dict(data_dict, world, rank)
+        kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel}
+        np.random.seed(0)
+        torch.manual_seed(0)
+        model = gpsa.VariationalGPSA(local_dd, n_spatial_dims=g.cfg.n_spatial_dims, m_X_per_view=g.cfg.m_X_per_view,
+                                     m_G=g.cfg.m_G, data_init=True, n_latent_gps=g.n_latent,
+                                     kernel_func_warp=kern[g.cfg.kernel_warp], kernel_func_data=kern[g.cfg.kernel_data],
+                                     fixed_view_idx=g.fixed)
+        model.load_state_dict(shard_state_dict(full.state_dict(), world, rank))
+        model = model.to("cuda")
+        local_dd = {m: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for m, d in local_dd.items()}
+        sh = GeneSharding(model, world, rank)
+        view_idx, Ns, _, _ = model.create_view_idx_dict(local_dd)
+        P = g.Y[g.mods[0]].shape[1]
+        lo, hi = gene_range(P, world, rank)
+        eps = {"G": {v: torch.from_numpy(e) for v, e in g.eps["G"].items()},  # identical warp noise on every rank
+               "F": {m: torch.from_numpy(e[:, :, lo:hi].copy()) for m, e in g.eps["F"].items()}, "F_test": {}}
+        X = {m: local_dd[m]["spatial_coords"] for m in g.mods}
+        ret = model.forward(X, view_idx=view_idx, Ns=Ns, S=g.S, _eps=eps)
+        loss = model.loss_fn(local_dd, ret[3])
+        sh.zero_grad()
+        loss.backward()
+        total = sh.allreduce(loss)
+        res = {"loss": float(total), "lo": lo, "hi": hi}
+        for n, p in model.named_parameters():
+            res[n] = p.grad.detach().cpu().numpy()
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_shipped", "c2_matern"])
+def test_sharded_iteration_equals_unsharded(name):
+    from test_gpu_parity import build, run
+
+    g = Golden(name)
+    model, data_dict = build(g)
+    _, loss = run(g, model, data_dict)
+    ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), name, out), nprocs=world, join=True)
+    out = dict(out)
+    assert abs(out[0]["loss"] - float(loss)) <= 2e-5 * abs(float(loss))
+    assert out[0]["loss"] == out[1]["loss"]
+    mod = g.mods[0]
+    for n, gref in ref.items():
+        if n == f"Omega_sqt_F_dict.{mod}":
+            got = np.concatenate([out[r][n] for r in range(world)], 0)
+        elif n == f"delta_F_dict.{mod}":
+            got = np.concatenate([out[r][n] for r in range(world)], 1)
+        else:
+            got = out[0][n]
+            assert np.array_equal(out[0][n], out[1][n]), n  # all-reduced: bitwise identical on every rank
+        assert relerr(got, gref) < 5e-5, n
