@@ -89,6 +89,9 @@ int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltri
  * L64: the fp64 factor from gpsa_omega_prepare; Linv64, Y64: [B,M,M] fp64 scratch. */
 int gpsa_omega_grad(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
                     double* Linv64, double* Y64, float* Osq_bar, cudaStream_t stream);
+/* Same, with the 2 Obar Osq product on the tcgen05 engine; tc_ws: gpsa_gemm_tc_ws_bytes(M, M, M, B) bytes. */
+int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
+                       double* Linv64, double* Y64, float* Osq_bar, void* tc_ws, size_t tc_ws_bytes, cudaStream_t stream);
 
 /* ---- implicit-feature quadratic form (the hot contraction) ------------------------------------
  * q2[r,p] = a_r^T Omega_p a_r with a_r = A[:,r];  replaces the [S,L,N,M] broadcast bmm at
@@ -119,6 +122,15 @@ int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float
                                void* ws, size_t ws_bytes, cudaStream_t stream);
 int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, const float* G, float* H, void* ws,
                                size_t ws_bytes, cudaStream_t stream);
+/* Generic fp32-in / fp32-out GEMM on the same engine: C[b] (op)= alpha * A[b] B[b]^T.  A is Mr x K with element (i,k) at
+ * A[b*sA + i*lda + k] (a_rows_major = 1) or A[b*sA + k*lda + i] (0); B likewise (Nc x K).  out_mode 0: C[b*sC + i*ldc + j] = v
+ * (split > 1 or split <= 0 = auto: C zeroed then atomically accumulated, needs ldc == Nc); out_mode 1: C[j*ldc + i] += v
+ * (batch 1).  Replaces the predictive-mean matmul (gpsa/models/vgpsa.py:182-184) and the autograd matmuls of the
+ * data layer.  ws: gpsa_gemm_tc_ws_bytes(Mr, Nc, K, batch) bytes. */
+size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch);
+int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, long lda, long sA, int a_rows_major, const float* B,
+                 long ldb, long sB, int b_rows_major, float* C, long ldc, long sC, float alpha, int out_mode, int split,
+                 void* ws, size_t ws_bytes, cudaStream_t stream);
 /* Plain C [Mr,Nc] = A [Mr,K] B[Nc,K]^T through the same TMA / tcgen05 / TMEM core (unit-test hook). */
 int gpsa_tc_gemm_test(int Mr, int Nc, int K, const float* A, const float* B, float* C, int split, void* ws,
                       size_t ws_bytes, cudaStream_t stream);

@@ -642,7 +642,7 @@ extern "C" int gpsa_prof_read(int* counts, double* total_ms) {
 // ================================================================================================
 // exported entry points
 // ================================================================================================
-extern "C" int gpsa_version(void) { return 103; }
+extern "C" int gpsa_version(void) { return 104; }
 
 extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, long ars, long acs, long sA,
                              const float* B, long brs, long bcs, long sB, float beta, float* C, long ldc, long sC,
@@ -699,11 +699,21 @@ extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, 
 
 extern "C" int gpsa_omega_grad(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
                                double* Linv64, double* Y64, float* Osq_bar, cudaStream_t st) {
+  return gpsa_omega_grad_tc(M, B, Osq, L64, Obar, coef, Linv64, Y64, Osq_bar, nullptr, 0, st);
+}
+
+extern "C" int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
+                                  double* Linv64, double* Y64, float* Osq_bar, void* tc_ws, size_t tc_ws_bytes,
+                                  cudaStream_t st) {
   if (M <= 0 || B <= 0) return GPSA_OK;
   const long MM = (long)M * M;
   // Osq_bar = (Obar + Obar^T) Osq = 2 Obar Osq  (Obar symmetric) ...
-  TRY((gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
-                                                B)));
+  if (tc_ws && M >= 32) {
+    TRY(gpsa_gemm_tc(M, M, M, B, Obar, M, MM, 1, Osq, M, MM, 0, Osq_bar, M, MM, 2.f, 0, 1, tc_ws, tc_ws_bytes, st));
+  } else {
+    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
+                                                  B)));
+  }
   if (coef) {
     // ... + 2 coef[b] Omega^-1 Osq, Omega^-1 = Linv^T Linv, in fp64
     TRY(gpsa_trtri_batched_f64(M, B, L64, Linv64, st));
@@ -837,8 +847,12 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   kq_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->log_var, a->kq);
   GPSA_LAUNCH_CHECK();
   // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
-  TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
-                                                1)));
+  if (a->engine == 1) {
+    TRY(gpsa_gemm_tc(R, L, M, 1, a->A, R, 0, 0, a->dlt, L, 0, 0, a->F, L, 0, 1.f, 0, 1, a->tc_ws, a->tc_ws_bytes, st));
+  } else {
+    TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
+                                                  1)));
+  }
   if (a->engine == 0) {
     TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
     gpsa_prof_begin(0, st);
@@ -876,7 +890,10 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
     GPSA_LAUNCH_CHECK();
   }
   // delta-bar = A Fbar (+ kl_bar K^-1 delta)
-  {
+  if (a->engine == 1 && R <= 2000000000L) {
+    TRY(gpsa_gemm_tc(M, L, (int)R, 1, a->A, R, 0, 1, a->F_bar, L, 0, 0, a->dlt_bar, L, 0, 1.f, 0, 0, a->tc_ws,
+                     a->tc_ws_bytes, st));
+  } else {
     const int split = pick_split(M, L, R, 1, tile_of<float>(M, L));
     if (cudaMemsetAsync(a->dlt_bar, 0, sizeof(float) * (size_t)M * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
     TRY((gemm_strided<float, float, float, float>(st, M, L, R, 1.0, a->A, R, 1, 0, a->F_bar, L, 1, 0, 1.0, a->dlt_bar,
@@ -885,8 +902,12 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   if (a->kl_bar) TRY((axpy_dev<double, float>(st, (long)M * L, 1.0, a->kl_bar, a->KD, a->dlt_bar)));
   // Abar = q1bar o B + delta Fbar^T + 2 (sum_p Gm Omega_p) a
   TRY(colscale<float>(st, M, R, a->q1bar, a->B, a->Abar, 0));
-  TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
-                                                R, 0, 1)));
+  if (a->engine == 1) {
+    TRY(gpsa_gemm_tc(R, M, L, 1, a->F_bar, L, 0, 1, a->dlt, L, 0, 1, a->Abar, R, 0, 1.f, 1, 1, a->tc_ws, a->tc_ws_bytes, st));
+  } else {
+    TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
+                                                  R, 0, 1)));
+  }
   gpsa_prof_begin(1, st);
   if (a->engine == 0) TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
   else TRY(gpsa_quadform_bwd_alpha_tc(M, R, L, a->A, a->Gm, a->Omega, a->Abar, a->tc_ws, a->tc_ws_bytes, st));

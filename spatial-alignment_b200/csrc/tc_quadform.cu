@@ -57,6 +57,10 @@ struct GemmParams {
   float* C;           // TEST: C [Mrows, Ncols];  OMEGA: H [NF, L]
   long ldc;
   int accumulate;     // OMEGA/TEST: 1 = atomicAdd (split-K), 0 = plain store
+  int batch;          // TEST: > 0 -> operands are 3-D maps [batch, rows, K], item = (b, tile); C advances by sC per batch
+  long sC;
+  int trans_add;      // TEST: 1 -> C[col*ldc + row] += alpha*acc (transposed, read-modify-write), 0 -> C[row*ldc + col]
+  float alpha;
   const float* Amat;  // ALPHA/OMEGA: A [Mind, R]
   long R;
   int Mind, nb, nblk;
@@ -65,6 +69,7 @@ struct GemmParams {
 
 __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& ks) {
   const int per_split = p.n_mt * p.n_nt;
+  if (p.batch > 0) item %= per_split * p.n_split;  // batch index = item / (tiles * splits), see item_batch()
   ks = item / per_split;
   int w = item - ks * per_split;
   const int gfull = p.group_m * p.n_nt;
@@ -74,6 +79,10 @@ __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& 
   w -= g * gfull;
   nt = w / gm;
   mt = m0 + w % gm;
+}
+
+__device__ __forceinline__ int item_batch(const GemmParams& p, int item) {
+  return p.batch > 0 ? item / (p.n_mt * p.n_nt * p.n_split) : 0;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -117,7 +126,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_mt * p.n_nt * p.n_split;
+  const int n_items = p.n_mt * p.n_nt * p.n_split * (p.batch > 0 ? p.batch : 1);
 
   // Producer and MMA warps run converged (all lanes wait on the barriers, loop state is warp-uniform); only the
   // TMA / MMA issue is predicated on elect.sync, which keeps the single issuing thread's instruction stream short.
@@ -144,7 +153,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], MODE == MODE_OMEGA ? 2 * B_TILE_BYTES : OPER_BYTES);
-          if (MODE != MODE_OMEGA) {
+          if (MODE == MODE_TEST && p.batch > 0) {
+            const int bz = item_batch(p, item);
+            tma_load_3d(st, &tmA_hi, &full[stage], kb * BK, mt * TM, bz);
+            tma_load_3d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM, bz);
+            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN, bz);
+            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN, bz);
+          } else if (MODE != MODE_OMEGA) {
             tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
             tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
           } else {
@@ -155,8 +170,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               for (int h = 0; h < 2; ++h)
                 tma_load_2d(st + OPER_BYTES + (gq * 2 + h) * 1024, &tmA_hi, &rawfull[stage], kb * BK + h * 32, grow[gq]);
           }
-          tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
-          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
+          if (!(MODE == MODE_TEST && p.batch > 0)) {
+            tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
+            tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -213,19 +230,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
       const long row = (long)mt * TM + q * 32 + lane;
       if (MODE == MODE_TEST || MODE == MODE_OMEGA) {
+        float* Cb = p.C + (MODE == MODE_TEST ? (long)item_batch(p, item) * p.sC : 0);
+        const float alpha = MODE == MODE_TEST ? p.alpha : 1.f;
+        const bool vec4 = MODE == MODE_TEST && !p.accumulate && !p.trans_add && (p.ldc & 3) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
 #pragma unroll 1
         for (int c = 0; c < TN / 32; ++c) {
+          const long col0 = (long)nt * TN + c * 32;
+          if (col0 >= p.Ncols) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
           if (row < p.Mrows) {
+            if (MODE == MODE_TEST && p.trans_add) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long col = (long)nt * TN + c * 32 + j;
-              if (col < p.Ncols) {
-                float* dst = p.C + row * p.ldc + col;
-                if (p.accumulate) atomicAdd(dst, __uint_as_float(v[j]));
-                else *dst = __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) {
+                const long col = col0 + j;
+                if (col < p.Ncols) Cb[col * p.ldc + row] += alpha * __uint_as_float(v[j]);  // lanes = consecutive rows: coalesced
+              }
+            } else if (vec4 && col0 + 32 <= p.Ncols) {
+              float4* dst = reinterpret_cast<float4*>(Cb + row * p.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(alpha * __uint_as_float(v[4 * j]), alpha * __uint_as_float(v[4 * j + 1]),
+                                     alpha * __uint_as_float(v[4 * j + 2]), alpha * __uint_as_float(v[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const long col = col0 + j;
+                if (col < p.Ncols) {
+                  float* dst = Cb + row * p.ldc + col;
+                  if (p.accumulate) atomicAdd(dst, alpha * __uint_as_float(v[j]));
+                  else *dst = alpha * __uint_as_float(v[j]);
+                }
               }
             }
           }
@@ -649,6 +686,49 @@ __global__ void pack_Gt_kernel(long R, int L, long Rp, const float* __restrict__
   }
 }
 
+// generic batched packs for gpsa_gemm_tc: out[b, row, k] (pitch Kp, bf16 hi/lo) from a row-major fp32 operand
+//   rows_major = 1: in[b*sIn + row*ld + k]          (operand already K-contiguous)
+//   rows_major = 0: in[b*sIn + k*ld + row]          (operand stored K x rows: transposed on the fly)
+__global__ void pack_rows_kernel(long rows, int K, int Kp, long ld, long sIn, const float* __restrict__ in,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int b = blockIdx.z;
+  const float* src = in + (long)b * sIn;
+  const long total = rows * K, obase = (long)b * rows * Kp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / K;
+    const int k = (int)(idx - r * K);
+    __nv_bfloat16 h, l;
+    split_one(src[r * ld + k], h, l);
+    hi[obase + r * Kp + k] = h;
+    lo[obase + r * Kp + k] = l;
+  }
+}
+__global__ void pack_trans_kernel(long rows, int K, int Kp, long ld, long sIn, const float* __restrict__ in,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const float* src = in + (long)b * sIn;
+  const long obase = (long)b * rows * Kp;
+  const long r0 = (long)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const int k = k0 + yy;
+    const long r = r0 + threadIdx.x;
+    t[yy][threadIdx.x] = (k < K && r < rows) ? src[(long)k * ld + r] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    const long r = r0 + yy;
+    const int k = k0 + threadIdx.x;
+    if (r < rows && k < K) {
+      __nv_bfloat16 h, l;
+      split_one(t[threadIdx.x][yy], h, l);
+      hi[obase + r * Kp + k] = h;
+      lo[obase + r * Kp + k] = l;
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
@@ -741,7 +821,7 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
       return GPSA_ERR_CUDA;
     attr_set = true;
   }
-  const int n_items = p.n_mt * p.n_nt * p.n_split;
+  const int n_items = p.n_mt * p.n_nt * p.n_split * (p.batch > 0 ? p.batch : 1);
   const int grid = n_items < sm_count() ? n_items : sm_count();
   tc_gemm_kernel<MODE><<<grid, gemm_threads(MODE), gemm_smem(MODE), st>>>(a_hi, a_lo, b_hi, b_lo, p);
   GPSA_LAUNCH_CHECK();
@@ -762,11 +842,18 @@ void set_split(GemmParams& p, int want_split) {
 // =================================================================================================
 extern "C" int gpsa_tc_supported(int M) { return (M >= 16 && M <= 256) ? 1 : 0; }
 
+extern "C" size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch);
+
+// scratch for everything the data layer runs on the tcgen05 engine at this shape: the three quadratic-form
+// products and the four plain GEMMs (predictive mean, delta-bar, A-bar += delta Fbar^T, Omega-bar Omega_sqt)
 extern "C" size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L) {
   if (M <= 0 || R <= 0 || L <= 0) return 0;
-  size_t a = fwd_layout(M, R, L).total, b = alpha_layout(M, R, L).total, c = omega_layout(M, R, L).total;
-  size_t m = a > b ? a : b;
-  return (m > c ? m : c) + 256;
+  size_t m = fwd_layout(M, R, L).total;
+  const size_t c[] = {alpha_layout(M, R, L).total, omega_layout(M, R, L).total, gpsa_gemm_tc_ws_bytes(R, L, M, 1),
+                      gpsa_gemm_tc_ws_bytes(M, L, (int)(R > 2000000000L ? 2000000000L : R), 1), gpsa_gemm_tc_ws_bytes(R, M, L, 1),
+                      gpsa_gemm_tc_ws_bytes(M, M, M, L)};
+  for (size_t v : c) m = v > m ? v : m;
+  return m + 256;
 }
 
 // C [Mr, Nc] = A [Mr, K] B[Nc, K]^T with A, B fp32 row-major: split to bf16 in `ws`, then the tcgen05 GEMM core.
@@ -794,9 +881,85 @@ extern "C" int gpsa_tc_gemm_test(int Mr, int Nc, int K, const float* A, const fl
   p.group_m = p.n_mt;
   p.kblocks = gpsa_cdiv(K, BK);
   set_split(p, split);
-  p.Mrows = Mr; p.Ncols = Nc; p.C = C; p.ldc = Nc;
+  p.Mrows = Mr; p.Ncols = Nc; p.C = C; p.ldc = Nc; p.alpha = 1.f;
   p.accumulate = p.n_split > 1;
   if (p.accumulate && cudaMemsetAsync(C, 0, sizeof(float) * (size_t)Mr * Nc, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  return launch_gemm<MODE_TEST>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+}
+
+// Generic tcgen05 GEMM on fp32 data: C[b] (op)= alpha * A[b] B[b]^T, 3-pass bf16 split, fp32 accumulate.
+//   A: Mr x K, element (i,k) at A[b*sA + i*lda + k] (a_rows_major = 1) or A[b*sA + k*lda + i] (= 0);  B likewise, Nc x K.
+//   out_mode 0: C[b*sC + i*ldc + j] = v      (split-K > 1: C is zeroed, then atomically accumulated)
+//   out_mode 1: C[j*ldc + i] += v            (transposed read-modify-write; batch must be 1, no split)
+extern "C" size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch) {
+  const size_t Kp = (size_t)rup(K, 8);
+  if (batch < 1) batch = 1;
+  return 2 * al256((size_t)batch * Mr * Kp * 2) + 2 * al256((size_t)batch * Nc * Kp * 2) + 256;
+}
+
+extern "C" int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, long lda, long sA, int a_rows_major,
+                            const float* B, long ldb, long sB, int b_rows_major, float* C, long ldc, long sC, float alpha,
+                            int out_mode, int split, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (Mr <= 0 || Nc <= 0 || K <= 0) return GPSA_OK;
+  if (batch < 1) batch = 1;
+  if (out_mode == 1 && batch != 1) return GPSA_ERR_ARG;
+  if (ws_bytes < gpsa_gemm_tc_ws_bytes(Mr, Nc, K, batch)) return GPSA_ERR_ARG;
+  const int Kp = (int)rup(K, 8);
+  const size_t sa = al256((size_t)batch * Mr * Kp * 2), sb = al256((size_t)batch * Nc * Kp * 2);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *a_hi = (__nv_bfloat16*)w, *a_lo = (__nv_bfloat16*)(w + sa), *b_hi = (__nv_bfloat16*)(w + 2 * sa),
+                *b_lo = (__nv_bfloat16*)(w + 2 * sa + sb);
+  auto pack = [&](long rows, const float* src, long ld, long sIn, int rows_major, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    if (rows_major) {
+      long blocks = (rows * K + 255) / 256;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      dim3 grid((unsigned)blocks, 1, batch);
+      pack_rows_kernel<<<grid, 256, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
+    } else {
+      dim3 grid(gpsa_cdiv(rows, 32), gpsa_cdiv(K, 32), batch), block(32, 8);
+      pack_trans_kernel<<<grid, block, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
+    }
+  };
+  pack(Mr, A, lda, sA, a_rows_major, a_hi, a_lo);
+  GPSA_LAUNCH_CHECK();
+  pack(Nc, B, ldb, sB, b_rows_major, b_hi, b_lo);
+  GPSA_LAUNCH_CHECK();
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const bool batched = batch > 1;
+  if (batched) {
+    const uint64_t da[3] = {(uint64_t)K, (uint64_t)Mr, (uint64_t)batch}, sa_[2] = {(uint64_t)Kp * 2, (uint64_t)Mr * Kp * 2};
+    const uint64_t db[3] = {(uint64_t)K, (uint64_t)Nc, (uint64_t)batch}, sb_[2] = {(uint64_t)Kp * 2, (uint64_t)Nc * Kp * 2};
+    const uint32_t ba[3] = {(uint32_t)BK, (uint32_t)TM, 1}, bb[3] = {(uint32_t)BK, (uint32_t)TN, 1};
+    if (make_tmap(&ta_hi, a_hi, 3, da, sa_, ba) || make_tmap(&ta_lo, a_lo, 3, da, sa_, ba) ||
+        make_tmap(&tb_hi, b_hi, 3, db, sb_, bb) || make_tmap(&tb_lo, b_lo, 3, db, sb_, bb))
+      return GPSA_ERR_CUDA;
+  } else {
+    if (make_tmap_2d(&ta_hi, a_hi, K, Mr, Kp, TM) || make_tmap_2d(&ta_lo, a_lo, K, Mr, Kp, TM) ||
+        make_tmap_2d(&tb_hi, b_hi, K, Nc, Kp, TN) || make_tmap_2d(&tb_lo, b_lo, K, Nc, Kp, TN))
+      return GPSA_ERR_CUDA;
+  }
+  GemmParams p = {};
+  p.n_mt = gpsa_cdiv(Mr, TM);
+  p.n_nt = gpsa_cdiv(Nc, TN);
+  p.group_m = p.n_mt < 32 ? p.n_mt : 32;
+  p.kblocks = gpsa_cdiv(K, BK);
+  if (split <= 0) {  // auto: split K until the grid covers the machine ~4 times, at least 16 K blocks per split
+    const long tiles = (long)p.n_mt * p.n_nt * batch;
+    split = 1;
+    if (tiles < 4L * sm_count()) split = (int)((4L * sm_count() + tiles - 1) / tiles);
+    const int max_split = p.kblocks / 16 > 0 ? p.kblocks / 16 : 1;
+    if (split > max_split) split = max_split;
+  }
+  if (out_mode == 1) split = 1;
+  set_split(p, split);
+  p.Mrows = Mr; p.Ncols = Nc; p.C = C; p.ldc = ldc; p.sC = sC; p.alpha = alpha;
+  p.batch = batched ? batch : 0;
+  p.trans_add = out_mode == 1;
+  p.accumulate = p.n_split > 1;
+  if (p.accumulate) {
+    if (ldc != Nc) return GPSA_ERR_ARG;
+    if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * Mr * Nc, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  }
   return launch_gemm<MODE_TEST>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
 }
 

@@ -104,6 +104,9 @@ SIGNATURES = {
     "gpsa_prior_prepare": [I, I, I, P, P, P, P, P, P, P, P, P, P],
     "gpsa_omega_prepare": [I, I, P, P, P, P, P, P, P],
     "gpsa_omega_grad": [I, I, P, P, P, P, P, P, P, P],
+    "gpsa_omega_grad_tc": [I, I, P, P, P, P, P, P, P, P, C.c_size_t, P],
+    "gpsa_gemm_tc_ws_bytes": [LNG, LNG, I, I],
+    "gpsa_gemm_tc": [LNG, LNG, I, I, P, LNG, LNG, I, P, LNG, LNG, I, P, LNG, LNG, F, I, I, P, C.c_size_t, P],
     "gpsa_feat_count": [I],
     "gpsa_feat_pack": [I, I, P, P, P],
     "gpsa_feat_unpack": [I, I, P, P, F, P, P, P],
@@ -124,7 +127,7 @@ SIGNATURES = {
     "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
 }
 _RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None,
-            "gpsa_quadform_tc_ws_bytes": C.c_size_t}
+            "gpsa_quadform_tc_ws_bytes": C.c_size_t, "gpsa_gemm_tc_ws_bytes": C.c_size_t}
 
 
 def _declare(l):

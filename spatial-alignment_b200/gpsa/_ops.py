@@ -114,13 +114,18 @@ def omega_prepare(Osq):
     return Omega, Ltril, L64, hld, info
 
 
-def omega_grad(Osq, L64, Obar, coef):
+def omega_grad(Osq, L64, Obar, coef, tc=False):
+    """Osq_bar = 2 (Obar + coef Omega^-1) Osq; tc=True runs the 2 Obar Osq product on the tcgen05 engine."""
     B, M, _ = Osq.shape
     Linv = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
     Y = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
     out = _new(Osq, B, M, M)
-    check(lib().gpsa_omega_grad(M, B, ptr(Osq), ptr(L64, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
-                                ptr(out), stream()), "omega_grad")
+    ws = None
+    if tc and M >= 32:
+        ws = torch.empty(int(lib().gpsa_gemm_tc_ws_bytes(M, M, M, B)), dtype=torch.uint8, device=Osq.device)
+    check(lib().gpsa_omega_grad_tc(M, B, ptr(Osq), ptr(L64, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
+                                   ptr(out), ptr(ws, torch.uint8), ws.numel() if ws is not None else 0, stream()),
+          "omega_grad")
     return out
 
 
@@ -300,7 +305,8 @@ class DataLayer(torch.autograd.Function):
                         tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
         check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
-        Osq_bar = omega_grad(Osq_F, L64, Obar, coef)
+        del tc_ws
+        Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine == 1))
         hyp = acc_hyp.to(f32)
         return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar, None
 

@@ -133,3 +133,35 @@ def test_data_layer_engines_agree(L, kind):
     names = ["F", "kl", "Gtilde", "log_ls", "log_var", "delta", "Omega_sqt", "G"]
     for name, x0, x1 in zip(names, outs[0], outs[1]):
         assert relerr(x1, x0) < 2e-4, name
+
+
+@pytest.mark.parametrize("Mr,Nc,K,batch,arm,brm,out_mode,split", [
+    (1000, 300, 200, 1, 0, 0, 0, 1),      # predictive mean: both operands stored K x rows
+    (200, 300, 5000, 1, 1, 0, 0, 0),      # delta-bar: auto split-K with atomics
+    (1000, 200, 300, 1, 1, 1, 1, 1),      # A-bar += ...: transposed read-modify-write
+    (200, 200, 200, 7, 1, 0, 0, 1),       # batched Omega-bar Omega_sqt with alpha = 2
+    (50, 50, 50, 3, 1, 0, 0, 1),
+])
+def test_gemm_tc_generic(L, Mr, Nc, K, batch, arm, brm, out_mode, split):
+    g = torch.Generator().manual_seed(Mr + Nc + K + batch)
+    A = torch.randn(batch, Mr, K, generator=g)
+    B = torch.randn(batch, Nc, K, generator=g)
+    alpha = 2.0 if batch > 1 else 1.0
+    ref = alpha * A.double() @ B.double().transpose(1, 2)
+    a = (A if arm else A.transpose(1, 2)).contiguous().cuda()
+    b = (B if brm else B.transpose(1, 2)).contiguous().cuda()
+    lda, ldb = (K if arm else Mr), (K if brm else Nc)
+    if out_mode == 1:
+        C0 = torch.randn(Nc, Mr, generator=g)
+        c = C0.clone().cuda()
+        ref = C0.double() + ref[0].T
+        ldc, sC = Mr, 0
+    else:
+        c = torch.full((batch, Mr, Nc), float("nan"), device="cuda")
+        ldc, sC = Nc, Mr * Nc
+    ws = torch.empty(int(L.lib().gpsa_gemm_tc_ws_bytes(Mr, Nc, K, batch)), dtype=u8, device="cuda")
+    rc = L.lib().gpsa_gemm_tc(Mr, Nc, K, batch, a.data_ptr(), lda, Mr * K, arm, b.data_ptr(), ldb, Nc * K, brm,
+                              c.data_ptr(), ldc, sC, alpha, out_mode, split, ws.data_ptr(), ws.numel(), stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert relerr(c.cpu().reshape(ref.shape), ref) < 2e-5
