@@ -11,6 +11,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <stdlib.h>
+
 template <typename T, int BM_, int BN_, int BK_, int TM_, int TN_>
 struct GemmCfg {
   using elem = T;
@@ -79,6 +81,49 @@ __device__ __forceinline__ void gemm_mainloop(const AL& al, const BL& bl, int m0
   }
 }
 
+// Same contraction with the NEXT k block's global loads issued (into registers) before the current block's FMAs,
+// so that a CTA overlaps its own memory latency even at one CTA per SM.  Needs loaders with load()/store().
+template <class C, class AL, class BL>
+__device__ __forceinline__ void gemm_mainloop_pf(const AL& al, const BL& bl, int m0, int n0, long k_begin, long k_end,
+                                                  typename C::elem* As, typename C::elem* Bs,
+                                                  typename C::elem (&acc)[C::TM][C::TN]) {
+  using T = typename C::elem;
+  const int tx = threadIdx.x % C::TX, ty = threadIdx.x / C::TX;
+  T ra[AL::NREG], rb[BL::NREG];
+  al.load(ra, m0, k_begin, k_end);
+  bl.load(rb, n0, k_begin, k_end);
+  for (long k0 = k_begin; k0 < k_end; k0 += C::BK) {
+    al.store(As, ra);
+    bl.store(Bs, rb);
+    __syncthreads();
+    if (k0 + C::BK < k_end) {
+      al.load(ra, m0, k0 + C::BK, k_end);
+      bl.load(rb, n0, k0 + C::BK, k_end);
+    }
+#pragma unroll
+    for (int kk = 0; kk < C::BK; ++kk) {
+      T a[C::TM], b[C::TN];
+#pragma unroll
+      for (int r = 0; r < C::TM; r += 4) {
+        T t[4];
+        ld4<T>(As + kk * C::LDA + tile_row<C>(ty, r), t);
+        a[r] = t[0]; a[r + 1] = t[1]; a[r + 2] = t[2]; a[r + 3] = t[3];
+      }
+#pragma unroll
+      for (int c = 0; c < C::TN; c += 4) {
+        T t[4];
+        ld4<T>(Bs + kk * C::LDB + tile_col<C>(tx, c), t);
+        b[c] = t[0]; b[c + 1] = t[1]; b[c + 2] = t[2]; b[c + 3] = t[3];
+      }
+#pragma unroll
+      for (int r = 0; r < C::TM; ++r)
+#pragma unroll
+        for (int c = 0; c < C::TN; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+}
+
 // Strided-view loader: element (i, k) at base[i*rs + k*cs], i < rows.  TI may differ from the
 // compute type (fp32 data feeding an fp64 accumulation).
 template <class C, typename TI, int B /*BM or BN*/, int LD>
@@ -86,6 +131,30 @@ struct StridedLoader {
   const TI* base;
   long rs, cs;
   long rows;
+  static constexpr int NREG = (B * C::BK + C::NT - 1) / C::NT;
+  // load(): this thread's share of the tile into registers; store(): registers -> shared (same index map as fill())
+  __device__ __forceinline__ void load(typename C::elem (&reg)[NREG], int r0, long k0, long k_end) const {
+    using T = typename C::elem;
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int idx = threadIdx.x + t * C::NT;
+      int i, kk;
+      if (cs == 1) { kk = idx % C::BK; i = idx / C::BK; } else { i = idx % B; kk = idx / B; }
+      const long gi = r0 + i, gk = k0 + kk;
+      reg[t] = (idx < B * C::BK && gi < rows && gk < k_end) ? T(base[gi * rs + gk * cs]) : T(0);
+    }
+  }
+  __device__ __forceinline__ void store(typename C::elem* S, const typename C::elem (&reg)[NREG]) const {
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int idx = threadIdx.x + t * C::NT;
+      if (idx < B * C::BK) {
+        int i, kk;
+        if (cs == 1) { kk = idx % C::BK; i = idx / C::BK; } else { i = idx % B; kk = idx / B; }
+        S[kk * LD + i] = reg[t];
+      }
+    }
+  }
   __device__ __forceinline__ void fill(typename C::elem* S, int r0, long k0, long k_end) const {
     using T = typename C::elem;
     if (cs == 1) {  // k contiguous in memory: consecutive threads walk k
@@ -109,13 +178,15 @@ struct StridedLoader {
 //   split_k > 1: gridDim.z = batch*split_k, partial products are atomically added to C
 //   (C must be pre-initialised, beta is ignored).
 //   lower_only: skip tiles strictly above the diagonal (symmetric/triangular outputs).
+//   tri: structure of op(A) used to trim the K range of a tile -- 1: op(A)(i,k) = 0 for k > i (lower triangular),
+//        2: op(A)(i,k) = 0 for k < i (upper triangular, e.g. the transpose of a lower factor).
 //   alpha_dev: optional device scalar(s) multiplied into alpha (per batch with stride 1, shared with stride 0).
 template <class C, typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long K, double alpha, const TA* A, long ars,
                                                               long acs, long sA, const TB* B, long brs, long bcs,
                                                               long sB, double beta, TC* Cm, long ldc, long sC,
                                                               int split_k, double diag, int lower_only,
-                                                              const float* alpha_dev, int alpha_dev_stride) {
+                                                              const float* alpha_dev, int alpha_dev_stride, int tri) {
   using T = typename C::elem;
   __shared__ __align__(16) T smem[C::SMEM_ELEMS];
   T* As = smem;
@@ -124,8 +195,10 @@ __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long 
   const int m0 = blockIdx.x * C::BM, n0 = blockIdx.y * C::BN;  // rows on x: R-sized row counts exceed the y limit
   if (lower_only && n0 > m0 + C::BM - 1) return;
   const long kchunk = ((K + split_k - 1) / split_k + C::BK - 1) / C::BK * C::BK;
-  const long k_begin = ks * kchunk;
-  const long k_end = (k_begin + kchunk < K) ? k_begin + kchunk : K;
+  long k_begin = ks * kchunk;
+  long k_end = (k_begin + kchunk < K) ? k_begin + kchunk : K;
+  if (tri == 1 && k_end > m0 + C::BM) k_end = m0 + C::BM;
+  if (tri == 2 && k_begin < m0) k_begin = (m0 / C::BK) * C::BK;
   StridedLoader<C, TA, C::BM, C::LDA> al{A + b * sA, ars, acs, M};
   StridedLoader<C, TB, C::BN, C::LDB> bl{B + b * sB, bcs, brs, N};  // "row" of the B tile is the column j
   T acc[C::TM][C::TN];
@@ -133,7 +206,7 @@ __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long 
   for (int r = 0; r < C::TM; ++r)
 #pragma unroll
     for (int c = 0; c < C::TN; ++c) acc[r][c] = T(0);
-  if (k_begin < k_end) gemm_mainloop<C>(al, bl, m0, n0, k_begin, k_end, As, Bs, acc);
+  if (k_begin < k_end) gemm_mainloop_pf<C>(al, bl, m0, n0, k_begin, k_end, As, Bs, acc);
   const int tx = threadIdx.x % C::TX, ty = threadIdx.x / C::TX;
   TC* Cb = Cm + b * sC;
   if (alpha_dev) alpha *= (double)alpha_dev[(long)b * alpha_dev_stride];  // device-resident scale (e.g. upstream dKL)
@@ -157,28 +230,45 @@ __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long 
   }
 }
 
-// Host-side launcher.  Picks a small or a large tile from the problem shape.
+// Host-side launcher.  Picks the tile from the problem shape: fp32 128x128 (8x8 micro-tile) when both extents
+// reach 96; fp64 an 8x8-micro-tile configuration (104 or 128 wide, whichever pads M x N less) for the batched
+// M x M algebra, else the 64x64 / 4x4 tile.
+template <class Cfg, typename TA, typename TB, typename TC>
+static void gemm_launch_cfg(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long ars, long acs, long sA,
+                            const TB* B, long brs, long bcs, long sB, double beta, TC* Cm, long ldc, long sC, int batch,
+                            int split_k, double diag, int lower_only, const float* alpha_dev, int alpha_dev_stride,
+                            int tri) {
+  dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
+  gemm_strided_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta,
+                                                                 Cm, ldc, sC, split_k, diag, lower_only, alpha_dev,
+                                                                 alpha_dev_stride, tri);
+}
+
 template <typename T, typename TA, typename TB, typename TC>
 static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long ars, long acs, long sA,
                         const TB* B, long brs, long bcs, long sB, double beta, TC* Cm, long ldc, long sC, int batch,
                         int split_k = 1, double diag = 0.0, int lower_only = 0, const float* alpha_dev = nullptr,
-                        int alpha_dev_stride = 0) {
+                        int alpha_dev_stride = 0, int tri = 0) {
   if (M <= 0 || N <= 0 || batch <= 0) return GPSA_OK;
   if (split_k < 1) split_k = 1;
-  const bool big = (sizeof(T) == 4) && M >= 96 && N >= 96;
-  if (big) {
-    using Cfg = GemmCfg<T, 128, 128, 8, 8, 8>;
-    dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
-    gemm_strided_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB,
-                                                                   beta, Cm, ldc, sC, split_k, diag, lower_only, alpha_dev,
-                                                                   alpha_dev_stride);
+#define GPSA_GEMM_ARGS st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, split_k, diag, \
+                       lower_only, alpha_dev, alpha_dev_stride, tri
+  if (sizeof(T) == 4) {
+    if (M >= 96 && N >= 96) gemm_launch_cfg<GemmCfg<T, 128, 128, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);
+    else gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
   } else {
-    using Cfg = GemmCfg<T, 64, 64, 16, 4, 4>;
-    dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
-    gemm_strided_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB,
-                                                                   beta, Cm, ldc, sC, split_k, diag, lower_only, alpha_dev,
-                                                                   alpha_dev_stride);
+    auto padded = [&](int t) { return (long)gpsa_cdiv(M, t) * t * ((long)gpsa_cdiv(N, t) * t); };
+    static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();  // experiments
+    if (force == 64) {
+      gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
+    } else if (M >= 96 && N >= 96) {
+      if (force == 104 || (force == 0 && padded(104) < padded(128))) gemm_launch_cfg<GemmCfg<T, 104, 104, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);
+      else gemm_launch_cfg<GemmCfg<T, 128, 128, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);
+    } else {
+      gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
+    }
   }
+#undef GPSA_GEMM_ARGS
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

@@ -220,6 +220,17 @@ __global__ void __launch_bounds__(256) kuf64_bwd_kernel(int M, long n, long chun
   }
 }
 
+// dst[b,i,j] = (float) src[b, max(i,j), min(i,j)]: fp32 copy of a symmetric matrix whose lower triangle is valid
+__global__ void cvt_sym_kernel(long n, int M, const double* __restrict__ src, float* __restrict__ dst) {
+  const long MM = (long)M * M;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const long b = idx / MM;
+    const int e = (int)(idx - b * MM);
+    const int i = e / M, j = e - i * M;
+    dst[idx] = (float)src[b * MM + (i >= j ? (long)i * M + j : (long)j * M + i)];
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void cvt_kernel(long n, const TS* __restrict__ src, TD* __restrict__ dst) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -687,9 +698,10 @@ extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, 
   if (M <= 0 || B <= 0) return GPSA_OK;
   const long MM = (long)M * M;
   // Omega = Osq Osq^T + 1e-5 I with fp64 accumulation, kept in fp64 for the factorisation
+  // (symmetric: only the tiles that touch the lower triangle are computed; the fp32 copy mirrors them)
   TRY((gemm_strided<double, float, float, double>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, L64, M, MM, B, 1,
-                                                  (double)GPSA_OFF)));
-  cvt_kernel<double, float><<<grid_for(MM * B), 256, 0, st>>>(MM * B, L64, Omega);
+                                                  (double)GPSA_OFF, 1)));
+  cvt_sym_kernel<<<grid_for(MM * B), 256, 0, st>>>(MM * B, M, L64, Omega);
   GPSA_LAUNCH_CHECK();
   TRY(gpsa_potrf_batched_f64(M, B, L64, half_logdet, info, st));
   cvt_kernel<double, float><<<grid_for(MM * B), 256, 0, st>>>(MM * B, L64, Ltril);
@@ -717,10 +729,11 @@ extern "C" int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* 
   if (coef) {
     // ... + 2 coef[b] Omega^-1 Osq, Omega^-1 = Linv^T Linv, in fp64
     TRY(gpsa_trtri_batched_f64(M, B, L64, Linv64, st));
+    // (Linv is lower triangular: the K range of each tile is trimmed to its non-zero part in both products)
     TRY((gemm_strided<double, double, float, double>(st, M, M, M, 1.0, Linv64, M, 1, MM, Osq, M, 1, MM, 0.0, Y64, M, MM,
-                                                     B)));
+                                                     B, 1, 0.0, 0, nullptr, 0, 1)));
     TRY((gemm_strided<double, double, double, float>(st, M, M, M, 2.0, Linv64, 1, M, MM, Y64, M, 1, MM, 1.0, Osq_bar, M,
-                                                     MM, B, 1, 0.0, 0, coef, 1)));
+                                                     MM, B, 1, 0.0, 0, coef, 1, 2)));
   }
   return GPSA_OK;
 }
