@@ -287,6 +287,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("GPSA_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.engine is not None:
         _ops.ENGINE["value"] = args.engine
