@@ -254,9 +254,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genes", type=int, default=None,
+                    help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
+                         "the JSON line is then NOT the named configuration and says so")
     ap.add_argument("--engine", type=int, default=None, help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 (default: auto)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
+    if args.genes is not None:
+        cfg["P"] = args.genes
+        cfg["desc"] += f" [REDUCED to {args.genes} genes: profiling aid, not the named configuration]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

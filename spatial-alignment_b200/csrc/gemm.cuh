@@ -259,7 +259,9 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
   } else {
     auto padded = [&](int t) { return (long)gpsa_cdiv(M, t) * t * ((long)gpsa_cdiv(N, t) * t); };
     static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();  // experiments
-    if (force == 64) {
+    // small problems (the per-view warp-layer products): the 8x8-micro-tile grid would not fill the machine
+    const long big_ctas = (long)gpsa_cdiv(M, 104) * gpsa_cdiv(N, 104) * batch * split_k;
+    if (force == 64 || (force == 0 && big_ctas < 2 * 148)) {
       gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
     } else if (M >= 96 && N >= 96) {
       if (force == 104 || (force == 0 && padded(104) < padded(128))) gemm_launch_cfg<GemmCfg<T, 104, 104, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);

@@ -38,6 +38,20 @@ def _zeros(like, *shape, dtype=f32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
+_SIDE = {}
+
+
+def _side_streams(device, n):
+    """A small pool of side streams per device: the views of the warp layer are independent and each is a chain of
+    small latency-bound kernels (M x M factorisation, M x n products), so they run concurrently and are joined back
+    into the caller's stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 def check_info(info, what):
     """Raise like torch.cholesky does when a matrix was not positive definite (this reads a device
     flag, i.e. it synchronises; callers gate it behind GPSA_B200_CHECK=1 / debug mode)."""
@@ -147,13 +161,20 @@ class WarpLayer(torch.autograd.Function):
         Omega_G, Ltril_G, L64_G, hld_G, info_G = omega_prepare(Osq_G)
         kl = _zeros(Xtilde, 1, dtype=f64)
         Lk_all = torch.full((V, M, M), float("nan"), dtype=f32, device=Xtilde.device)  # NaN rows for fixed views (:237-242)
-        ws64 = _new(Xtilde, 2 * M * M, dtype=f64)
         info = _zeros(Xtilde, V, dtype=i32)
         hldK = _zeros(Xtilde, V, dtype=f64)
         saved, outs = [], []
+        cur = torch.cuda.current_stream()
+        side = _side_streams(Xtilde.device, min(len(free), 4)) if len(free) > 1 else []
+        for s_ in side:
+            s_.wait_stream(cur)
+        keep = []
         for k, v in enumerate(free):
             X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
             n = X.shape[0]
+            ws64 = _new(Xtilde, 2 * M * M, dtype=f64)
+            keep.append(ws64)
+            st = C.c_void_p(side[k % len(side)].cuda_stream) if side else stream()
             Kinv = _new(X, M, M, dtype=f64)
             A, B, T = _new(X, M, n, dtype=f64), _new(X, M, n, dtype=f64), _new(X, D, M, n, dtype=f64)
             Ke, var = _new(X, D, M, dtype=f64), _new(X, n, D)
@@ -168,9 +189,12 @@ class WarpLayer(torch.autograd.Function):
                                 B=ptr(B, f64), T=ptr(T, f64), Ke=ptr(Ke, f64), var=ptr(var),
                                 Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
                                 kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64))
-                check(lib().gpsa_warp_view_fwd(C.byref(a), stream()), "warp_view_fwd")
+                check(lib().gpsa_warp_view_fwd(C.byref(a), st), "warp_view_fwd")
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
+        for s_ in side:
+            cur.wait_stream(s_)
+        del keep
         ctx.meta = meta
         ctx.save_for_backward(Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, L64_G, *saved)
         info_all = torch.cat([info_G, info])
@@ -188,9 +212,14 @@ class WarpLayer(torch.autograd.Function):
         klb = _c(kl_bar.to(f32).reshape(1)) if use_kl else None
         acc_Z, acc_dlt = _zeros(dev, V, M, D, dtype=f64), _zeros(dev, V, M, D, dtype=f64)
         acc_hyp = _zeros(dev, V, 2, dtype=f64)
-        Obar = _zeros(dev, V * D, M, M)
-        ws64 = _new(dev, 3 * M * M, dtype=f64)
         xgrads = []
+        cur = torch.cuda.current_stream()
+        live = [k for k in range(len(free)) if saved[7 * k].shape[0] > 0]
+        side = _side_streams(dev.device, min(len(live), 4)) if len(live) > 1 else []
+        for s_ in side:
+            s_.wait_stream(cur)
+        # views add into overlapping Omega-bar slices (v*D+j and j*V+v): one buffer per concurrent view, summed at the join
+        Obars, keep = [], []
         for k, v in enumerate(free):
             X, eps, Kinv, A, B, T, Ke = saved[7 * k: 7 * k + 7]
             n = X.shape[0]
@@ -198,6 +227,11 @@ class WarpLayer(torch.autograd.Function):
             xgrads += [None, None]
             if n == 0:
                 continue
+            st = C.c_void_p(side[len(Obars) % len(side)].cuda_stream) if side else stream()
+            if side or not Obars:
+                Obars.append(_zeros(dev, V * D, M, M))
+            Obar = Obars[-1]
+            ws64 = _new(dev, 3 * M * M, dtype=f64)
             gm = _c(gm) if gm is not None else None
             gs = _c(gs) if gs is not None else None
             mubar, varbar, q1bar = _new(dev, n, D), _new(dev, n, D), _new(dev, n)
@@ -213,7 +247,17 @@ class WarpLayer(torch.autograd.Function):
                             acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
                             mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar, f64),
                             C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64))
-            check(lib().gpsa_warp_view_bwd(C.byref(a), stream()), "warp_view_bwd")
+            check(lib().gpsa_warp_view_bwd(C.byref(a), st), "warp_view_bwd")
+            keep += [gm, gs, mubar, varbar, q1bar, Abar, Cm, AS, ws64]
+        for s_ in side:
+            cur.wait_stream(s_)
+        del keep
+        if not Obars:
+            Obar = _zeros(dev, V * D, M, M)
+        elif len(Obars) == 1:
+            Obar = Obars[0]
+        else:
+            Obar = torch.stack(Obars).sum(0)
         coef = None
         if use_kl:
             # d(-half_logdet Omega_{j*V+v})/dOmega = -1/2 Omega^-1 on the free views' KL slices only;
