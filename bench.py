@@ -254,6 +254,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole iteration from one CUDA graph (gpsa.graph.GraphedIteration); for the "
+                         "launch-bound toy configurations c1/c2")
     ap.add_argument("--genes", type=int, default=None,
                     help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
                          "the JSON line is then NOT the named configuration and says so")
@@ -314,10 +317,19 @@ def main():
     data_dev = {"expression": {"spatial_coords": data_dict["expression"]["spatial_coords"].cuda(),
                                "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    use_graph = args.graph and world == 1
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=use_graph)
     x_dev, y_dev = data_dev["expression"]["spatial_coords"], data_dev["expression"]["outputs"]
+    graphed = None
+    if use_graph:
+        from gpsa.graph import GraphedIteration
+
+        torch.manual_seed(999)
+        graphed = GraphedIteration(model, data_dev, opt, S)
 
     def step(it):
+        if graphed is not None:
+            return graphed.step()
         torch.manual_seed(1000 + it)
         _, _, _, F = model.forward({"expression": x_dev}, view_idx=view_idx, Ns=Ns, S=S)
         loss = model.loss_fn(data_dev, F)
@@ -440,7 +452,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "arithmetic": "fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; MxM factorisations fp64", "l2": "working set (Omega_sqt 320 MB, F/eps/var 1 GB each at c3) far exceeds the 126 MB L2",
-                   "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
+                   "cuda_graph": bool(use_graph), "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
         "e2e": {"value": e2e_value, "unit": "spot-samples/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
