@@ -166,15 +166,12 @@ class WarpLayer(torch.autograd.Function):
         saved, outs = [], []
         cur = torch.cuda.current_stream()
         side = _side_streams(Xtilde.device, min(len(free), 4)) if len(free) > 1 else []
-        for s_ in side:
-            s_.wait_stream(cur)
         keep = []
         for k, v in enumerate(free):
             X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
             n = X.shape[0]
             ws64 = _new(Xtilde, 2 * M * M, dtype=f64)
             keep.append(ws64)
-            st = C.c_void_p(side[k % len(side)].cuda_stream) if side else stream()
             Kinv = _new(X, M, M, dtype=f64)
             A, B, T = _new(X, M, n, dtype=f64), _new(X, M, n, dtype=f64), _new(X, D, M, n, dtype=f64)
             Ke, var = _new(X, D, M, dtype=f64), _new(X, n, D)
@@ -189,6 +186,11 @@ class WarpLayer(torch.autograd.Function):
                                 B=ptr(B, f64), T=ptr(T, f64), Ke=ptr(Ke, f64), var=ptr(var),
                                 Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
                                 kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64))
+                st = stream()
+                if side:
+                    # fork HERE: everything this view reads (copies, zero fills) has been enqueued on `cur` by now
+                    side[k % len(side)].wait_stream(cur)
+                    st = C.c_void_p(side[k % len(side)].cuda_stream)
                 check(lib().gpsa_warp_view_fwd(C.byref(a), st), "warp_view_fwd")
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
@@ -216,8 +218,6 @@ class WarpLayer(torch.autograd.Function):
         cur = torch.cuda.current_stream()
         live = [k for k in range(len(free)) if saved[7 * k].shape[0] > 0]
         side = _side_streams(dev.device, min(len(live), 4)) if len(live) > 1 else []
-        for s_ in side:
-            s_.wait_stream(cur)
         # views add into overlapping Omega-bar slices (v*D+j and j*V+v): one buffer per concurrent view, summed at the join
         Obars, keep = [], []
         for k, v in enumerate(free):
@@ -227,7 +227,7 @@ class WarpLayer(torch.autograd.Function):
             xgrads += [None, None]
             if n == 0:
                 continue
-            st = C.c_void_p(side[len(Obars) % len(side)].cuda_stream) if side else stream()
+            lane = len(Obars) % len(side) if side else 0
             if side or not Obars:
                 Obars.append(_zeros(dev, V * D, M, M))
             Obar = Obars[-1]
@@ -247,6 +247,11 @@ class WarpLayer(torch.autograd.Function):
                             acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
                             mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar, f64),
                             C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64))
+            st = stream()
+            if side:
+                # fork HERE, after this view's zero fills / contiguous copies were enqueued on `cur`
+                side[lane].wait_stream(cur)
+                st = C.c_void_p(side[lane].cuda_stream)
             check(lib().gpsa_warp_view_bwd(C.byref(a), st), "warp_view_bwd")
             keep += [gm, gs, mubar, varbar, q1bar, Abar, Cm, AS, ws64]
         for s_ in side:

@@ -159,3 +159,25 @@ def test_graphed_iteration_matches_eager():
     assert abs(losses[-1] - float(l)) < 0.2 * abs(float(l))
     for p in model.parameters():
         assert torch.isfinite(p).all()
+
+
+def test_iteration_survives_poisoned_allocator_blocks():
+    """The views of the warp layer run on side streams.  Re-run the same iteration after filling the caching
+    allocator's free blocks with NaN: any kernel that reads a buffer before its zero-fill / copy was ordered in
+    front of it (a fork placed too early) turns the gradients into NaN or changes them."""
+    from test_gpu_parity import build, run
+
+    g = Golden("v3_d3_free")
+    model, data_dict = build(g)
+    _, loss0 = run(g, model, data_dict)
+    ref = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    for rep in range(5):
+        poison = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(8)]
+        small = [torch.full((n,), float("nan"), device="cuda") for n in (64, 1000, 40000, 200000) for _ in range(8)]
+        del poison, small
+        _, loss = run(g, model, data_dict)
+        assert torch.isfinite(loss)
+        assert abs(float(loss) - float(loss0)) <= 1e-6 * abs(float(loss0))
+        for n, p in model.named_parameters():
+            assert torch.isfinite(p.grad).all(), n
+            assert relerr(p.grad.cpu(), ref[n].cpu()) < 1e-5, n
