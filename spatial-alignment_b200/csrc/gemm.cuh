@@ -230,6 +230,164 @@ __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp64 GEMM on the DMMA path (mma.sync.m8n8k4.f64): same contract as gemm_strided_kernel.
+// The fp64 pipe of B200 retires 64 FMA/clk/SM through DFMA and through DMMA alike (measured,
+// tools/mma_probe.cu); what DMMA buys is operand reuse in registers: a warp tile of WM x WN 8x8 atoms
+// needs WM + WN shared-memory loads per WM*WN atoms (256 FMA each), 5x less LDS traffic than the 8x8
+// SIMT micro-tile, which is LDS-bound at a quarter of the pipe.
+// ------------------------------------------------------------------------------------------------
+template <int BM_, int BN_, int BK_, int WM_, int WN_>
+struct DmmaCfg {
+  using elem = double;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_;
+  static constexpr int WARPS_M = BM / (8 * WM), WARPS_N = BN / (8 * WN), NT = 32 * WARPS_M * WARPS_N;
+  // leading dimensions = 4 (mod 16) doubles: the 16 lanes of a half-warp (4 k x 4 rows) hit 16 distinct 8-byte banks
+  static constexpr int pad16(int x) { return x + ((4 - x % 16) + 16) % 16; }
+  static constexpr int LDA = pad16(BM), LDB = pad16(BN);
+  static constexpr int SMEM_ELEMS = BK * (LDA + LDB);
+  static_assert(BM % (8 * WM) == 0 && BN % (8 * WN) == 0 && BK % 4 == 0, "tile / warp-tile mismatch");
+};
+
+// loader with the register stage kept in the INPUT type (fp32 operands cost half the registers)
+template <class C, typename TI, int B, int LD>
+struct DmmaLoader {
+  const TI* base;
+  long rs, cs;
+  long rows;
+  static constexpr int NREG = (B * C::BK + C::NT - 1) / C::NT;
+  __device__ __forceinline__ void load(TI (&reg)[NREG], int r0, long k0, long k_end) const {
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int idx = threadIdx.x + t * C::NT;
+      int i, kk;
+      if (cs == 1) { kk = idx % C::BK; i = idx / C::BK; } else { i = idx % B; kk = idx / B; }
+      const long gi = r0 + i, gk = k0 + kk;
+      reg[t] = (idx < B * C::BK && gi < rows && gk < k_end) ? base[gi * rs + gk * cs] : TI(0);
+    }
+  }
+  __device__ __forceinline__ void store(double* S, const TI (&reg)[NREG]) const {
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int idx = threadIdx.x + t * C::NT;
+      if (idx < B * C::BK) {
+        int i, kk;
+        if (cs == 1) { kk = idx % C::BK; i = idx / C::BK; } else { i = idx % B; kk = idx / B; }
+        S[kk * LD + i] = (double)reg[t];
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <class C, typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(C::NT, 1) gemm_dmma_kernel(int M, int N, long K, double alpha, const TA* A, long ars,
+                                                             long acs, long sA, const TB* B, long brs, long bcs, long sB,
+                                                             double beta, TC* Cm, long ldc, long sC, int split_k,
+                                                             double diag, int lower_only, const float* alpha_dev,
+                                                             int alpha_dev_stride, int tri) {
+  __shared__ __align__(16) double smem[C::SMEM_ELEMS];
+  double* As = smem;
+  double* Bs = smem + C::BK * C::LDA;
+  const int b = blockIdx.z / split_k, ks = blockIdx.z % split_k;
+  const int m0 = blockIdx.x * C::BM, n0 = blockIdx.y * C::BN;
+  if (lower_only && n0 > m0 + C::BM - 1) return;
+  const long kchunk = ((K + split_k - 1) / split_k + C::BK - 1) / C::BK * C::BK;
+  long k_begin = ks * kchunk;
+  long k_end = (k_begin + kchunk < K) ? k_begin + kchunk : K;
+  if (tri == 1 && k_end > m0 + C::BM) k_end = m0 + C::BM;
+  if (tri == 2 && k_begin < m0) k_begin = (m0 / C::BK) * C::BK;
+  DmmaLoader<C, TA, C::BM, C::LDA> al{A + b * sA, ars, acs, M};
+  DmmaLoader<C, TB, C::BN, C::LDB> bl{B + b * sB, bcs, brs, N};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[C::WM][C::WN][2];
+#pragma unroll
+  for (int mi = 0; mi < C::WM; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < C::WN; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  if (k_begin < k_end) {
+    TA ra[DmmaLoader<C, TA, C::BM, C::LDA>::NREG];
+    TB rb[DmmaLoader<C, TB, C::BN, C::LDB>::NREG];
+    al.load(ra, m0, k_begin, k_end);
+    bl.load(rb, n0, k_begin, k_end);
+    const double* Aw = As + wm * (8 * C::WM) + g + t * C::LDA;
+    const double* Bw = Bs + wn * (8 * C::WN) + g + t * C::LDB;
+    for (long k0 = k_begin; k0 < k_end; k0 += C::BK) {
+      al.store(As, ra);
+      bl.store(Bs, rb);
+      __syncthreads();
+      if (k0 + C::BK < k_end) {
+        al.load(ra, m0, k0 + C::BK, k_end);
+        bl.load(rb, n0, k0 + C::BK, k_end);
+      }
+#pragma unroll
+      for (int kk = 0; kk < C::BK; kk += 4) {
+        double a[C::WM];
+#pragma unroll
+        for (int mi = 0; mi < C::WM; ++mi) a[mi] = Aw[kk * C::LDA + mi * 8];
+        // B fragments in chunks of <= 7 atoms: keeps the live fragment registers low (the 13-warp tile has 104
+        // accumulator registers and a 128-register budget)
+        constexpr int CH = C::WN > 7 ? (C::WN + 1) / 2 : C::WN;
+#pragma unroll
+        for (int n0c = 0; n0c < C::WN; n0c += CH) {
+          double bf[CH];
+#pragma unroll
+          for (int ni = 0; ni < CH; ++ni)
+            if (n0c + ni < C::WN) bf[ni] = Bw[kk * C::LDB + (n0c + ni) * 8];
+#pragma unroll
+          for (int ni = 0; ni < CH; ++ni)
+            if (n0c + ni < C::WN) {
+#pragma unroll
+              for (int mi = 0; mi < C::WM; ++mi) dmma884(acc[mi][n0c + ni][0], acc[mi][n0c + ni][1], a[mi], bf[ni]);
+            }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  TC* Cb = Cm + b * sC;
+  if (alpha_dev) alpha *= (double)alpha_dev[(long)b * alpha_dev_stride];
+#pragma unroll
+  for (int mi = 0; mi < C::WM; ++mi) {
+    const int i = m0 + wm * (8 * C::WM) + mi * 8 + g;
+    if (i >= M) continue;
+#pragma unroll
+    for (int ni = 0; ni < C::WN; ++ni) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = n0 + wn * (8 * C::WN) + ni * 8 + 2 * t + e;
+        if (j >= N) continue;
+        double v = alpha * acc[mi][ni][e];
+        if (split_k > 1) {
+          if (k_begin < k_end) atomicAdd(&Cb[i * ldc + j], TC(v));
+        } else {
+          if (beta != 0.0) v += beta * (double)Cb[i * ldc + j];
+          if (i == j) v += diag;
+          Cb[i * ldc + j] = TC(v);
+        }
+      }
+    }
+  }
+}
+
+template <class Cfg, typename TA, typename TB, typename TC>
+static void gemm_launch_dmma(cudaStream_t st, int M, int N, long K, double alpha, const TA* A, long ars, long acs, long sA,
+                             const TB* B, long brs, long bcs, long sB, double beta, TC* Cm, long ldc, long sC, int batch,
+                             int split_k, double diag, int lower_only, const float* alpha_dev, int alpha_dev_stride,
+                             int tri) {
+  dim3 grid(gpsa_cdiv(M, Cfg::BM), gpsa_cdiv(N, Cfg::BN), batch * split_k);
+  gemm_dmma_kernel<Cfg, TA, TB, TC><<<grid, Cfg::NT, 0, st>>>(M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm,
+                                                              ldc, sC, split_k, diag, lower_only, alpha_dev,
+                                                              alpha_dev_stride, tri);
+}
+
 // Host-side launcher.  Picks the tile from the problem shape: fp32 128x128 (8x8 micro-tile) when both extents
 // reach 96; fp64 an 8x8-micro-tile configuration (104 or 128 wide, whichever pads M x N less) for the batched
 // M x M algebra, else the 64x64 / 4x4 tile.
@@ -261,6 +419,27 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
     static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();  // experiments
     // small problems (the per-view warp-layer products): the 8x8-micro-tile grid would not fill the machine
     const long big_ctas = (long)gpsa_cdiv(M, 104) * gpsa_cdiv(N, 104) * batch * split_k;
+    // DMMA path: a 208 x 104 CTA tile (13 warps, 16 x 104 each) when M pads well to 208 (the M = 200 algebra),
+    // else 128 x 128 (8 warps, 32 x 64 each); split-K is re-derived for the larger tile so the grid still fills the GPU
+    if (force == 0 && M >= 64 && N >= 64) {
+      const bool t208 = (long)gpsa_cdiv(M, 208) * 208 * ((long)gpsa_cdiv(N, 104) * 104) <=
+                        (long)gpsa_cdiv(M, 128) * 128 * ((long)gpsa_cdiv(N, 128) * 128);
+      const long tiles = t208 ? (long)gpsa_cdiv(M, 208) * gpsa_cdiv(N, 104) * batch
+                              : (long)gpsa_cdiv(M, 128) * gpsa_cdiv(N, 128) * batch;
+      int sk = split_k;
+      if (split_k > 1) {
+        long want = (2 * 148 + tiles - 1) / tiles;
+        const long smax = K / 512 > 0 ? K / 512 : 1;
+        if (want > smax) want = smax;
+        sk = (int)(want < 1 ? 1 : want);
+      }
+      if (tiles * sk >= 120 || split_k > 1) {
+        if (t208) gemm_launch_dmma<DmmaCfg<208, 104, 8, 2, 13>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
+        else gemm_launch_dmma<DmmaCfg<128, 128, 16, 4, 4>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
+        GPSA_LAUNCH_CHECK();
+        return GPSA_OK;
+      }
+    }
     if (force == 64 || (force == 0 && big_ctas < 2 * 148)) {
       gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
     } else if (M >= 96 && N >= 96) {

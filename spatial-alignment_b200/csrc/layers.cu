@@ -304,6 +304,20 @@ __global__ void sample_fwd_kernel(long total, int L, const float* __restrict__ k
     F[i] = fmaf(sqrtf(v), eps[i], F[i]);
   }
 }
+// same, one CTA per row r at a time (L >= 128): no 64-bit division per element
+__global__ void __launch_bounds__(256) sample_fwd_rows_kernel(long R, int L, const float* __restrict__ kq,
+                                                              const float* __restrict__ eps, float* __restrict__ F,
+                                                              float* __restrict__ var) {
+  for (long r = blockIdx.x; r < R; r += gridDim.x) {
+    const float k = kq[r];
+    const long base = r * L;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+      const float v = (k + var[base + p] + GPSA_OFF) + GPSA_OFF;
+      var[base + p] = v;
+      F[base + p] = fmaf(sqrtf(v), eps[base + p], F[base + p]);
+    }
+  }
+}
 
 // one warp per row r: Gm[r,p] = Fbar*eps/(2 sqrt(var)); q1bar[r] = -sum_p Gm; acc_hyp[1] += sigma2 * sum Gm
 __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const float* __restrict__ Fbar,
@@ -519,9 +533,15 @@ __global__ void __launch_bounds__(256) ll_fwd_kernel(long N, int P, int S, const
   const float inv = 1.f / sigma;
   const long NP = N * P, total = NP * S;
   double acc = 0.0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const float z = (Y[i % NP] - F[i]) * inv;
-    acc += (double)(z * z);
+  // one thread = one (spot, gene) for all S samples: Y is read once, no 64-bit modulo per element
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < NP; i += (long)gridDim.x * blockDim.x) {
+    const float y = Y[i];
+    float part = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float z = (y - F[(long)s * NP + i]) * inv;
+      part = fmaf(z, z, part);
+    }
+    acc += (double)part;
   }
   __shared__ double red[32];
   acc = block_sum<double>(acc, red);
@@ -542,11 +562,16 @@ __global__ void __launch_bounds__(256) ll_bwd_kernel(long N, int P, int S, const
   const float c = ll_bar[0] * inv * inv / (float)S;
   const long NP = N * P, total = NP * S;
   double acc = 0.0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const float d = Y[i % NP] - F[i];
-    F_bar[i] = c * d;
-    const float z = d * inv;
-    acc += (double)(z * z);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < NP; i += (long)gridDim.x * blockDim.x) {
+    const float y = Y[i];
+    float part = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float d = y - F[(long)s * NP + i];
+      F_bar[(long)s * NP + i] = c * d;
+      const float z = d * inv;
+      part = fmaf(z, z, part);
+    }
+    acc += (double)part;
   }
   __shared__ double red[32];
   acc = block_sum<double>(acc, red);
@@ -876,7 +901,8 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
     TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->var, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   }
-  sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
+  if (L >= 128) sample_fwd_rows_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(R, L, a->kq, a->eps, a->F, a->var);
+  else sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
   GPSA_LAUNCH_CHECK();
   // KD = K^-1 delta (fp64)
   TRY((gemm_nn<double, double, float, double>(st, M, L, M, 1.0, a->Kinv64, M, a->dlt, L, 0.0, a->KD, L)));
@@ -953,7 +979,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
 extern "C" int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
                                     double* ll_acc, cudaStream_t st) {
   if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
-  ll_fwd_kernel<<<grid_for(N * P * S, 1024, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_acc);
+  ll_fwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_acc);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -961,7 +987,7 @@ extern "C" int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const 
 extern "C" int gpsa_gaussian_ll_bwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
                                     const float* ll_bar, float* F_bar, double* acc_noise, cudaStream_t st) {
   if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
-  ll_bwd_kernel<<<grid_for(N * P * S, 1024, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_bar, F_bar, acc_noise);
+  ll_bwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_bar, F_bar, acc_noise);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

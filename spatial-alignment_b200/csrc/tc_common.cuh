@@ -59,6 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for a CONVERGED warp: the exit condition goes through a full-mask vote, which the compiler knows to be
+// warp-uniform -- loop state after the wait then stays in uniform registers (no R2UR chain in front of every
+// UTCHMMA / UTMALDG of a single-warp issue loop).
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -105,7 +105,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* rawfull = bars + 2 * NSTAGE + 4; // [NSTAGE]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NSTAGE + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are convergent for the compiler
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi);
     if (MODE != MODE_OMEGA) prefetch_tmap(&tmA_lo);
@@ -375,11 +376,13 @@ constexpr int FK = 32;                 // K elements per block
 constexpr int FROW = 64;               // bytes per operand row
 constexpr int FA_BYTES = TM * FROW;    // one A slab: 8 KB
 constexpr int FWD_MAXSLOT = 8;
+constexpr int FWD_MAXKB = 8;            // Mp <= 256
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 struct FwdParams {
   int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes;
   long R;
   float* q2;
-  int dbg;  // timing experiments only (GPSA_TC_DBG): 1 = dense N, 2 = no epilogue TMEM reads, 4 = no B loads
+  int dbg;  // timing experiments only (GPSA_TC_DBG): 2 = no epilogue TMEM reads, 4 = no B loads
 };
 struct FwdMaps {
   CUtensorMap a_hi, a_lo;    // At [R, Kp], box 32 x 128
@@ -401,7 +404,8 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   uint64_t* a_empty = a_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are convergent for the compiler
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm.a_hi);
     prefetch_tmap(&tm.a_lo);
@@ -422,31 +426,34 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   const int n_items = p.n_rt * p.gsplit;
   const int Mp = p.Mp, nkb = p.nkb;
 
-  // Producer and MMA warps run their loops CONVERGED (every lane waits on the barriers, all loop state is
-  // warp-uniform) and only the issue itself is predicated on elect.sync: the issuing thread of this kernel
-  // has ~60 cycles per MMA, so its instruction stream has to stay short.
+  // Producer and MMA warps run their loops CONVERGED and every barrier wait ends in a full-mask vote
+  // (mbar_wait_u), so the compiler keeps the loop state -- ring position, descriptors, barrier addresses -- in
+  // UNIFORM registers; the K loop of the MMA warp is fully unrolled, so the A-tile descriptors and the
+  // instruction descriptors (N shrinks with K) are immediates.  What is left per K block in the issuing
+  // thread is ~45 uniform-datapath instructions for 6 UTCHMMA; before this the same block cost ~90 instructions
+  // with a dozen R2UR round trips and the tensor pipe idled 40 % of the time waiting for the issue.
   if (warp == 0) {
     int slot = 0;
     uint32_t sphase = 0, aphase = 0;
     const int half_bytes = p.slot_bytes >> 1;
+    const bool leader = elect_one();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rt = item % p.n_rt, gs = item / p.n_rt;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait(a_empty, aphase ^ 1);
-      if (elect_one()) {
+      mbar_wait_u(a_empty, aphase ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(a_full, 2 * nkb * FA_BYTES);
         for (int kb = 0; kb < nkb; ++kb) {
           tma_load_2d(sA_hi + kb * FA_BYTES, &tm.a_hi, a_full, kb * FK, rt * TM);
           tma_load_2d(sA_lo + kb * FA_BYTES, &tm.a_lo, a_full, kb * FK, rt * TM);
         }
       }
-      __syncwarp();
       aphase ^= 1;
       for (int g = g0; g < g1; ++g) {
         for (int kb = nkb - 1; kb >= 0; --kb) {
           const int nrows = min(FK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
-          mbar_wait(&empty[slot], sphase ^ 1);
-          if (elect_one()) {
+          mbar_wait_u(&empty[slot], sphase ^ 1);
+          if (leader) {
             uint8_t* dst = ring + slot * p.slot_bytes;
             if (p.dbg & 4) {
               mbar_arrive(&full[slot]);
@@ -463,7 +470,6 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
               }
             }
           }
-          __syncwarp();
           if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
       }
@@ -471,53 +477,55 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   } else if (warp == 1) {
     int slot = 0, acc = 0;
     uint32_t sphase = 0, acc_phase = 0, aphase = 0;
-    const uint32_t half16 = (uint32_t)(p.slot_bytes >> 1) >> 4;  // hi -> lo block, in descriptor units
-    const uint64_t a_hi0 = make_desc_sw64(smem_u32(sA_hi));
-    const uint64_t a_lo0 = make_desc_sw64(smem_u32(sA_lo));
-    const uint64_t ring0 = make_desc_sw64(smem_u32(ring));
-    const uint32_t idesc0 = make_idesc_bf16(TM, 0);
+    // descriptors as (low word, constant high word): the low word carries the start address, so stepping through
+    // the tile is 32-bit arithmetic
+    const uint32_t DHI = (uint32_t)(make_desc_sw64(0) >> 32);
+    const uint32_t a_hi0 = (uint32_t)make_desc_sw64(smem_u32(sA_hi));
+    const uint32_t a_lo0 = (uint32_t)make_desc_sw64(smem_u32(sA_lo));
+    const uint32_t ring0 = (uint32_t)make_desc_sw64(smem_u32(ring));
+    const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, half16 = slot16 >> 1;  // slot / hi -> lo stride, descriptor units
+    constexpr uint32_t idesc0 = make_idesc_bf16(TM, 0);
+    const bool leader = elect_one();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int gs = item / p.n_rt;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait(a_full, aphase);
+      mbar_wait_u(a_full, aphase);
       aphase ^= 1;
       tc_fence_after();
       for (int g = g0; g < g1; ++g) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait_u(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * TN;
-        uint32_t accum = 0;  // the first MMA of a gene has N = Mp and initialises every column
-        for (int kb = nkb - 1; kb >= 0; --kb) {
-          mbar_wait(&full[slot], sphase);
+#pragma unroll
+        for (int kb = FWD_MAXKB - 1; kb >= 0; --kb) {
+          if (kb >= nkb) continue;  // uniform
+          mbar_wait_u(&full[slot], sphase);
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t b_hi = ring0 + (uint64_t)((uint32_t)(slot * p.slot_bytes) >> 4);
-            const uint64_t a_hi = a_hi0 + (uint64_t)((uint32_t)(kb * FA_BYTES) >> 4);
-            const uint64_t a_lo = a_lo0 + (uint64_t)((uint32_t)(kb * FA_BYTES) >> 4);
+          const uint32_t b_hi = ring0 + (uint32_t)slot * slot16;
+          if (leader) {
 #pragma unroll
             for (int k = FK / UMMA_K - 1; k >= 0; --k) {
               const int k0 = kb * FK + k * UMMA_K;
               if (k0 >= Mp) continue;
-              const uint32_t idesc = idesc0 | ((uint32_t)(((p.dbg >> 4) ? 16 * (p.dbg >> 4) : (p.dbg & 1) ? Mp : k0 + UMMA_K) >> 3) << 17);
-              const uint32_t off = (k * UMMA_K * 2) >> 4;
-              umma_bf16(d, a_hi + off, b_hi + off, idesc, accum);
-              umma_bf16(d, a_lo + off, b_hi + off, idesc, 1u);
-              umma_bf16(d, a_hi + off, b_hi + half16 + off, idesc, 1u);
-              accum = 1;
+              // N = k0 + 16: columns beyond it only meet structural zeros of the factor.  The first MMA of a gene
+              // (k0 = Mp - 16) therefore has N = Mp and initialises every accumulator column.
+              const uint32_t idesc = idesc0 | ((uint32_t)((k0 + UMMA_K) >> 3) << 17);
+              const uint32_t accum = (k0 != Mp - UMMA_K) ? 1u : 0u;
+              const uint32_t aoff = (uint32_t)((kb * FA_BYTES) >> 4) + (uint32_t)(k * UMMA_K * 2 >> 4);
+              const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
+              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
+              umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
+              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + half16 + boff, DHI), idesc, 1u);
             }
             umma_commit(&empty[slot]);
           }
-          __syncwarp();
-          accum = 1;
           if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);
-        __syncwarp();
+        if (leader) umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (elect_one()) umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
-      __syncwarp();
+      if (leader) umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
