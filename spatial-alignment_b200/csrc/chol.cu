@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "gpsa_b200.h"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int NB = 32;
@@ -40,9 +42,11 @@ __device__ __forceinline__ bool warp_potrf32(T* Dg, int kn) {
     else if (lane > j) r[j] *= inv;
     const T lij = r[j];
 #pragma unroll
-    for (int c = j + 1; c < NB; ++c) {
-      const T lcj = shfl(r[j], c);
-      if (lane >= c) r[c] -= lij * lcj;
+    for (int c = 0; c < NB; ++c) {  // static bounds: r[] stays in registers
+      if (c > j) {
+        const T lcj = shfl(r[j], c);
+        if (lane >= c) r[c] -= lij * lcj;
+      }
     }
   }
 #pragma unroll
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(256) potrf_kernel(int M, T* A, long stride, T*
         if (c < kn) {
           T s = x[c];
 #pragma unroll
-          for (int t = 0; t < c; ++t) s -= x[t] * Dg[c * LDP + t];
+          for (int t = 0; t < NB; ++t)
+            if (t < c) s -= x[t] * Dg[c * LDP + t];
           x[c] = s / Dg[c * LDP + c];
         }
       }
@@ -210,8 +215,310 @@ __global__ void __launch_bounds__(256) trtri_kernel(int M, const T* L, T* X, lon
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed in-shared-memory variants (one CTA of 512 threads per matrix): the whole lower triangle lives in shared
+// memory, row-major packed (element (i,j) at i(i+1)/2 + j), so neither factorisation nor inversion touches global
+// memory between the initial load and the final store.  fp64: M <= 208 (174 KB); fp32: M <= 300.
+// The panel kernels above round-trip the trailing matrix through L2 once per 32 columns and spend 0.4 ms on a
+// single 200 x 200 fp64 matrix; these are bound by the M barriers of the column sweep instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int PK_THREADS = 512;
+__host__ __device__ inline long pk(int i, int j) { return (long)i * (i + 1) / 2 + j; }
+
+// threads per row/column group: the largest power of two <= min(32, PK_THREADS / n)
+__device__ __forceinline__ int group_width(int n) {
+  int w = 32;
+  while (w > 1 && w * n > PK_THREADS) w >>= 1;
+  return w;
+}
+
+constexpr int PB = 16;        // panel width of the packed kernels
+constexpr int PLD = PB + 1;
+
+// Factor the identity-padded PB x PB diagonal block held one row per lane (lanes >= kn: identity rows).
+// On exit lane i holds row i of the factor in r[0..i].  Returns true on a non-positive pivot.
+template <typename T>
+__device__ __forceinline__ bool warp_potrf16(T (&r)[PB], int lane) {
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    T d = shfl(r[j], j);
+    if (!(d > T(0))) { bad = true; d = T(1); }
+    const T inv = rsqrt(d);  // <= 1 ulp; the pivot itself is d * rsqrt(d): no division, no second special function
+    d = d * inv;
+    if (lane == j) r[j] = d;
+    else if (lane > j) r[j] *= inv;
+    const T lij = r[j];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {  // static bounds: r[] stays in registers
+      if (c > j) {
+        const T lcj = shfl(r[j], c);
+        if (lane >= c) r[c] -= lij * lcj;
+      }
+    }
+  }
+  return bad;
+}
+
+// Right-looking blocked factorisation on the packed triangle: per 16-column panel, warp 0 factors the diagonal
+// block in registers, one thread per row solves the panel against it, and the trailing triangle is updated in
+// 8 x 4 register tiles (12 shared-memory loads per 32 FMAs).  The fp64 pipe of one SM (64 FMA/clk) bounds a
+// 200 x 200 matrix at ~25 us; the barriers and the serial diagonal blocks add about as much again.
+template <typename T>
+__global__ void __launch_bounds__(PK_THREADS, 1) potrf_packed_kernel(int M, T* A, long stride, T* half_logdet, int* info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Lp = reinterpret_cast<T*>(smem_raw);       // packed lower triangle
+  T* Dg = Lp + (long)M * (M + 1) / 2;           // [PB][PLD] current diagonal block
+  T* dinv = Dg + PB * PLD;                      // [PB]
+  T* Ab = A + (long)blockIdx.x * stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  for (long idx = tid; idx < (long)M * M; idx += PK_THREADS) {
+    const int i = idx / M, j = idx % M;
+    if (j <= i) Lp[pk(i, j)] = Ab[idx];
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < M; k0 += PB) {
+    const int kn = (M - k0 < PB) ? M - k0 : PB;
+    const int base = k0 + kn, rem = M - base;
+    if (warp == 0) {
+      T r[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c)
+        r[c] = (lane < kn && c <= lane) ? Lp[pk(k0 + lane, k0 + c)] : ((lane == c) ? T(1) : T(0));
+      const bool bad = warp_potrf16<T>(r, lane);
+      if (__any_sync(0xffffffffu, bad) && lane == 0) s_bad = 1;
+      if (lane < PB) {
+#pragma unroll
+        for (int c = 0; c < PB; ++c) {
+          Dg[lane * PLD + c] = (c <= lane) ? r[c] : T(0);
+          if (lane < kn && c <= lane) Lp[pk(k0 + lane, k0 + c)] = r[c];
+          if (c == lane) dinv[lane] = T(1) / r[c];
+        }
+      }
+    }
+    __syncthreads();
+    // panel: row i of A21 <- a_i L11^-T
+    for (int row = base + tid; row < M; row += PK_THREADS) {
+      T* ar = Lp + pk(row, k0);
+      T x[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) x[c] = (c < kn) ? ar[c] : T(0);
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        T s0 = x[c], s1 = T(0);  // two chains: halves the dependent-FMA latency of the substitution
+#pragma unroll
+        for (int t = 0; t < PB; ++t) {
+          if (t < c) {
+            if (t & 1) s1 -= x[t] * Dg[c * PLD + t];
+            else s0 -= x[t] * Dg[c * PLD + t];
+          }
+        }
+        x[c] = (s0 + s1) * dinv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c)
+        if (c < kn) ar[c] = x[c];
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: A22 -= P P^T in 8 (rows) x 4 (cols) tiles; row tile ti needs the
+    // column tiles 0 .. 2 ti + 1, i.e. tiles are enumerated as t = ti^2 + ti + tj
+    if (rem > 0) {
+      const int nrt = (rem + 7) / 8;
+      const int ntiles = nrt * nrt + nrt;
+      for (int t = tid; t < ntiles; t += PK_THREADS) {
+        int ti = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (ti * ti + ti > t) --ti;
+        while ((ti + 1) * (ti + 1) + (ti + 1) <= t) ++ti;
+        const int tj = t - ti * ti - ti;
+        const int i0 = base + 8 * ti, j0 = base + 4 * tj;
+        if (j0 >= M) continue;
+        const T* pa[8];
+        const T* pb[4];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) pa[a] = Lp + pk(min(i0 + a, M - 1), k0);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pb[b] = Lp + pk(min(j0 + b, M - 1), k0);
+        T acc[8][4];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+        for (int c = 0; c < kn; ++c) {
+          T va[8], vb[4];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) va[a] = pa[a][c];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) vb[b] = pb[b][c];
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += va[a] * vb[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int i = i0 + a;
+          if (i >= M) continue;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int j = j0 + b;
+            if (j <= i) Lp[pk(i, j)] -= acc[a][b];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (long idx = tid; idx < (long)M * M; idx += PK_THREADS) {
+    const int i = idx / M, j = idx % M;
+    Ab[idx] = (j <= i) ? Lp[pk(i, j)] : T(0);
+  }
+  T ld = 0;
+  for (int i = tid; i < M; i += PK_THREADS) ld += log(Lp[pk(i, i)]);
+  __shared__ T red[32];
+  ld = block_sum<T>(ld, red);
+  if (tid == 0) {
+    if (half_logdet) half_logdet[blockIdx.x] = ld;
+    if (info) info[blockIdx.x] = s_bad;
+  }
+}
+
+// In-place inversion of the packed factor by block rows of 16:
+//   X_II = L_II^-1,   X[I, 0:I0] = -X_II (L[I, 0:I0] X[0:I0, 0:I0]).
+// The block row of L is staged in a side buffer (it is overwritten by X[I, :]); the product W = L[I,:] X runs in
+// 4 x 4 register tiles with the contraction split over 4 adjacent lanes (the early block rows are short and would
+// otherwise leave most of the CTA idle), while one warp inverts the diagonal block.
+template <typename T>
+__global__ void __launch_bounds__(PK_THREADS, 1) trtri_packed_kernel(int M, const T* L, T* X, long stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Xp = reinterpret_cast<T*>(smem_raw);   // packed: L on entry, X on exit
+  T* stage = Xp + (long)M * (M + 1) / 2;    // [PB][M]  block row of L
+  T* Wst = stage + (long)PB * M;            // [PB][M]  W = L[I, 0:I0] X[0:I0, 0:I0]
+  T* Dg = Wst + (long)PB * M;               // [PB][PLD] L_II, then X_II
+  const T* Lb = L + (long)blockIdx.x * stride;
+  T* Xb = X + (long)blockIdx.x * stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (long idx = tid; idx < (long)M * M; idx += PK_THREADS) {
+    const int i = idx / M, j = idx % M;
+    if (j <= i) Xp[pk(i, j)] = Lb[idx];
+  }
+  __syncthreads();
+  for (int I0 = 0; I0 < M; I0 += PB) {
+    const int in = (M - I0 < PB) ? M - I0 : PB;
+    for (int idx = tid; idx < PB * I0; idx += PK_THREADS) {
+      const int i = idx / I0, t = idx % I0;
+      stage[i * M + t] = (i < in) ? Xp[pk(I0 + i, t)] : T(0);
+    }
+    for (int idx = tid; idx < PB * PB; idx += PK_THREADS) {
+      const int i = idx / PB, j = idx % PB;
+      Dg[i * PLD + j] = (i < in && j <= i) ? Xp[pk(I0 + i, I0 + j)] : ((i == j) ? T(1) : T(0));
+    }
+    __syncthreads();
+    if (warp == 15) {
+      // X_II by forward substitution: lane c solves L_II x = e_c; written back as column c (zeros above the diagonal)
+      T xcol[PB];
+      const int c = lane & (PB - 1);
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        T sacc = (i == c) ? T(1) : T(0);
+#pragma unroll
+        for (int t = 0; t < i; ++t) sacc -= Dg[i * PLD + t] * xcol[t];
+        xcol[i] = sacc / Dg[i * PLD + i];
+      }
+      __syncwarp();
+      if (lane < PB) {
+#pragma unroll
+        for (int i = 0; i < PB; ++i) Dg[i * PLD + c] = xcol[i];
+      }
+    }
+    // work item = (row group of 4, column group of 4, contraction split ks of 4); the loop bound is rounded up to a
+    // whole warp so that the shuffles below are executed by every lane
+    const int ncg = (I0 + 3) / 4;
+    const int nwork = 4 * ncg * 4;
+    const int nwork32 = (nwork + 31) & ~31;
+    for (int item = tid; item < nwork32; item += PK_THREADS) {
+      const bool valid = item < nwork;
+      const int ks = item & 3;
+      const int cg = valid ? (item >> 2) % ncg : 0, rg = valid ? (item >> 2) / ncg : 0;
+      const int c0 = cg * 4;
+      T acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+      if (valid) {
+        for (int t = c0 + ks; t < I0; t += 4) {
+          T lv[4], xv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) lv[a] = stage[(rg * 4 + a) * M + t];
+          const T* xr = Xp + pk(t, c0);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) xv[b] = (c0 + b <= t) ? xr[b] : T(0);  // X[t, c] = 0 above the diagonal
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += lv[a] * xv[b];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          T v = acc[a][b];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          acc[a][b] = v;
+        }
+      if (valid && ks == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (c0 + b < I0) Wst[(rg * 4 + a) * M + c0 + b] = acc[a][b];
+      }
+    }
+    __syncthreads();
+    // X[I, c] = -X_II W[:, c], and the diagonal block
+    for (int idx = tid; idx < in * I0; idx += PK_THREADS) {
+      const int i = idx / I0, c = idx % I0;
+      T sacc = T(0);
+#pragma unroll
+      for (int k = 0; k < PB; ++k) sacc -= Dg[i * PLD + k] * Wst[k * M + c];
+      Xp[pk(I0 + i, c)] = sacc;
+    }
+    for (int idx = tid; idx < in * in; idx += PK_THREADS) {
+      const int i = idx / in, j = idx % in;
+      if (j <= i) Xp[pk(I0 + i, I0 + j)] = Dg[i * PLD + j];
+    }
+    __syncthreads();
+  }
+  for (long idx = tid; idx < (long)M * M; idx += PK_THREADS) {
+    const int i = idx / M, j = idx % M;
+    Xb[idx] = (j <= i) ? Xp[pk(i, j)] : T(0);
+  }
+}
+
+template <typename T>
+size_t packed_smem(int M, int extra_rows) {
+  return ((size_t)M * (M + 1) / 2 + (size_t)extra_rows * M + PB * PLD + PB) * sizeof(T);
+}
+
 template <typename T>
 int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t st) {
+  static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+  const size_t psm = packed_smem<T>(M, 0);
+  if (!no_packed && psm <= 226 * 1024) {
+    static size_t attr = 0;
+    if (psm > 48 * 1024 && psm > attr) {
+      if (cudaFuncSetAttribute(potrf_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+        return GPSA_ERR_CUDA;
+      attr = 226 * 1024;
+    }
+    potrf_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, A, (long)M * M, half_logdet, info);
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
+  }
   const size_t smem = (size_t)(NB * LDP + (size_t)M * LDP) * sizeof(T);
   if (smem > 220 * 1024) return GPSA_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
@@ -224,6 +531,19 @@ int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t
 
 template <typename T>
 int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
+  static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+  const size_t psm = packed_smem<T>(M, 2 * PB);
+  if (!no_packed && psm <= 226 * 1024 && L != X) {
+    static size_t attr = 0;
+    if (psm > 48 * 1024 && psm > attr) {
+      if (cudaFuncSetAttribute(trtri_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+        return GPSA_ERR_CUDA;
+      attr = 226 * 1024;
+    }
+    trtri_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, L, X, (long)M * M);
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
+  }
   const size_t smem = (size_t)(NB * LDP + (size_t)M * NB) * sizeof(T);
   if (smem > 220 * 1024) return GPSA_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&

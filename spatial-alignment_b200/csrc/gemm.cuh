@@ -433,7 +433,7 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
         if (want > smax) want = smax;
         sk = (int)(want < 1 ? 1 : want);
       }
-      if (tiles * sk >= 120 || split_k > 1) {
+      if (tiles * sk >= 120) {
         if (t208) gemm_launch_dmma<DmmaCfg<208, 104, 8, 2, 13>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
         else gemm_launch_dmma<DmmaCfg<128, 128, 16, 4, 4>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
         GPSA_LAUNCH_CHECK();

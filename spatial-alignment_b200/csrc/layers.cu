@@ -26,9 +26,9 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 int pick_split(int M, int N, long K, int batch, int tile) {
   const long tiles = (long)gpsa_cdiv(M, tile) * gpsa_cdiv(N, tile) * batch;
-  if (tiles >= 296 || K < 4096) return 1;
+  if (tiles >= 296 || K < 1024) return 1;
   long s = (592 + tiles - 1) / tiles;
-  const long smax = K / 1024;
+  const long smax = K / 512;
   if (s > smax) s = smax;
   return s < 1 ? 1 : (int)s;
 }

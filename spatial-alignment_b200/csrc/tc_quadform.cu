@@ -379,7 +379,7 @@ constexpr int FWD_MAXSLOT = 8;
 constexpr int FWD_MAXKB = 8;            // Mp <= 256
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 struct FwdParams {
-  int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes;
+  int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes, ring_bytes;
   long R;
   float* q2;
   int dbg;  // timing experiments only (GPSA_TC_DBG): 2 = no epilogue TMEM reads, 4 = no B loads
@@ -389,13 +389,24 @@ struct FwdMaps {
   CUtensorMap b_hi[4], b_lo[4];  // Lt [L, Mp, Kp], boxes 32 x {128, 64, 32, 16} x 1
 };
 
+// CL = CTAs per cluster.  CL = 2: the two CTAs of a cluster work on two different 128-row tiles against the SAME gene
+// stream; each K block of the factor is fetched from L2 once per cluster -- CTA 0 issues the hi half, CTA 1 the lo
+// half, both as TMA multicasts into the same ring slot of both CTAs -- which halves the L2 -> shared-memory traffic
+// that bounds the single-CTA kernel (6.8 TB/s at C3).  A slot is released by both MMA warps (multicast commit).
+//
+// GR ("gene ring"): the factor ring holds exactly ONE gene, K block kb at the fixed offset 2048 kb (kb + 1) with its own
+// full/empty barrier pair, sized to its triangular extent (32 (kb+1) rows instead of Mp).  Block (g, kb) overwrites
+// block (g-1, kb) as soon as that one is consumed, so a whole gene of loads (112 KB at M = 200) is in flight ahead of
+// the MMA warp -- the uniform 4-slot ring kept ~50 KB in flight and the kernel waited on TMA latency.  Used whenever
+// the A tile and one gene fit in shared memory together (M <= 208); otherwise the uniform ring of p.nslot slots.
+template <int CL, bool GR>
 __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA_hi = smem;                           // [nkb][128 x 32]
   uint8_t* sA_lo = smem + p.nkb * FA_BYTES;        // [nkb][128 x 32]
   uint8_t* ring = smem + 2 * p.nkb * FA_BYTES;     // [nslot][hi: Mp x 32 | lo: Mp x 32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.nslot * p.slot_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ring_bytes);
   uint64_t* full = bars;                    // [FWD_MAXSLOT]
   uint64_t* empty = bars + FWD_MAXSLOT;     // [FWD_MAXSLOT]
   uint64_t* tfull = bars + 2 * FWD_MAXSLOT; // [2]
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
     for (int i = 0; i < 4; ++i) { prefetch_tmap(&tm.b_hi[i]); prefetch_tmap(&tm.b_lo[i]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -421,10 +432,15 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_rt * p.gsplit;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int n_rp = (p.n_rt + CL - 1) / CL;  // row-tile groups: CTA `crank` of a cluster takes tile rp * CL + crank
+  const int n_items = n_rp * p.gsplit;
   const int Mp = p.Mp, nkb = p.nkb;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
   // Producer and MMA warps run their loops CONVERGED and every barrier wait ends in a full-mask vote
   // (mbar_wait_u), so the compiler keeps the loop state -- ring position, descriptors, barrier addresses -- in
@@ -435,10 +451,9 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   if (warp == 0) {
     int slot = 0;
     uint32_t sphase = 0, aphase = 0;
-    const int half_bytes = p.slot_bytes >> 1;
     const bool leader = elect_one();
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int rt = item % p.n_rt, gs = item / p.n_rt;
+    for (int item = cid; item < n_items; item += ncl) {
+      const int rt = (item % n_rp) * CL + crank, gs = item / n_rp;  // rt may be >= n_rt in the last group: zero tile
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
       mbar_wait_u(a_empty, aphase ^ 1);
       if (leader) {
@@ -452,26 +467,46 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
       for (int g = g0; g < g1; ++g) {
         for (int kb = nkb - 1; kb >= 0; --kb) {
           const int nrows = min(FK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
+          if (GR) slot = kb;
           mbar_wait_u(&empty[slot], sphase ^ 1);
           if (leader) {
-            uint8_t* dst = ring + slot * p.slot_bytes;
+            uint8_t* dst = GR ? ring + 2048 * kb * (kb + 1) : ring + slot * p.slot_bytes;
+            const int half_bytes = GR ? nrows * FROW : (p.slot_bytes >> 1);
             if (p.dbg & 4) {
               mbar_arrive(&full[slot]);
             } else {
-              mbar_arrive_expect_tx(&full[slot], 2 * nrows * FROW);
+              mbar_arrive_expect_tx(&full[slot], 2 * nrows * FROW);  // both halves, whoever issues them
               int row = 0;
 #pragma unroll
               for (int hsel = 0; hsel < 4; ++hsel) {
                 const int hgt = 128 >> hsel;
                 for (; row + hgt <= nrows; row += hgt) {
-                  tma_load_3d(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g);
-                  tma_load_3d(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g);
+                  if (CL == 1) {
+                    tma_load_3d(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g);
+                    tma_load_3d(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g);
+                  } else if (crank == 0) {
+                    tma_load_3d_mc(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g, MC_MASK);
+                  } else {
+                    tma_load_3d_mc(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g, MC_MASK);
+                  }
                 }
               }
             }
           }
-          if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+          if (!GR && ++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
+        if (GR) sphase ^= 1;  // every barrier of the gene ring completes one phase per gene
+      }
+    }
+    if (CL > 1) {
+      // drain: the last use of every slot has been released by BOTH MMA warps, i.e. no multicast commit of the peer
+      // is still on its way to this CTA's barriers when it exits
+      const int ns = GR ? nkb : p.nslot;
+      if (GR) slot = 0;
+      for (int i = 0; i < ns; ++i) {
+        mbar_wait_u(&empty[slot], sphase ^ 1);
+        if (GR) ++slot;
+        else if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -486,8 +521,8 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
     const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, half16 = slot16 >> 1;  // slot / hi -> lo stride, descriptor units
     constexpr uint32_t idesc0 = make_idesc_bf16(TM, 0);
     const bool leader = elect_one();
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int gs = item / p.n_rt;
+    for (int item = cid; item < n_items; item += ncl) {
+      const int gs = item / n_rp;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
       mbar_wait_u(a_full, aphase);
       aphase ^= 1;
@@ -499,9 +534,11 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
 #pragma unroll
         for (int kb = FWD_MAXKB - 1; kb >= 0; --kb) {
           if (kb >= nkb) continue;  // uniform
+          if (GR) slot = kb;
           mbar_wait_u(&full[slot], sphase);
           tc_fence_after();
-          const uint32_t b_hi = ring0 + (uint32_t)slot * slot16;
+          const uint32_t b_hi = GR ? ring0 + (uint32_t)((2048 * kb * (kb + 1)) >> 4) : ring0 + (uint32_t)slot * slot16;
+          const uint32_t b_lo = b_hi + (GR ? (uint32_t)((kb + 1 < nkb ? FK * (kb + 1) : Mp) * FROW) >> 4 : half16);
           if (leader) {
 #pragma unroll
             for (int k = FK / UMMA_K - 1; k >= 0; --k) {
@@ -515,12 +552,14 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
               const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
               umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
               umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + half16 + boff, DHI), idesc, 1u);
+              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
             }
-            umma_commit(&empty[slot]);
+            if (CL == 1) umma_commit(&empty[slot]);
+            else umma_commit_mc(&empty[slot], MC_MASK);
           }
-          if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
+          if (!GR && ++slot == p.nslot) { slot = 0; sphase ^= 1; }
         }
+        if (GR) sphase ^= 1;
         if (leader) umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -532,8 +571,8 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int rt = item % p.n_rt, gs = item / p.n_rt;
+    for (int item = cid; item < n_items; item += ncl) {
+      const int rt = (item % n_rp) * CL + crank, gs = item / n_rp;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
       const long row = (long)rt * TM + q * 32 + lane;
       for (int g = g0; g < g1; ++g) {
@@ -575,6 +614,7 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1023,19 +1063,66 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   p.gsplit = (L + p.genes_per - 1) / p.genes_per;
   p.slot_bytes = 2 * f.Mp * FROW;  // one K block: hi rows, then lo rows
   const int fixed = 2 * f.nkb * FA_BYTES + 1024 + 256;
-  p.nslot = (232448 - fixed) / p.slot_bytes;
-  if (p.nslot > FWD_MAXSLOT) p.nslot = FWD_MAXSLOT;
-  if (p.nslot < 2) return GPSA_ERR_UNSUPPORTED;
-  const int smem_bytes = fixed + p.nslot * p.slot_bytes;
+  // gene ring: block kb at 2048 kb (kb+1), the top block (Mp rows) last
+  static const int want_gr = [] { const char* e = getenv("GPSA_FWD_GENE_RING"); return e ? atoi(e) : 1; }();
+  const int gr_bytes = 2048 * (f.nkb - 1) * f.nkb + 2 * f.Mp * FROW;
+  const bool gr = want_gr && fixed + gr_bytes <= 232448;
+  if (gr) {
+    p.nslot = f.nkb;
+    p.ring_bytes = gr_bytes;
+  } else {
+    p.nslot = (232448 - fixed) / p.slot_bytes;
+    if (p.nslot > FWD_MAXSLOT) p.nslot = FWD_MAXSLOT;
+    if (p.nslot < 2) return GPSA_ERR_UNSUPPORTED;
+    p.ring_bytes = p.nslot * p.slot_bytes;
+  }
+  const int smem_bytes = fixed + p.ring_bytes;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
-    if (cudaFuncSetAttribute(tc_qf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_qf_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
       return GPSA_ERR_CUDA;
     attr_bytes = smem_bytes;
   }
+  // clusters of 2 CTAs (multicast factor stream) whenever there are at least two row tiles per gene range
+  static const int want_cl = [] { const char* e = getenv("GPSA_FWD_CLUSTER"); return e ? atoi(e) : 2; }();
+  const int cl = (want_cl >= 2 && p.n_rt >= 2) ? 2 : 1;
+  if (cl == 2) {
+    // re-derive the gene split for row-tile PAIRS
+    const int n_rp = (p.n_rt + 1) / 2, ncl_max = sm_count() / 2;
+    p.gsplit = 1;
+    if (n_rp < ncl_max) {
+      p.gsplit = (ncl_max + n_rp - 1) / n_rp;
+      if (p.gsplit > L) p.gsplit = L;
+    }
+    p.genes_per = (L + p.gsplit - 1) / p.gsplit;
+    p.gsplit = (L + p.genes_per - 1) / p.genes_per;
+    const int n_items = n_rp * p.gsplit;
+    const int ncl = n_items < ncl_max ? n_items : ncl_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t rc = gr ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true>, maps, p)
+                              : cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, false>, maps, p);
+    if (rc != cudaSuccess) return GPSA_ERR_CUDA;
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
+  }
   const int n_items = p.n_rt * p.gsplit;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  tc_qf_fwd_kernel<<<grid, 256, smem_bytes, st>>>(maps, p);
+  if (gr) tc_qf_fwd_kernel<1, true><<<grid, 256, smem_bytes, st>>>(maps, p);
+  else tc_qf_fwd_kernel<1, false><<<grid, 256, smem_bytes, st>>>(maps, p);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

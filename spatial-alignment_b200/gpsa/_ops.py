@@ -165,7 +165,11 @@ class WarpLayer(torch.autograd.Function):
         hldK = _zeros(Xtilde, V, dtype=f64)
         saved, outs = [], []
         cur = torch.cuda.current_stream()
-        side = _side_streams(Xtilde.device, min(len(free), 4)) if len(free) > 1 else []
+        # meta["overlap"]: work that does not depend on the warp layer (the caller passes the preparation of the
+        # gene-batched Omega_F: large kernels).  It is enqueued on the caller's stream between fork and join, so the
+        # views' latency-bound chains of small kernels run underneath it.
+        overlap = meta.get("overlap")
+        side = _side_streams(Xtilde.device, min(len(free), 4)) if (len(free) > 1 or (overlap and free)) else []
         keep = []
         for k, v in enumerate(free):
             X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
@@ -194,6 +198,8 @@ class WarpLayer(torch.autograd.Function):
                 check(lib().gpsa_warp_view_fwd(C.byref(a), st), "warp_view_fwd")
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
+        if overlap:
+            overlap()
         for s_ in side:
             cur.wait_stream(s_)
         del keep

@@ -230,8 +230,16 @@ class VariationalGPSA(GPSA):
 
         if not self._kl_mask_ready(free):
             self._set_kl_mask(free)
+        # Omega_F = Omega_sqt Omega_sqt^T + eps I and its factor do not depend on the warp layer: prepared while the
+        # per-view chains run on their side streams (see _ops.WarpLayer.forward)
+        pre_F = {}
+
+        def _prepare_omega_F():
+            for mod in mods:
+                pre_F[mod] = _ops.omega_prepare(self.Omega_sqt_F_dict[mod].detach().contiguous())
+
         meta = {"kind": _ops.KINDS[self._kind_warp], "V": V, "S": S, "free": free, "with_kl": True,
-                "kl_mask": self._kl_mask}
+                "kl_mask": self._kl_mask, "overlap": _prepare_omega_F}
         flat = []
         for vv in free:
             flat += [X_views[vv], eps_G[vv]]
@@ -283,7 +291,7 @@ class VariationalGPSA(GPSA):
             L = self.n_latent_outputs[mod]
             N = int(Ns[mod])
             Osq = self.Omega_sqt_F_dict[mod]
-            pre = _ops.omega_prepare(Osq.detach().contiguous())
+            pre = pre_F[mod] if mod in pre_F else _ops.omega_prepare(Osq.detach().contiguous())
             eps_F = _eps["F"][mod].to(dev, torch.float32) if _eps is not None else torch.randn(S, N, L, device=dev)
             F_lat, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayer.apply(
                 {"kind": kind_d, "with_kl": True, "omega": pre},
