@@ -399,7 +399,16 @@ struct FwdMaps {
 // block (g-1, kb) as soon as that one is consumed, so a whole gene of loads (112 KB at M = 200) is in flight ahead of
 // the MMA warp -- the uniform 4-slot ring kept ~50 KB in flight and the kernel waited on TMA latency.  Used whenever
 // the A tile and one gene fit in shared memory together (M <= 208); otherwise the uniform ring of p.nslot slots.
-template <int CL, bool GR>
+//
+// NTS ("TMEM A"): the hi half of the first NTS K steps of the resident A tile is also copied into the TMEM columns the
+// accumulators leave free ([Mp, Mp + 8 NTS)) by the epilogue warps at the start of a work item, and the hi*hi and
+// hi*lo passes of those K steps use the TS form of tcgen05.mma.  An SS-form MMA fetches its 4 KB A operand from
+// shared memory every time -- that fetch is the 58-cycle floor of the small-N steps -- while the TS form costs
+// N/2 + 10..19 cycles (tools/mma_probe.cu).  Measured at C3: NTS = 4 (the steps with N <= 64, where TS is cheaper per
+// MMA) 31.4 ms, NTS = 12 (everything the free TMEM columns hold; 96 KB less shared-memory traffic per (tile, gene))
+// 29.2 ms, NTS = 0 31.6 ms.  NTS is a template parameter: with a run-time count both forms of every MMA were emitted
+// and the issue loop spilled uniform registers (32.6 - 38 ms).
+template <int CL, bool GR, int NTS>
 __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -413,7 +422,8 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   uint64_t* tempty = tfull + 2;             // [2]
   uint64_t* a_full = tempty + 2;
   uint64_t* a_empty = a_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+  uint64_t* ta_full = a_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_full + 1);
 
   // warp index through a shuffle: provably warp-uniform, so the role branches below are convergent for the compiler
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -427,6 +437,7 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
+    mbar_init(ta_full, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -525,6 +536,7 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
       const int gs = item / n_rp;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
       mbar_wait_u(a_full, aphase);
+      if (NTS > 0) mbar_wait_u(ta_full, aphase);  // the epilogue warps have copied A_hi into TMEM for this item
       aphase ^= 1;
       tc_fence_after();
       for (int g = g0; g < g1; ++g) {
@@ -550,9 +562,17 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
               const uint32_t accum = (k0 != Mp - UMMA_K) ? 1u : 0u;
               const uint32_t aoff = (uint32_t)((kb * FA_BYTES) >> 4) + (uint32_t)(k * UMMA_K * 2 >> 4);
               const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
-              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
-              umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-              umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
+              const int ks = kb * (FK / UMMA_K) + k;
+              if (ks < NTS) {
+                const uint32_t a_t = tmem_base + (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));  // NTS > 6: Mp <= 208
+                umma_bf16_ts(d, a_t, desc64(b_hi + boff, DHI), idesc, accum);
+                umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
+                umma_bf16_ts(d, a_t, desc64(b_lo + boff, DHI), idesc, 1u);
+              } else {
+                umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
+                umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
+                umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
+              }
             }
             if (CL == 1) umma_commit(&empty[slot]);
             else umma_commit_mc(&empty[slot], MC_MASK);
@@ -569,12 +589,32 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, ta_phase = 0;
     const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
     for (int item = cid; item < n_items; item += ncl) {
       const int rt = (item % n_rp) * CL + crank, gs = item / n_rp;
       const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
       const long row = (long)rt * TM + q * 32 + lane;
+      if (NTS > 0) {
+        // every MMA of the previous item has completed (its last tfull was consumed above), so the TMEM copy of
+        // A_hi can be replaced: thread = row, 32 bytes (one K step) per tcgen05.st out of the swizzled smem tile
+        mbar_wait(a_full, ta_phase);
+        ta_phase ^= 1;
+        const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
+#pragma unroll
+        for (int ks = 0; ks < NTS; ++ks) {
+          const uint8_t* src = sA_hi + (ks >> 1) * FA_BYTES + rl * FROW;
+          const int c = (ks & 1) * 2;
+          const uint4 v0 = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+          const uint4 v1 = *reinterpret_cast<const uint4*>(src + (((c + 1) ^ sw) << 4));
+          const uint32_t col = (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
+          tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + col, v0, v1);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ta_full);
+      }
       for (int g = g0; g < g1; ++g) {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
@@ -1079,13 +1119,20 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   const int smem_bytes = fixed + p.ring_bytes;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
-    if (cudaFuncSetAttribute(tc_qf_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_qf_fwd_kernel<1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
       return GPSA_ERR_CUDA;
     attr_bytes = smem_bytes;
   }
+  // A_hi in TMEM (gene-ring variants): 12 of the 13 K steps when Mp = 208 (both column gaps, 96 columns), else the
+  // first 4 K steps if 32 columns are free next to the accumulator.  GPSA_FWD_TMEM_A=0/4 overrides (experiments).
+  static const int want_ta = [] { const char* e = getenv("GPSA_FWD_TMEM_A"); return e ? atoi(e) : 12; }();
+  const bool ta = want_ta > 0 && gr && (TN - f.Mp) >= 32 && f.Mp >= 5 * UMMA_K;
   // clusters of 2 CTAs (multicast factor stream) whenever there are at least two row tiles per gene range
   static const int want_cl = [] { const char* e = getenv("GPSA_FWD_CLUSTER"); return e ? atoi(e) : 2; }();
   const int cl = (want_cl >= 2 && p.n_rt >= 2) ? 2 : 1;
@@ -1113,16 +1160,19 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    const cudaError_t rc = gr ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true>, maps, p)
-                              : cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, false>, maps, p);
+    const cudaError_t rc = (ta && want_ta == 12 && f.Mp == 208) ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 12>, maps, p)
+                           : ta ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 4>, maps, p)
+                           : gr ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 0>, maps, p)
+                                : cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, false, 0>, maps, p);
     if (rc != cudaSuccess) return GPSA_ERR_CUDA;
     GPSA_LAUNCH_CHECK();
     return GPSA_OK;
   }
   const int n_items = p.n_rt * p.gsplit;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  if (gr) tc_qf_fwd_kernel<1, true><<<grid, 256, smem_bytes, st>>>(maps, p);
-  else tc_qf_fwd_kernel<1, false><<<grid, 256, smem_bytes, st>>>(maps, p);
+  if (ta) tc_qf_fwd_kernel<1, true, 4><<<grid, 256, smem_bytes, st>>>(maps, p);
+  else if (gr) tc_qf_fwd_kernel<1, true, 0><<<grid, 256, smem_bytes, st>>>(maps, p);
+  else tc_qf_fwd_kernel<1, false, 0><<<grid, 256, smem_bytes, st>>>(maps, p);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

@@ -48,6 +48,103 @@ __global__ void __launch_bounds__(128, 1) mma_chain_kernel(int N, int chains, in
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// same chain with the A operand in TENSOR MEMORY (tcgen05.mma TS form): does the ~58-cycle floor of small-N MMAs
+// (the 4 KB A fetch from shared memory) go away?
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) mma_chain_ts_kernel(int N, int iters, int mix, long long* out, float* check) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 8192;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8192 + 16384);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  // B = identity-like pattern: B[n][k] = (n == k) ? 1 : 0 for the first 16 columns (K-major rows of 64 B, SW64)
+  for (int i = threadIdx.x; i < (8192 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int n = threadIdx.x, k = threadIdx.x;  // element (row n, col k) of B, bf16 1.0 = 0x3F80
+    const int chunk = (k >> 3) ^ ((n >> 1) & 3);
+    reinterpret_cast<uint16_t*>(sB + n * 64 + chunk * 16)[k & 7] = 0x3F80;
+  }
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  // A in TMEM columns 448..455: row r (lane) holds bf16 pairs (k = 2c, 2c+1) = (r + 2c, r + 2c + 1) as small integers
+  {
+    uint32_t v[8];
+    const int r = threadIdx.x;
+    for (int c = 0; c < 8; ++c) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn((float)((r + 2 * c) & 63), (float)((r + 2 * c + 1) & 63));
+      v[c] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 448;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const uint64_t a = make_desc_sw64(smem_u32(sA)), b = make_desc_sw64(smem_u32(sB));
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      __syncwarp();
+      t0 = clock64();
+      if (elect_one()) {
+        for (int i = 0; i < iters; ++i) {
+          if (mix && (i % 3 == 1)) umma_bf16(tmem, a, b, idesc, i > 0 ? 1u : 0u);  // 2 TS : 1 SS like the 3-pass product
+          else umma_bf16_ts(tmem, tmem + 448, b, idesc, i > 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, rep & 1);
+      t1 = clock64();
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // numerical check of the TS layout: one fresh MMA D = A * B^T with N = 16 -> D[r][n] = A[r][n]
+  if (check) {
+    if (warp == 0) {
+      if (elect_one()) {
+        umma_bf16_ts(tmem + 256, tmem + 448, make_desc_sw64(smem_u32(sB)), make_idesc_bf16(128, 16), 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + 256, v);
+    tmem_ld_wait();
+    for (int n = 0; n < 16; ++n) check[threadIdx.x * 16 + n] = __uint_as_float(v[n]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 // fp64 throughput probes: 8 independent accumulator chains per thread
 __global__ void dfma_kernel(int iters, double* out, long long* cyc) {
   double a[8], x = 1.0000001 + threadIdx.x * 1e-9, y = 1e-9;
@@ -117,6 +214,32 @@ int main() {
   cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
   printf("148 CTAs, N=112, 2 chains: %.1f cycles/MMA\n", (double)h / (iters * 8));
 
+  {
+    cudaFuncSetAttribute(mma_chain_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    float* d_chk;
+    cudaMalloc(&d_chk, 128 * 16 * 4);
+    printf("A operand in TMEM (TS form): cycles per MMA\n%6s %8s %8s %8s\n", "N", "TS", "2TS:1SS", "N/2");
+    for (int N : Ns) {
+      printf("%6d", N);
+      for (int mix : {0, 1}) {
+        mma_chain_ts_kernel<<<1, 128, smem>>>(N, 510, mix, d_out, nullptr);
+        long long hh = 0;
+        cudaError_t e = cudaMemcpy(&hh, d_out, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf(" err:%s\n", cudaGetErrorString(e)); return 1; }
+        printf(" %8.1f", (double)hh / 510);
+      }
+      printf(" %8.1f\n", N / 2.0);
+    }
+    mma_chain_ts_kernel<<<1, 128, smem>>>(16, 3, 0, d_out, d_chk);
+    float hc[128 * 16];
+    cudaError_t e = cudaMemcpy(hc, d_chk, sizeof(hc), cudaMemcpyDeviceToHost);
+    int bad = 0;
+    for (int r = 0; r < 128; ++r)
+      for (int n = 0; n < 16; ++n)
+        if (hc[r * 16 + n] != (float)((r + n) & 63)) ++bad;
+    printf("TS layout check (lane = row, column c = bf16 pair (2c, 2c+1)): %s, %d mismatches; row 5: %g %g %g %g ... (%s)\n",
+           bad ? "MISMATCH" : "ok", bad, hc[80], hc[81], hc[82], hc[83], cudaGetErrorString(e));
+  }
   double* d_d;
   cudaMalloc(&d_d, 148 * 8 * 1024 * 8);
   for (int threads : {128, 256, 512, 1024}) {
