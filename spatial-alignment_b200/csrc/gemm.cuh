@@ -237,10 +237,10 @@ __global__ void __launch_bounds__(C::NT) gemm_strided_kernel(int M, int N, long 
 // needs WM + WN shared-memory loads per WM*WN atoms (256 FMA each), 5x less LDS traffic than the 8x8
 // SIMT micro-tile, which is LDS-bound at a quarter of the pipe.
 // ------------------------------------------------------------------------------------------------
-template <int BM_, int BN_, int BK_, int WM_, int WN_>
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int MINB_ = 1>
 struct DmmaCfg {
   using elem = double;
-  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, MINB = MINB_;
   static constexpr int WARPS_M = BM / (8 * WM), WARPS_N = BN / (8 * WN), NT = 32 * WARPS_M * WARPS_N;
   // leading dimensions = 4 (mod 16) doubles: the 16 lanes of a half-warp (4 k x 4 rows) hit 16 distinct 8-byte banks
   static constexpr int pad16(int x) { return x + ((4 - x % 16) + 16) % 16; }
@@ -286,7 +286,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <class C, typename TA, typename TB, typename TC>
-__global__ void __launch_bounds__(C::NT, 1) gemm_dmma_kernel(int M, int N, long K, double alpha, const TA* A, long ars,
+__global__ void __launch_bounds__(C::NT, C::MINB) gemm_dmma_kernel(int M, int N, long K, double alpha, const TA* A, long ars,
                                                              long acs, long sA, const TB* B, long brs, long bcs, long sB,
                                                              double beta, TC* Cm, long ldc, long sC, int split_k,
                                                              double diag, int lower_only, const float* alpha_dev,
@@ -419,12 +419,13 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
     static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();  // experiments
     // small problems (the per-view warp-layer products): the 8x8-micro-tile grid would not fill the machine
     const long big_ctas = (long)gpsa_cdiv(M, 104) * gpsa_cdiv(N, 104) * batch * split_k;
-    // DMMA path: a 208 x 104 CTA tile (13 warps, 16 x 104 each) when M pads well to 208 (the M = 200 algebra),
-    // else 128 x 128 (8 warps, 32 x 64 each); split-K is re-derived for the larger tile so the grid still fills the GPU
+    // DMMA path: 104 x 104 CTA tiles (13 warps, 8 x 104 each) when M pads well to 208 (the M = 200 algebra), else
+    // 128 x 128 (8 warps, 32 x 64 each, one CTA per SM); split-K is re-derived for the tile so the grid still
+    // fills the GPU
     if (force == 0 && M >= 64 && N >= 64) {
       const bool t208 = (long)gpsa_cdiv(M, 208) * 208 * ((long)gpsa_cdiv(N, 104) * 104) <=
                         (long)gpsa_cdiv(M, 128) * 128 * ((long)gpsa_cdiv(N, 128) * 128);
-      const long tiles = t208 ? (long)gpsa_cdiv(M, 208) * gpsa_cdiv(N, 104) * batch
+      const long tiles = t208 ? (long)gpsa_cdiv(M, 104) * gpsa_cdiv(N, 104) * batch
                               : (long)gpsa_cdiv(M, 128) * gpsa_cdiv(N, 128) * batch;
       int sk = split_k;
       if (split_k > 1) {
@@ -434,7 +435,11 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
         sk = (int)(want < 1 ? 1 : want);
       }
       if (tiles * sk >= 120) {
-        if (t208) gemm_launch_dmma<DmmaCfg<208, 104, 8, 2, 13>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
+        // 104 x 104 tiles, 13 warps of 8 x 104, 72 registers -> two CTAs per SM (measured 1.7x a 208 x 104 tile at one
+        // CTA per SM); on the symmetric / triangular M x M algebra they also skip the upper-right quarter of the
+        // output (lower_only) or a quarter of the K range (tri)
+        if (t208)
+          gemm_launch_dmma<DmmaCfg<104, 104, 8, 1, 13, 2>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
         else gemm_launch_dmma<DmmaCfg<128, 128, 16, 4, 4>, TA, TB, TC>(st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, sk, diag, lower_only, alpha_dev, alpha_dev_stride, tri);
         GPSA_LAUNCH_CHECK();
         return GPSA_OK;
