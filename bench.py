@@ -271,7 +271,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     S, N = cfg["S"], cfg["V"] * cfg["Nv"]
     workload = (f"{args.config}: {cfg['desc']}, D={cfg['D']}, M_X=M_G={cfg['M']}, S={cfg['S']}, {cfg['kernel']}, "
-                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step")
+                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step (torch.optim.Adam, fused=True)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -318,7 +318,7 @@ def main():
                                "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
     use_graph = args.graph and world == 1
-    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=use_graph)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=use_graph, fused=True)
     x_dev, y_dev = data_dev["expression"]["spatial_coords"], data_dev["expression"]["outputs"]
     graphed = None
     if use_graph:
