@@ -9,7 +9,8 @@
  *
  * Shapes use the symbols of SURVEY.md:  M inducing points, D spatial dims (1..3), R = S*N rows
  * (Monte-Carlo sample s, spot n; r = s*N + n), L latent outputs (genes), V views.
- * Kernel kinds: 0 = rbf (gpsa/util/util.py:8-23), 1 = matern12 (gpsa/util/util.py:33-47).
+ * Kernel kinds: 0 = rbf (gpsa/util/util.py:8-23), 1 = matern12 (gpsa/util/util.py:33-47),
+ * 2 = matern32 (gpsa/util/util.py:50-66).
  */
 #ifndef GPSA_B200_H
 #define GPSA_B200_H

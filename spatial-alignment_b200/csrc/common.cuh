@@ -10,6 +10,7 @@
 
 #define GPSA_KIND_RBF 0
 #define GPSA_KIND_MATERN12 1
+#define GPSA_KIND_MATERN32 2
 
 #define GPSA_OFF 1e-5f  // diagonal_offset, reference gpsa/models/gpsa.py:153
 

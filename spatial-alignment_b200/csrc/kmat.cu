@@ -3,6 +3,7 @@
 // Replaces the chains of elementwise ATen kernels behind
 //   rbf_kernel       reference gpsa/util/util.py:8-23
 //   matern12_kernel  reference gpsa/util/util.py:33-47
+//   matern32_kernel  reference gpsa/util/util.py:50-66
 // as called from gpsa/models/vgpsa.py:314-318 (warp K_uu, K_uf) and :390,:409 (data K_uu, K_uf).
 // Coordinates are D <= 3 floats per point and live in registers; no [M,R,D] difference tensor
 // and no distance matrix is ever materialised.  Parameters are log-scale device scalars, so
@@ -32,6 +33,10 @@ __device__ __forceinline__ Pt<D> load_pt(const float* p, long i) {
 template <int KIND>
 __device__ __forceinline__ float kval(float r2, float inv_ls, float var) {
   if (KIND == GPSA_KIND_RBF) return var * expf(-0.5f * r2 * inv_ls * inv_ls);
+  if (KIND == GPSA_KIND_MATERN32) {  // var (1 + t) exp(-t), t = sqrt(3) sqrt(r2 + 1e-10) / ls
+    const float t = 1.7320508075688772f * sqrtf(r2 + 1e-10f) * inv_ls;
+    return var * (1.f + t) * expf(-t);
+  }
   return var * expf(-0.5f * sqrtf(r2 + 1e-10f) * inv_ls);
 }
 
@@ -76,6 +81,14 @@ __device__ __forceinline__ float kgrad(float r2, float inv_ls, float var, float&
     coef = k * inv_ls * inv_ls;
     dls = coef * r2;
     return k;
+  }
+  if (KIND == GPSA_KIND_MATERN32) {
+    // dk/dr = -var (sqrt3/ls) t e^-t  ->  dk/dx1 = -(3 var e^-t / ls^2) (x1 - x2);  dk/dlog_ls = var t^2 e^-t
+    const float t = 1.7320508075688772f * sqrtf(r2 + 1e-10f) * inv_ls;
+    const float e = var * expf(-t);
+    coef = 3.f * e * inv_ls * inv_ls;
+    dls = e * t * t;
+    return e * (1.f + t);
   }
   const float t = sqrtf(r2 + 1e-10f);
   const float k = var * expf(-0.5f * t * inv_ls);
@@ -222,6 +235,10 @@ int launch_bwd(int M, long R, const float* x1, const float* x2, const float* ls,
       if (D == 1) return CALL(1, GPSA_KIND_MATERN12);                                \
       if (D == 2) return CALL(2, GPSA_KIND_MATERN12);                                \
       if (D == 3) return CALL(3, GPSA_KIND_MATERN12);                                \
+    } else if (kind == GPSA_KIND_MATERN32) {                                         \
+      if (D == 1) return CALL(1, GPSA_KIND_MATERN32);                                \
+      if (D == 2) return CALL(2, GPSA_KIND_MATERN32);                                \
+      if (D == 3) return CALL(3, GPSA_KIND_MATERN32);                                \
     }                                                                                \
     return GPSA_ERR_UNSUPPORTED;                                                     \
   } while (0)

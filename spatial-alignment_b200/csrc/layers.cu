@@ -66,7 +66,35 @@ int grid_for(long n, int per_block = 256, int cap = 148 * 16) {
 template <int KIND>
 __device__ __forceinline__ double kval64(double r2, double inv_ls, double var) {
   if (KIND == GPSA_KIND_RBF) return var * exp(-0.5 * r2 * inv_ls * inv_ls);
+  if (KIND == GPSA_KIND_MATERN32) {
+    const double t = 1.7320508075688772 * sqrt(r2 + 1e-10) * inv_ls;
+    return var * (1.0 + t) * exp(-t);
+  }
   return var * exp(-0.5 * sqrt(r2 + 1e-10) * inv_ls);
+}
+
+// K and the pieces of its gradient in fp64 (same conventions as kgrad in kmat.cu):
+//   dK/dz_d = -coef (z_d - x_d),  dK/dlog_ls = dls
+template <int KIND>
+__device__ __forceinline__ double kgrad64(double r2, double inv_ls, double var, double& coef, double& dls) {
+  if (KIND == GPSA_KIND_RBF) {
+    const double k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
+    coef = k * inv_ls * inv_ls;
+    dls = coef * r2;
+    return k;
+  }
+  if (KIND == GPSA_KIND_MATERN32) {
+    const double t = 1.7320508075688772 * sqrt(r2 + 1e-10) * inv_ls;
+    const double e = var * exp(-t);
+    coef = 3.0 * e * inv_ls * inv_ls;
+    dls = e * t * t;
+    return e * (1.0 + t);
+  }
+  const double t = sqrt(r2 + 1e-10);
+  const double k = var * exp(-0.5 * t * inv_ls);
+  coef = 0.5 * k * inv_ls / t;
+  dls = 0.5 * k * t * inv_ls;
+  return k;
 }
 
 template <int D, int KIND>
@@ -112,17 +140,8 @@ __global__ void __launch_bounds__(256) prior_bwd_kernel(int M, const float* __re
         dd[d] = zi[d] - (double)Z[j * D + d];
         r2 += dd[d] * dd[d];
       }
-      double k, coef, dls;
-      if (KIND == GPSA_KIND_RBF) {
-        k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
-        coef = k * inv_ls * inv_ls;
-        dls = coef * r2;
-      } else {
-        const double t = sqrt(r2 + 1e-10);
-        k = var * exp(-0.5 * t * inv_ls);
-        coef = 0.5 * k * inv_ls / t;
-        dls = 0.5 * k * t * inv_ls;
-      }
+      double coef, dls;
+      const double k = kgrad64<KIND>(r2, inv_ls, var, coef, dls);
       const double kij = Kbar[(long)i * M + j], kji = Kbar[(long)j * M + i];
       const double w = -(kij + kji) * coef;
 #pragma unroll
@@ -190,17 +209,8 @@ __global__ void __launch_bounds__(256) kuf64_bwd_kernel(int M, long n, long chun
       dd[d] = z[d] - (double)X[r * D + d];
       r2 += dd[d] * dd[d];
     }
-    double k, coef, dls;
-    if (KIND == GPSA_KIND_RBF) {
-      k = var * exp(-0.5 * r2 * inv_ls * inv_ls);
-      coef = k * inv_ls * inv_ls;
-      dls = coef * r2;
-    } else {
-      const double t = sqrt(r2 + 1e-10);
-      k = var * exp(-0.5 * t * inv_ls);
-      coef = 0.5 * k * inv_ls / t;
-      dls = 0.5 * k * t * inv_ls;
-    }
+    double coef, dls;
+    const double k = kgrad64<KIND>(r2, inv_ls, var, coef, dls);
     const double kb = Bbar[(long)m * n + r];
     const double w = -kb * coef;
 #pragma unroll
@@ -592,6 +602,8 @@ int prior_bwd(int kind, int D, int M, const float* Z, const float* ls, const flo
     if (D == 1) PB(1, GPSA_KIND_RBF); else if (D == 2) PB(2, GPSA_KIND_RBF); else PB(3, GPSA_KIND_RBF);
   } else if (kind == GPSA_KIND_MATERN12) {
     if (D == 1) PB(1, GPSA_KIND_MATERN12); else if (D == 2) PB(2, GPSA_KIND_MATERN12); else PB(3, GPSA_KIND_MATERN12);
+  } else if (kind == GPSA_KIND_MATERN32) {
+    if (D == 1) PB(1, GPSA_KIND_MATERN32); else if (D == 2) PB(2, GPSA_KIND_MATERN32); else PB(3, GPSA_KIND_MATERN32);
   } else {
     return GPSA_ERR_UNSUPPORTED;
   }
@@ -700,6 +712,8 @@ extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const 
     if (D == 1) PK(1, GPSA_KIND_RBF); else if (D == 2) PK(2, GPSA_KIND_RBF); else PK(3, GPSA_KIND_RBF);
   } else if (kind == GPSA_KIND_MATERN12) {
     if (D == 1) PK(1, GPSA_KIND_MATERN12); else if (D == 2) PK(2, GPSA_KIND_MATERN12); else PK(3, GPSA_KIND_MATERN12);
+  } else if (kind == GPSA_KIND_MATERN32) {
+    if (D == 1) PK(1, GPSA_KIND_MATERN32); else if (D == 2) PK(2, GPSA_KIND_MATERN32); else PK(3, GPSA_KIND_MATERN32);
   } else {
     return GPSA_ERR_UNSUPPORTED;
   }
@@ -771,6 +785,9 @@ extern "C" int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* 
     } else if (kind == GPSA_KIND_MATERN12) {                                                                \
       if (D == 1) CALL(1, GPSA_KIND_MATERN12); else if (D == 2) CALL(2, GPSA_KIND_MATERN12);                \
       else CALL(3, GPSA_KIND_MATERN12);                                                                     \
+    } else if (kind == GPSA_KIND_MATERN32) {                                                                \
+      if (D == 1) CALL(1, GPSA_KIND_MATERN32); else if (D == 2) CALL(2, GPSA_KIND_MATERN32);                \
+      else CALL(3, GPSA_KIND_MATERN32);                                                                     \
     } else {                                                                                                \
       return GPSA_ERR_UNSUPPORTED;                                                                          \
     }                                                                                                       \

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpsa_b200.so")
 
-KIND_RBF, KIND_MATERN12 = 0, 1
+KIND_RBF, KIND_MATERN12, KIND_MATERN32 = 0, 1, 2
 OFF = 1e-5
 
 _lib = None

@@ -10,7 +10,7 @@ from ._lib import DataBwdArgs, DataFwdArgs, WarpBwdArgs, WarpFwdArgs, check, lib
 
 f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
-KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12}
+KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12, "matern32": _lib.KIND_MATERN32}
 
 # quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16, "auto" = tcgen05 whenever the shape can
 # fill 128-row MMA tiles (the SIMT engine stays for the launch-bound toy configurations)

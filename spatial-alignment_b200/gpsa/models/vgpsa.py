@@ -14,7 +14,7 @@ from sklearn.cluster import KMeans
 
 from .gpsa import GPSA
 from .. import _ops
-from ..util.util import matern12_kernel, rbf_kernel
+from ..util.util import matern12_kernel, matern32_kernel, rbf_kernel
 
 _DEBUG_CHECKS = os.environ.get("GPSA_B200_CHECK", "0") == "1"
 
@@ -26,9 +26,11 @@ def _kernel_kind(fn):
         return "rbf"
     if fn is matern12_kernel:
         return "matern12"
+    if fn is matern32_kernel:
+        return "matern32"
     raise NotImplementedError(
         f"kernel function {getattr(fn, '__name__', fn)!r} is not supported by the fused B200 path; "
-        "use gpsa.rbf_kernel or gpsa.matern12_kernel"
+        "use gpsa.rbf_kernel, gpsa.matern12_kernel or gpsa.matern32_kernel"
     )
 
 

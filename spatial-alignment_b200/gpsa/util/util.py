@@ -47,11 +47,11 @@ def matern12_kernel(x1, x2, lengthscale_unconstrained, output_variance_unconstra
 
 
 def matern32_kernel(x1, x2, lengthscale_unconstrained, output_variance_unconstrained, diag=False):
-    """reference gpsa/util/util.py:50-66.  Exported by the reference but never used by its model or
-    examples; SURVEY.md 8(f)-3 ranks a fused version "next", so it is not in the CUDA evaluator yet."""
-    raise NotImplementedError(
-        "matern32_kernel is not part of the fused B200 evaluator yet (SURVEY.md 8(f)-3); "
-        "use rbf_kernel or matern12_kernel"
+    """var * (1 + t) * exp(-t), t = sqrt(3) * sqrt(|x1 - x2|^2 + 1e-10) / ls  (reference gpsa/util/util.py:50-66)."""
+    if diag:
+        return _diag_kernel("matern32", x1, x2, lengthscale_unconstrained, output_variance_unconstrained)
+    return _ops.kernel_matrix(
+        "matern32", x1, x2, _as_param(lengthscale_unconstrained, x1), _as_param(output_variance_unconstrained, x1)
     )
 
 

@@ -27,14 +27,14 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
 warnings.filterwarnings("ignore")
 import gpsa  # noqa: E402  (the reference)
-from gpsa import VariationalGPSA, matern12_kernel, rbf_kernel  # noqa: E402
+from gpsa import VariationalGPSA, matern12_kernel, matern32_kernel, rbf_kernel  # noqa: E402
 
 assert gpsa.__file__.startswith(REF), gpsa.__file__
 torch.autograd.set_detect_anomaly(False)
 
 from oracle import gpsa_oracle as orc  # noqa: E402
 
-KERN = {"rbf": rbf_kernel, "matern12": matern12_kernel}
+KERN = {"rbf": rbf_kernel, "matern12": matern12_kernel, "matern32": matern32_kernel}
 
 
 def load_example_h5ad():
@@ -62,6 +62,8 @@ def synth(rng, n_list, D, P):
 def run_case(name, data, m_X, m_G, S, kern_warp="rbf", kern_data="rbf", fixed=None, n_latent=None,
              seed=0, fwd_seed=1000, tweak=None, with_gtest=False):
     """data = {mod: (X, Y, n_samples_list)}"""
+    if ONLY and name not in ONLY:
+        return
     np.random.seed(seed)
     torch.manual_seed(seed)
     mods = list(data.keys())
@@ -170,6 +172,9 @@ def run_case(name, data, m_X, m_G, S, kern_warp="rbf", kern_data="rbf", fixed=No
     print(f"{name}: loss={float(loss):.6f}  -> {os.path.getsize(path)/1024:.0f} KiB")
 
 
+ONLY = set(sys.argv[1:])  # optional: regenerate only the named cases
+
+
 def main():
     X, Y, batch = load_example_h5ad()
     nl = [int((batch == 0).sum()), int((batch == 1).sum())]
@@ -186,6 +191,8 @@ def main():
     run_case("c1_named", {"expression": (X, Y[:, :5].copy(), nl)}, 50, 50, 5, fixed=0)
     # C2: Matern-1/2 warp + data kernels on the same data
     run_case("c2_matern", {"expression": (X, Y[:, :5].copy(), nl)}, 50, 50, 5, "matern12", "matern12", fixed=0)
+    # Matern-3/2 warp + data kernels (gpsa/util/util.py:50-66), same data
+    run_case("c2_matern32", {"expression": (X, Y[:, :5].copy(), nl)}, 50, 50, 5, "matern32", "matern32", fixed=0)
     # well-conditioned RBF (short lengthscales) on the example data
     run_case("c1_rbf_short", {"expression": (X, Y[:, :5].copy(), nl)}, 25, 25, 5, fixed=0, tweak=short_ls)
 

@@ -32,7 +32,7 @@ def stream():
 
 
 # --------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["rbf", "matern12"])
+@pytest.mark.parametrize("kind", ["rbf", "matern12", "matern32"])
 @pytest.mark.parametrize("D", [1, 2, 3])
 @pytest.mark.parametrize("M,R", [(1, 1), (7, 33), (25, 300), (50, 1000), (200, 2049)])
 def test_kernel_matrix_fwd_bwd(L, kind, D, M, R):
@@ -43,7 +43,7 @@ def test_kernel_matrix_fwd_bwd(L, kind, D, M, R):
     x2 = torch.rand(R, D, generator=g) * 10
     ls, var = torch.tensor([0.7]), torch.tensor([-0.3])
     Kbar = torch.randn(M, R, generator=g)
-    fn = gpsa.rbf_kernel if kind == "rbf" else gpsa.matern12_kernel
+    fn = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel, "matern32": gpsa.matern32_kernel}[kind]
     a = [t.cuda().requires_grad_() for t in (x1, x2, ls, var)]
     K = fn(a[0], a[1], a[2], a[3])
     (K * Kbar.cuda()).sum().backward()
@@ -186,7 +186,7 @@ def test_omega_prepare_and_grad(L, M, B):
     assert relerr(out.cpu(), od.grad) < 1e-5
 
 
-@pytest.mark.parametrize("kind", ["rbf", "matern12"])
+@pytest.mark.parametrize("kind", ["rbf", "matern12", "matern32"])
 @pytest.mark.parametrize("M,D", [(25, 2), (200, 2), (256, 3)])
 def test_prior_prepare(L, kind, M, D):
     g = torch.Generator().manual_seed(M + D)
@@ -211,7 +211,7 @@ def test_prior_prepare(L, kind, M, D):
 
 
 def orc_kind(kind):
-    return {"rbf": 0, "matern12": 1}[kind]
+    return {"rbf": 0, "matern12": 1, "matern32": 2}[kind]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _model_from_golden(g, **kw):
     import gpsa
 
-    kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel}
+    kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel, "matern32": gpsa.matern32_kernel}
     data_dict = {
         m: {
             "spatial_coords": torch.from_numpy(g.X[m]).float().clone(),

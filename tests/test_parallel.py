@@ -120,7 +120,7 @@ def _gpu_worker(rank, world, port, name, out):
         sd = {k: torch.from_numpy(np.asarray(v)) for k, v in g.params.items() if k not in g.fixed_params}
         full.load_state_dict(sd, strict=True)
         local_dd = shard_data_dict(data_dict, world, rank)
-        kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel}
+        kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel, "matern32": gpsa.matern32_kernel}
         np.random.seed(0)
         torch.manual_seed(0)
         model = gpsa.VariationalGPSA(local_dd, n_spatial_dims=g.cfg.n_spatial_dims, m_X_per_view=g.cfg.m_X_per_view,
