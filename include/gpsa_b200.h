@@ -114,7 +114,7 @@ int gpsa_quadform_bwd_alpha_f32(int M, long R, int L, const float* A, const floa
  * (gpsa/models/vgpsa.py:193-196); the backward products use Omega / the packed features as above.
  * `ws` is caller-provided device scratch of at least gpsa_quadform_tc_ws_bytes(M, R, L) bytes (bf16
  * copies of the operands); gpsa_tc_supported(M) says whether the forward kernel covers this M
- * (16 <= M <= 256 for now).  G [R,L] = dLoss/dq2, Abar [M,R] is ADDED to, H as for the fp32 engine. */
+ * (16 <= M <= 512; above 256 the forward streams both operands through the generic GEMM core).  G [R,L] = dLoss/dq2, Abar [M,R] is ADDED to, H as for the fp32 engine. */
 int gpsa_tc_supported(int M);
 size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L);
 int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws, size_t ws_bytes,

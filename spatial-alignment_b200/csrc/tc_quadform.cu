@@ -45,7 +45,7 @@ constexpr int NSTAGE = 2;
 constexpr int OPER_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
 constexpr int RAW_BYTES = 8192;  // Omega-bar only: 4 row groups x 2 halves of [8 rows x 32 r] fp32, 128B-swizzled
 
-enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2 };
+enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_SUMSQ = 3 };
 constexpr int N_GEN_WARPS = 8;
 __host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode == MODE_OMEGA ? RAW_BYTES : 0); }
 __host__ __device__ constexpr int gemm_smem(int mode) { return NSTAGE * stage_bytes(mode) + 1024 /*alignment*/ + 256 /*barriers*/; }
@@ -65,6 +65,7 @@ struct GemmParams {
   long R;
   int Mind, nb, nblk;
   float* Abar;        // ALPHA: [Mind, R], added to
+  int halves, L;      // SUMSQ: column tiles per gene, genes; C = q2 [Mrows, L], accumulated atomically
 };
 
 __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& ks) {
@@ -138,7 +139,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
-      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      // SUMSQ: column tile h of gene nt / halves; K rows below h * TN only meet structural zeros of the factor
+      const int kb0 = MODE == MODE_SUMSQ ? (nt % p.halves) * (TN / BK) : ks * p.kb_per;
+      const int kb1 = min(p.kblocks, kb0 + p.kb_per);
       int grow[4] = {0, 0, 0, 0};  // MODE_OMEGA: first A row of the (I, J) index groups of the tile's two feature blocks
       if (MODE == MODE_OMEGA) {
         for (int q = 0; q < 2; ++q) {
@@ -160,6 +163,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_3d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM, bz);
             tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN, bz);
             tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN, bz);
+          } else if (MODE == MODE_SUMSQ) {
+            tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
+            tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
+            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, (nt % p.halves) * TN, nt / p.halves);
+            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, (nt % p.halves) * TN, nt / p.halves);
           } else if (MODE != MODE_OMEGA) {
             tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
             tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
@@ -171,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               for (int h = 0; h < 2; ++h)
                 tma_load_2d(st + OPER_BYTES + (gq * 2 + h) * 1024, &tmA_hi, &rawfull[stage], kb * BK + h * 32, grow[gq]);
           }
-          if (!(MODE == MODE_TEST && p.batch > 0)) {
+          if (!(MODE == MODE_TEST && p.batch > 0) && MODE != MODE_SUMSQ) {
             tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
             tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
           }
@@ -189,7 +197,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
-      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      const int kb0 = MODE == MODE_SUMSQ ? (nt % p.halves) * (TN / BK) : ks * p.kb_per;
+      const int kb1 = min(p.kblocks, kb0 + p.kb_per);
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)acc * TN;
@@ -230,7 +239,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
       const long row = (long)mt * TM + q * 32 + lane;
-      if (MODE == MODE_TEST || MODE == MODE_OMEGA) {
+      if (MODE == MODE_SUMSQ) {
+        // q2[row, gene] += sum over this tile's columns of T^2 (columns beyond Mp are zero rows of the packed factor)
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < TN / 32; ++c) {
+          if ((long)(nt % p.halves) * TN + c * 32 >= p.Ncols) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
+            s0 = fmaf(x, x, s0);
+            s1 = fmaf(y, y, s1);
+          }
+        }
+        if (row < p.Mrows) atomicAdd(&p.C[row * p.ldc + nt / p.halves], s0 + s1);
+      } else if (MODE == MODE_TEST || MODE == MODE_OMEGA) {
         float* Cb = p.C + (MODE == MODE_TEST ? (long)item_batch(p, item) * p.sC : 0);
         const float alpha = MODE == MODE_TEST ? p.alpha : 1.f;
         const bool vec4 = MODE == MODE_TEST && !p.accumulate && !p.trans_add && (p.ldc & 3) == 0 &&
@@ -797,8 +823,10 @@ __global__ void pack_trans_kernel(long rows, int K, int Kp, long ld, long sIn, c
   const int b = blockIdx.z;
   const float* src = in + (long)b * sIn;
   const long obase = (long)b * rows * Kp;
-  const long r0 = (long)blockIdx.x * 32;
-  const int k0 = blockIdx.y * 32;
+  // flattened (row tile, K tile) index on x: either extent can exceed the 65535 limit of grid.y (R-sized operands)
+  const unsigned nkt = (unsigned)((K + 31) / 32);
+  const long r0 = (long)(blockIdx.x / nkt) * 32;
+  const int k0 = (int)(blockIdx.x % nkt) * 32;
   for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
     const int k = k0 + yy;
     const long r = r0 + threadIdx.x;
@@ -928,7 +956,7 @@ void set_split(GemmParams& p, int want_split) {
 // =================================================================================================
 // exported entry points
 // =================================================================================================
-extern "C" int gpsa_tc_supported(int M) { return (M >= 16 && M <= 256) ? 1 : 0; }
+extern "C" int gpsa_tc_supported(int M) { return (M >= 16 && M <= 512) ? 1 : 0; }
 
 extern "C" size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch);
 
@@ -1004,7 +1032,7 @@ extern "C" int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, 
       dim3 grid((unsigned)blocks, 1, batch);
       pack_rows_kernel<<<grid, 256, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
     } else {
-      dim3 grid(gpsa_cdiv(rows, 32), gpsa_cdiv(K, 32), batch), block(32, 8);
+      dim3 grid((unsigned)((long)gpsa_cdiv(rows, 32) * gpsa_cdiv(K, 32)), 1, batch), block(32, 8);
       pack_trans_kernel<<<grid, block, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
     }
   };
@@ -1067,6 +1095,28 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
     dim3 grid2(f.Kp / 32, gpsa_cdiv(f.Mp, 32), L);
     pack_Lt_kernel<<<grid2, block, 0, st>>>(M, f.Mp, f.Kp, Ltril, lt_hi, lt_lo);
     GPSA_LAUNCH_CHECK();
+  }
+  if (f.Mp > TN) {
+    // M > 256 (C5: M = 512): the A tile (128 x Mp, hi + lo) no longer fits in shared memory next to a factor ring, so
+    // both operands are streamed through the generic 128 x 256 GEMM core: one item = (row tile, gene, 256-column
+    // slice of T), K blocks below the slice skipped (structural zeros), sum of squares out of TMEM added to q2.
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (make_tmap_2d(&ta_hi, at_hi, f.Mp, R, f.Kp, TM) || make_tmap_2d(&ta_lo, at_lo, f.Mp, R, f.Kp, TM)) return GPSA_ERR_CUDA;
+    const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
+    const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)TN, 1};
+    if (make_tmap(&tb_hi, lt_hi, 3, dims, str, box) || make_tmap(&tb_lo, lt_lo, 3, dims, str, box)) return GPSA_ERR_CUDA;
+    GemmParams g = {};
+    g.halves = gpsa_cdiv(f.Mp, TN);
+    g.L = L;
+    g.n_mt = gpsa_cdiv(R, TM);
+    g.n_nt = L * g.halves;
+    g.group_m = g.n_mt < 32 ? g.n_mt : 32;
+    g.kblocks = gpsa_cdiv(f.Mp, BK);
+    set_split(g, 1);
+    g.Mrows = R; g.Ncols = f.Mp; g.C = q2; g.ldc = L;
+    if (cudaMemsetAsync(q2, 0, sizeof(float) * (size_t)R * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
+    return launch_gemm<MODE_SUMSQ>(ta_hi, ta_lo, tb_hi, tb_lo, g, st);
   }
   FwdMaps maps;
   {
@@ -1164,9 +1214,20 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
                            : ta ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 4>, maps, p)
                            : gr ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 0>, maps, p)
                                 : cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, false, 0>, maps, p);
-    if (rc != cudaSuccess) return GPSA_ERR_CUDA;
-    GPSA_LAUNCH_CHECK();
-    return GPSA_OK;
+    if (rc == cudaSuccess) {
+      GPSA_LAUNCH_CHECK();
+      return GPSA_OK;
+    }
+    // a device that cannot co-schedule the 2-CTA cluster at this shared-memory size: clear the launch error and
+    // run the single-CTA kernel (same results, the factor stream is then fetched per CTA)
+    (void)cudaGetLastError();
+    p.gsplit = 1;
+    if (p.n_rt < sm_count()) {
+      p.gsplit = (sm_count() + p.n_rt - 1) / p.n_rt;
+      if (p.gsplit > L) p.gsplit = L;
+    }
+    p.genes_per = (L + p.gsplit - 1) / p.gsplit;
+    p.gsplit = (L + p.genes_per - 1) / p.genes_per;
   }
   const int n_items = p.n_rt * p.gsplit;
   const int grid = n_items < sm_count() ? n_items : sm_count();

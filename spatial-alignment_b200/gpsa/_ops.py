@@ -22,7 +22,7 @@ def pick_engine(M, R, L):
     if e == "auto":
         return 1 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
     if e == 1 and not lib().gpsa_tc_supported(int(M)):
-        raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} yet (16 <= M <= 256)")
+        raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} yet (16 <= M <= 512)")
     return int(e)
 
 

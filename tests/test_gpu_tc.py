@@ -60,7 +60,7 @@ def _problem(M, R, Lg, seed):
 
 
 @pytest.mark.parametrize("M,R,Lg", [(64, 128, 1), (64, 1000, 5), (200, 700, 37), (256, 2049, 9), (50, 300, 3),
-                                    (100, 4096, 300)])
+                                    (100, 4096, 300), (512, 700, 5), (320, 300, 3)])
 def test_quadform_tc_fwd_bwd(L, M, R, Lg):
     from gpsa import _ops
 
@@ -99,9 +99,9 @@ def test_quadform_tc_fwd_bwd(L, M, R, Lg):
 
 def test_tc_unsupported_M(L):
     lib = L.lib()
-    assert lib.gpsa_tc_supported(512) == 0
+    assert lib.gpsa_tc_supported(512) == 1 and lib.gpsa_tc_supported(1024) == 0
     x = torch.zeros(16, device="cuda")
-    assert lib.gpsa_quadform_fwd_tc(512, 128, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, stream()) == 3
+    assert lib.gpsa_quadform_fwd_tc(1024, 128, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, stream()) == 3
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern12"])
