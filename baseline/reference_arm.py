@@ -14,7 +14,8 @@ import os
 import sys
 import time
 
-os.environ["CUDA_VISIBLE_DEVICES"] = ""
+if "--device=cuda" not in sys.argv:  # default: the CPU arm bench.py reports; CUDA hidden before torch is imported
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "baseline", "_ref")
 
@@ -27,6 +28,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--anomaly", type=int, default=0)
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="cuda (pass as --device=cuda): the reference's own eager PyTorch path on this box's GPU "
+                         "(C1/C2 only fit), the 'same box, library kernels' bar of SURVEY.md 8(d)")
     args = ap.parse_args()
     if not os.path.isdir(os.path.join(REF, "gpsa")):
         print(json.dumps({"unavailable": "baseline/_ref/gpsa missing (reference not installed)"}))
@@ -45,7 +49,8 @@ def main():
     cfg = CONFIGS[args.config]
     genes = [int(g) for g in args.genes.split(",") if g] or [cfg["P"]]
     kern = gpsa.rbf_kernel if cfg["kernel"] == "rbf" else gpsa.matern12_kernel
-    out = {"cores": os.cpu_count(), "torch_threads": torch.get_num_threads(), "anomaly": bool(args.anomaly), "runs": []}
+    out = {"cores": os.cpu_count(), "torch_threads": torch.get_num_threads(), "anomaly": bool(args.anomaly),
+           "device": args.device, "runs": []}
     for P in genes:
         X, Y, nl = make_data(cfg, args.seed, genes=P)
         data_dict = {"expression": {"spatial_coords": torch.from_numpy(X), "outputs": torch.from_numpy(Y),
@@ -56,6 +61,10 @@ def main():
                                      data_init=True, minmax_init=False, grid_init=False,
                                      n_latent_gps={"expression": None}, mean_function="identity_fixed",
                                      kernel_func_warp=kern, kernel_func_data=kern, fixed_view_idx=0)
+        if args.device == "cuda":
+            model = model.to("cuda")
+            for k in ("spatial_coords", "outputs"):
+                data_dict["expression"][k] = data_dict["expression"][k].cuda()
         view_idx, Ns, _, _ = model.create_view_idx_dict(data_dict)
         opt = torch.optim.Adam(model.parameters(), lr=1e-2)
         x = data_dict["expression"]["spatial_coords"]
@@ -75,7 +84,7 @@ def main():
         ts = []
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            loss = step()
+            loss = step()  # ends in loss.item(): the device is synchronised
             ts.append(time.perf_counter() - t0)
         out["runs"].append({"genes": P, "s_per_step": float(np.median(ts)), "steps": args.steps, "loss": loss})
     print(json.dumps(out))
