@@ -1194,6 +1194,9 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
       p.gsplit = (ncl_max + n_rp - 1) / n_rp;
       if (p.gsplit > L) p.gsplit = L;
     }
+    // (Chunking the genes so that a chunk of packed factors stays L2-resident across all row tiles was tried: with
+    // 80 MB chunks the kernel's DRAM reads went UP, 2.28 -> 2.89 GB -- the q2 write stream and the A tiles evict the
+    // chunk -- at the same kernel time, so items stay (row-tile pair, all genes).)
     p.genes_per = (L + p.gsplit - 1) / p.gsplit;
     p.gsplit = (L + p.genes_per - 1) / p.genes_per;
     const int n_items = n_rp * p.gsplit;
