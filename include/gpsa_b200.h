@@ -37,6 +37,8 @@ int gpsa_version(void);
  *   (slot 0 = quadratic form forward, 1 = its A-bar backward, 2 = its Omega-bar backward).
  * gpsa_prof_read: synchronise, return per slot the number of timed launches and their total ms. */
 long gpsa_launch_count(void);
+/* testing aid: 1 = use the scalar variants of the sampling / log-likelihood kernels where the 128-bit ones apply */
+void gpsa_debug_disable_vec4(int off);
 void gpsa_prof_enable(int on);
 int gpsa_prof_read(int* counts, double* total_ms);
 

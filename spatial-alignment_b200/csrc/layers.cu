@@ -329,6 +329,27 @@ __global__ void __launch_bounds__(256) sample_fwd_rows_kernel(long R, int L, con
   }
 }
 
+// 128-bit variant (L % 4 == 0, 16-byte aligned rows): four genes per thread and access
+__global__ void __launch_bounds__(256) sample_fwd_rows4_kernel(long R, int L4, const float* __restrict__ kq,
+                                                               const float4* __restrict__ eps, float4* __restrict__ F,
+                                                               float4* __restrict__ var) {
+  for (long r = blockIdx.x; r < R; r += gridDim.x) {
+    const float k = kq[r];
+    const long base = r * L4;
+    for (int p = threadIdx.x; p < L4; p += blockDim.x) {
+      float4 v = var[base + p];
+      const float4 e = eps[base + p];
+      float4 f = F[base + p];
+      v.x = (k + v.x + GPSA_OFF) + GPSA_OFF; v.y = (k + v.y + GPSA_OFF) + GPSA_OFF;
+      v.z = (k + v.z + GPSA_OFF) + GPSA_OFF; v.w = (k + v.w + GPSA_OFF) + GPSA_OFF;
+      f.x = fmaf(sqrtf(v.x), e.x, f.x); f.y = fmaf(sqrtf(v.y), e.y, f.y);
+      f.z = fmaf(sqrtf(v.z), e.z, f.z); f.w = fmaf(sqrtf(v.w), e.w, f.w);
+      var[base + p] = v;
+      F[base + p] = f;
+    }
+  }
+}
+
 // one warp per row r: Gm[r,p] = Fbar*eps/(2 sqrt(var)); q1bar[r] = -sum_p Gm; acc_hyp[1] += sigma2 * sum Gm
 __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const float* __restrict__ Fbar,
                                                          const float* __restrict__ eps, const float* __restrict__ var,
@@ -344,6 +365,38 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const fl
       const float g = 0.5f * Fbar[i] * eps[i] / sqrtf(var[i]);
       Gm[i] = g;
       s += g;
+    }
+    s = warp_sum(s);
+    if (lane == 0) { q1bar[r] = -s; tot += (double)s; }
+  }
+  __shared__ double red[8];
+  if (lane == 0) red[warp] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(&acc_hyp[1], t * exp((double)log_var[0]));
+  }
+}
+
+// 128-bit variant of sample_bwd_kernel (L % 4 == 0)
+__global__ void __launch_bounds__(256) sample_bwd4_kernel(long R, int L4, const float4* __restrict__ Fbar,
+                                                          const float4* __restrict__ eps, const float4* __restrict__ var,
+                                                          const float* __restrict__ log_var, float4* __restrict__ Gm,
+                                                          float* __restrict__ q1bar, double* acc_hyp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  double tot = 0.0;
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + warp; r < R; r += nwarps) {
+    float s = 0.f;
+    for (int p = lane; p < L4; p += 32) {
+      const long i = r * L4 + p;
+      const float4 fb = Fbar[i], e = eps[i], v = var[i];
+      float4 g;
+      g.x = 0.5f * fb.x * e.x / sqrtf(v.x); g.y = 0.5f * fb.y * e.y / sqrtf(v.y);
+      g.z = 0.5f * fb.z * e.z / sqrtf(v.z); g.w = 0.5f * fb.w * e.w / sqrtf(v.w);
+      Gm[i] = g;
+      s += (g.x + g.y) + (g.z + g.w);
     }
     s = warp_sum(s);
     if (lane == 0) { q1bar[r] = -s; tot += (double)s; }
@@ -593,6 +646,62 @@ __global__ void __launch_bounds__(256) ll_bwd_kernel(long N, int P, int S, const
   }
 }
 
+// 128-bit variants (N*P % 4 == 0, 16-byte aligned): one thread = four (spot, gene) entries over all S samples
+__global__ void __launch_bounds__(256) ll_fwd4_kernel(long NP4, int S, const float4* __restrict__ F,
+                                                      const float4* __restrict__ Y, const float* __restrict__ log_noise,
+                                                      double* ll_acc) {
+  const float sigma = expf(log_noise[0]) + GPSA_OFF;
+  const float inv = 1.f / sigma;
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < NP4; i += (long)gridDim.x * blockDim.x) {
+    const float4 y = Y[i];
+    float part = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float4 f = F[(long)s * NP4 + i];
+      const float zx = (y.x - f.x) * inv, zy = (y.y - f.y) * inv, zz = (y.z - f.z) * inv, zw = (y.w - f.w) * inv;
+      part = fmaf(zx, zx, part); part = fmaf(zy, zy, part); part = fmaf(zz, zz, part); part = fmaf(zw, zw, part);
+    }
+    acc += (double)part;
+  }
+  __shared__ double red[32];
+  acc = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) {
+    double v = -0.5 * acc;
+    if (blockIdx.x == 0) v -= (double)(NP4 * 4 * S) * (log((double)sigma) + 0.91893853320467274178);
+    atomicAdd(ll_acc, v / (double)S);
+  }
+}
+
+__global__ void __launch_bounds__(256) ll_bwd4_kernel(long NP4, int S, const float4* __restrict__ F,
+                                                      const float4* __restrict__ Y, const float* __restrict__ log_noise,
+                                                      const float* __restrict__ ll_bar, float4* __restrict__ F_bar,
+                                                      double* acc_noise) {
+  const float en = expf(log_noise[0]);
+  const float sigma = en + GPSA_OFF;
+  const float inv = 1.f / sigma;
+  const float c = ll_bar[0] * inv * inv / (float)S;
+  double acc = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < NP4; i += (long)gridDim.x * blockDim.x) {
+    const float4 y = Y[i];
+    float part = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float4 f = F[(long)s * NP4 + i];
+      const float dx = y.x - f.x, dy = y.y - f.y, dz = y.z - f.z, dw = y.w - f.w;
+      F_bar[(long)s * NP4 + i] = make_float4(c * dx, c * dy, c * dz, c * dw);
+      const float zx = dx * inv, zy = dy * inv, zz = dz * inv, zw = dw * inv;
+      part = fmaf(zx, zx, part); part = fmaf(zy, zy, part); part = fmaf(zz, zz, part); part = fmaf(zw, zw, part);
+    }
+    acc += (double)part;
+  }
+  __shared__ double red[32];
+  acc = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) {
+    double v = acc * (double)inv;
+    if (blockIdx.x == 0) v -= (double)(NP4 * 4 * S) * (double)inv;
+    atomicAdd(acc_noise, (double)ll_bar[0] * v * (double)en / (double)S);
+  }
+}
+
 // prior_bwd launcher
 int prior_bwd(int kind, int D, int M, const float* Z, const float* ls, const float* var, const double* Kbar,
               double* acc_Z, double* acc_hyp, cudaStream_t st) {
@@ -665,6 +774,9 @@ void gpsa_prof_end(int slot, cudaStream_t st) {
   if (p.n < PROF_RING) { cudaEventRecord(p.end[p.n], st); ++p.n; }
 }
 
+namespace { int g_no_vec4 = 0; }
+// testing aid: 1 = run the scalar variants of the sampling / log-likelihood kernels even where the 128-bit ones apply
+extern "C" void gpsa_debug_disable_vec4(int off) { g_no_vec4 = off; }
 extern "C" long gpsa_launch_count(void) { return g_gpsa_launches; }
 extern "C" void gpsa_prof_enable(int on) {
   g_prof_on = on;
@@ -918,7 +1030,13 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
     TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->var, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   }
-  if (L >= 128) sample_fwd_rows_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(R, L, a->kq, a->eps, a->F, a->var);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a->eps) | reinterpret_cast<uintptr_t>(a->F) |
+                      reinterpret_cast<uintptr_t>(a->var)) & 15) == 0;
+  if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
+    sample_fwd_rows4_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(
+        R, L / 4, a->kq, reinterpret_cast<const float4*>(a->eps), reinterpret_cast<float4*>(a->F),
+        reinterpret_cast<float4*>(a->var));
+  else if (L >= 128) sample_fwd_rows_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(R, L, a->kq, a->eps, a->F, a->var);
   else sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
   GPSA_LAUNCH_CHECK();
   // KD = K^-1 delta (fp64)
@@ -942,7 +1060,15 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   {
     long b = (R + 7) / 8;
     if (b > 148 * 8) b = 148 * 8;
-    sample_bwd_kernel<<<(int)b, 256, 0, st>>>(R, L, a->F_bar, a->eps, a->var, a->log_var, a->Gm, a->q1bar, a->acc_hyp);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(a->F_bar) | reinterpret_cast<uintptr_t>(a->eps) |
+                        reinterpret_cast<uintptr_t>(a->var) | reinterpret_cast<uintptr_t>(a->Gm)) & 15) == 0;
+    if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
+      sample_bwd4_kernel<<<(int)b, 256, 0, st>>>(R, L / 4, reinterpret_cast<const float4*>(a->F_bar),
+                                                 reinterpret_cast<const float4*>(a->eps),
+                                                 reinterpret_cast<const float4*>(a->var), a->log_var,
+                                                 reinterpret_cast<float4*>(a->Gm), a->q1bar, a->acc_hyp);
+    else
+      sample_bwd_kernel<<<(int)b, 256, 0, st>>>(R, L, a->F_bar, a->eps, a->var, a->log_var, a->Gm, a->q1bar, a->acc_hyp);
     GPSA_LAUNCH_CHECK();
   }
   // delta-bar = A Fbar (+ kl_bar K^-1 delta)
@@ -996,7 +1122,12 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
 extern "C" int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
                                     double* ll_acc, cudaStream_t st) {
   if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
-  ll_fwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_acc);
+  const long NP = N * P;
+  if ((NP & 3) == 0 && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && NP >= 4096 && !g_no_vec4)
+    ll_fwd4_kernel<<<grid_for(NP / 4, 256, 148 * 8), 256, 0, st>>>(NP / 4, S, reinterpret_cast<const float4*>(F),
+                                                                    reinterpret_cast<const float4*>(Y), log_noise, ll_acc);
+  else
+    ll_fwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_acc);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -1004,7 +1135,14 @@ extern "C" int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const 
 extern "C" int gpsa_gaussian_ll_bwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
                                     const float* ll_bar, float* F_bar, double* acc_noise, cudaStream_t st) {
   if (N <= 0 || P <= 0 || S <= 0) return GPSA_OK;
-  ll_bwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_bar, F_bar, acc_noise);
+  const long NP = N * P;
+  if ((NP & 3) == 0 && NP >= 4096 && !g_no_vec4 &&
+      ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(F_bar)) & 15) == 0)
+    ll_bwd4_kernel<<<grid_for(NP / 4, 256, 148 * 8), 256, 0, st>>>(NP / 4, S, reinterpret_cast<const float4*>(F),
+                                                                    reinterpret_cast<const float4*>(Y), log_noise, ll_bar,
+                                                                    reinterpret_cast<float4*>(F_bar), acc_noise);
+  else
+    ll_bwd_kernel<<<grid_for(N * P, 256, 148 * 8), 256, 0, st>>>(N, P, S, F, Y, log_noise, ll_bar, F_bar, acc_noise);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

@@ -92,6 +92,7 @@ class DataBwdArgs(C.Structure):
 SIGNATURES = {
     "gpsa_version": [],
     "gpsa_launch_count": [],
+    "gpsa_debug_disable_vec4": [I],
     "gpsa_prof_enable": [I],
     "gpsa_prof_read": [P, P],
     "gpsa_kernel_matrix_fwd": [I, I, I, LNG, P, P, P, P, P, P],
@@ -126,7 +127,7 @@ SIGNATURES = {
     "gpsa_gaussian_ll_fwd": [LNG, I, I, P, P, P, P, P],
     "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
 }
-_RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None,
+_RESTYPE = {"gpsa_feat_count": LNG, "gpsa_launch_count": LNG, "gpsa_prof_enable": None, "gpsa_debug_disable_vec4": None,
             "gpsa_quadform_tc_ws_bytes": C.c_size_t, "gpsa_gemm_tc_ws_bytes": C.c_size_t}
 
 

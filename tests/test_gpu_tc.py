@@ -165,3 +165,35 @@ def test_gemm_tc_generic(L, Mr, Nc, K, batch, arm, brm, out_mode, split):
     assert rc == 0
     torch.cuda.synchronize()
     assert relerr(c.cpu().reshape(ref.shape), ref) < 2e-5
+
+
+def test_vectorised_elementwise_kernels_match_scalar(L):
+    """The 128-bit sampling / log-likelihood kernels (L % 4 == 0, L >= 128) against their scalar variants: same data
+    layer and the same Gaussian log-likelihood, forward and backward, with the vector path switched off and on."""
+    from gpsa import _ops
+
+    g = torch.Generator().manual_seed(23)
+    M, D, Lg, S, N = 64, 2, 128, 2, 1100
+    Gt = torch.rand(M, D, generator=g) * 10
+    G = torch.rand(S, N, D, generator=g) * 10
+    Osq = torch.randn(Lg, M, M, generator=g) * 0.1
+    dlt = torch.randn(M, Lg, generator=g)
+    eps = torch.randn(S, N, Lg, generator=g)
+    Y = torch.randn(N, Lg, generator=g)
+    ls, var, ln = torch.tensor([0.3]), torch.tensor([0.1]), torch.tensor([-0.2])
+    outs = {}
+    for off in (1, 0):
+        L.lib().gpsa_debug_disable_vec4(off)
+        try:
+            leaves = [t.clone().cuda().requires_grad_() for t in (Gt, ls, var, dlt, Osq, G, ln)]
+            F, kl, _, _, _ = _ops.DataLayer.apply({"kind": _ops.KINDS["rbf"], "with_kl": True}, *leaves[:5], leaves[5],
+                                                  eps.cuda())
+            ll = _ops.GaussianLL.apply(F, Y.cuda(), leaves[6])
+            (kl - ll).backward()
+            outs[off] = [F.detach().cpu(), ll.detach().cpu()] + [t.grad.cpu() for t in leaves]
+        finally:
+            L.lib().gpsa_debug_disable_vec4(0)
+    for name, x0, x1 in zip(["F", "ll", "Gtilde", "log_ls", "log_var", "delta", "Omega_sqt", "G", "log_noise"], outs[1],
+                            outs[0]):
+        # the A-bar product accumulates with atomics (run-to-run order) and G-bar amplifies it through K^-1: 1e-4
+        assert relerr(x1, x0) < (1e-4 if name in ("G", "Gtilde", "log_ls", "log_var") else 1e-5), name
