@@ -419,7 +419,7 @@ def main():
     q_ms = sum(tot_ms[i] for i in range(3))
     q_launch = sum(counts[i] for i in range(3))
     names = ["fwd", "bwd_alpha", "bwd_omega"]
-    kern = {"fwd": "tc_qf_fwd_kernel<2,1>", "bwd_alpha": "tc_gemm_kernel<1>", "bwd_omega": "tc_gemm_kernel<2>"}
+    kern = {"fwd": "tc_qf_fwd_kernel<2,1,12>", "bwd_alpha": "tc_gemm_kernel<1>", "bwd_omega": "tc_gemm_kernel<2>"}
     per = {n: tot_ms[i] / max(counts[i], 1) for i, n in enumerate(names)}
     f_one = f_q2 / 3.0  # algorithmic (symmetric-minimum) flops of ONE of the three products, per launch
     tc = (_ops.pick_engine(cfg["M"], S * N, local_genes) == 1)
@@ -433,8 +433,8 @@ def main():
         "bound": "tensor", "kernel": f"{products[dom]['kernel']} ({dom}: dominant of the three quadratic-form products)",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
         "peak_source": peak_src,
-        "traffic": 3.32e9 if (tc and args.config == "c3" and dom == "fwd" and world == 1 and args.genes is None) else None,
-        "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r1b_tc_ncu_summary.txt" if tc else None,
+        "traffic": 3.30e9 if (tc and args.config == "c3" and dom == "fwd" and world == 1 and args.genes is None) else None,
+        "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r1c_fwd_ncu_summary.txt" if tc else None,
         "note": ("achieved counts ALGORITHMIC flops (M(M+1) per (sample, spot, gene)); the tcgen05 engine issues 3 bf16 MMA "
                  "passes per product for fp32-class accuracy, so the tensor pipe runs at `issued_tflops`"),
         "frac_issued": (passes * achieved / peak_tf) if achieved else None,
