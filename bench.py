@@ -271,7 +271,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     S, N = cfg["S"], cfg["V"] * cfg["Nv"]
     workload = (f"{args.config}: {cfg['desc']}, D={cfg['D']}, M_X=M_G={cfg['M']}, S={cfg['S']}, {cfg['kernel']}, "
-                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step (torch.optim.Adam, fused=True)")
+                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step")
 
     if args.impl == "reference":
         if rank != 0:
@@ -452,7 +452,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "arithmetic": "fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; MxM factorisations fp64", "l2": "working set (Omega_sqt 320 MB, F/eps/var 1 GB each at c3) far exceeds the 126 MB L2",
-                   "cuda_graph": bool(use_graph), "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
+                   "optimizer": "torch.optim.Adam(lr=1e-2, fused=True)", "cuda_graph": bool(use_graph), "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
         "e2e": {"value": e2e_value, "unit": "spot-samples/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
