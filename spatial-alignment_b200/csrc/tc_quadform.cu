@@ -817,6 +817,36 @@ __global__ void pack_rows_kernel(long rows, int K, int Kp, long ld, long sIn, co
     lo[obase + r * Kp + k] = l;
   }
 }
+// 128-bit variant of pack_rows_kernel / pack_G_kernel (K % 4 == 0, ld % 4 == 0, 16-byte aligned source): one warp per
+// row, four elements per lane and access, no per-element 64-bit division
+__global__ void __launch_bounds__(256) pack_rows4_kernel(long rows, int K4, int Kp, long ld, long sIn,
+                                                         const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo) {
+  const int b = blockIdx.z;
+  const float* src = in + (long)b * sIn;
+  const long obase = (long)b * rows * Kp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + warp; r < rows; r += nwarps) {
+    const float4* s4 = reinterpret_cast<const float4*>(src + r * ld);
+    uint2* h2 = reinterpret_cast<uint2*>(hi + obase + r * Kp);
+    uint2* l2 = reinterpret_cast<uint2*>(lo + obase + r * Kp);
+    for (int k = lane; k < K4; k += 32) {
+      const float4 v = s4[k];
+      uint2 h, l;
+      split_pair(v.x, v.y, h.x, l.x);
+      split_pair(v.z, v.w, h.y, l.y);
+      h2[k] = h;
+      l2[k] = l;
+    }
+  }
+}
+// true if the 128-bit pack applies
+static inline bool pack4_ok(const float* src, long ld, long sIn, int K, int Kp) {
+  return K >= 128 && (K & 3) == 0 && (Kp & 3) == 0 && (ld & 3) == 0 && (sIn & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+
 __global__ void pack_trans_kernel(long rows, int K, int Kp, long ld, long sIn, const float* __restrict__ in,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float t[32][33];
@@ -1026,7 +1056,12 @@ extern "C" int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, 
   __nv_bfloat16 *a_hi = (__nv_bfloat16*)w, *a_lo = (__nv_bfloat16*)(w + sa), *b_hi = (__nv_bfloat16*)(w + 2 * sa),
                 *b_lo = (__nv_bfloat16*)(w + 2 * sa + sb);
   auto pack = [&](long rows, const float* src, long ld, long sIn, int rows_major, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    if (rows_major) {
+    if (rows_major && pack4_ok(src, ld, sIn, K, Kp)) {
+      long blocks = (rows + 7) / 8;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      dim3 grid((unsigned)blocks, 1, batch);
+      pack_rows4_kernel<<<grid, 256, 0, st>>>(rows, K / 4, Kp, ld, sIn, src, hi, lo);
+    } else if (rows_major) {
       long blocks = (rows * K + 255) / 256;
       if (blocks > 148 * 8) blocks = 148 * 8;
       dim3 grid((unsigned)blocks, 1, batch);
@@ -1249,7 +1284,13 @@ extern "C" int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, 
   uint8_t* w = static_cast<uint8_t*>(ws);
   __nv_bfloat16 *g_hi = (__nv_bfloat16*)w, *g_lo = (__nv_bfloat16*)(w + a.g), *w_hi = (__nv_bfloat16*)(w + 2 * a.g),
                 *w_lo = (__nv_bfloat16*)(w + 2 * a.g + a.w);
-  pack_G_kernel<<<148 * 8, 256, 0, st>>>(R, L, a.Lp, G, g_hi, g_lo);
+  if (pack4_ok(G, L, 0, L, a.Lp)) {
+    long blocks = (R + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_rows4_kernel<<<dim3((unsigned)blocks, 1, 1), 256, 0, st>>>(R, L / 4, a.Lp, L, 0, G, g_hi, g_lo);
+  } else {
+    pack_G_kernel<<<148 * 8, 256, 0, st>>>(R, L, a.Lp, G, g_hi, g_lo);
+  }
   GPSA_LAUNCH_CHECK();
   {
     dim3 grid((unsigned)feat_nblk(M), (unsigned)((L + 31) / 32 < 64 ? (L + 31) / 32 : 64));
