@@ -273,7 +273,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const long col = col0 + j;
-                if (col < p.Ncols) Cb[col * p.ldc + row] += alpha * __uint_as_float(v[j]);  // lanes = consecutive rows: coalesced
+                // lanes = consecutive rows: coalesced.  A reduction (RED.ADD, fire and forget) instead of load-add-store:
+                // every element has exactly one writer, so the result is the same, but 200 dependent global round
+                // trips per thread (the compiler cannot hoist the loads over the stores) made this epilogue cost
+                // ~95 us per tile
+                if (col < p.Ncols) atomicAdd(&Cb[col * p.ldc + row], alpha * __uint_as_float(v[j]));
               }
             } else if (vec4 && col0 + 32 <= p.Ncols) {
               float4* dst = reinterpret_cast<float4*>(Cb + row * p.ldc + col0);
