@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) kl_G_kernel(int M, int D, int V, int v, c
   for (int i = threadIdx.x; i < M * M; i += blockDim.x) s += Kinv[i] * (double)Om[i];
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     double t = 0.0;
-    for (int k = 0; k < M; ++k) t += Kinv[(long)m * M + k] * e[k];
+    for (int k = 0; k < M; ++k) t += Kinv[(long)k * M + m] * e[k];  // K^-1 = X^T X is bitwise symmetric: coalesced over m
     Ke[(long)j * M + m] = t;
     s += t * e[m];
   }
