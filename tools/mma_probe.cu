@@ -50,14 +50,7 @@ __global__ void __launch_bounds__(128, 1) mma_chain_kernel(int N, int chains, in
 
 // same chain with the A operand in TENSOR MEMORY (tcgen05.mma TS form): does the ~58-cycle floor of small-N MMAs
 // (the 4 KB A fetch from shared memory) go away?
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// (umma_bf16_ts now lives in tc_common.cuh)
 
 __global__ void __launch_bounds__(128, 1) mma_chain_ts_kernel(int N, int iters, int mix, long long* out, float* check) {
   extern __shared__ uint8_t smem_raw[];
@@ -143,6 +136,95 @@ __global__ void __launch_bounds__(128, 1) mma_chain_ts_kernel(int N, int iters, 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 probe: a CTA pair issues ONE tcgen05.mma of M = 256 (each CTA its own 128 rows of A and of D in its
+// own TMEM) with the B operand split by rows between the two CTAs' shared memories (CTA 0: rows [0, N/2), CTA 1:
+// rows [N/2, N)).  Checks that understanding numerically and times a dependent chain in the leader.
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+mma2_probe_kernel(int N, int iters, long long* out, float* check) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 8192;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8192 + 16384);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int crank = (int)cluster_ctarank();
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (8192 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  __syncthreads();
+  {  // A[grow][k] = (grow + k) & 15, grow = 128 * crank + r; K-major rows of 64 B, 64-byte swizzle
+    const int r = threadIdx.x, grow = 128 * crank + r;
+    for (int k = 0; k < 16; ++k) {
+      const int chunk = (k >> 3) ^ ((r >> 1) & 3);
+      reinterpret_cast<__nv_bfloat16*>(sA + r * 64 + chunk * 16)[k & 7] = __float2bfloat16_rn((float)((grow + k) & 15));
+    }
+    // this CTA's half of B: local row j <-> n = crank * N/2 + j;  B[n][k] = (k == n % 16) ? n + 1 : 0
+    for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+      const int n = crank * (N / 2) + j, k = n & 15;
+      const int chunk = (k >> 3) ^ ((j >> 1) & 3);
+      reinterpret_cast<__nv_bfloat16*>(sB + j * 64 + chunk * 16)[k & 7] = __float2bfloat16_rn((float)(n + 1));
+    }
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    if (crank == 0) {
+      const uint64_t a = make_desc_sw64(smem_u32(sA)), b = make_desc_sw64(smem_u32(sB));
+      const uint32_t idesc = make_idesc_bf16(256, N);
+      __syncwarp();
+      t0 = clock64();
+      if (elect_one()) {
+        for (int i = 0; i < iters; ++i) {
+          const uint32_t acc = i > 0 ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+              "l"(a), "l"(b), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, 0);  // both CTAs: the multicast commit arrives on each CTA's own barrier
+    t1 = clock64();
+    if (crank == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (check) {  // D[grow][n] for n < 64: lane = row, 32 columns per load
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      for (int n = 0; n < 32; ++n) check[((long)crank * 128 + threadIdx.x) * 64 + c * 32 + n] = __uint_as_float(v[n]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
 }
 
 // fp64 throughput probes: 8 independent accumulator chains per thread
@@ -239,6 +321,32 @@ int main() {
         if (hc[r * 16 + n] != (float)((r + n) & 63)) ++bad;
     printf("TS layout check (lane = row, column c = bf16 pair (2c, 2c+1)): %s, %d mismatches; row 5: %g %g %g %g ... (%s)\n",
            bad ? "MISMATCH" : "ok", bad, hc[80], hc[81], hc[82], hc[83], cudaGetErrorString(e));
+  }
+  {
+    cudaFuncSetAttribute(mma2_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    float* d_chk2;
+    cudaMalloc(&d_chk2, 256 * 64 * 4);
+    mma2_probe_kernel<<<2, 128, smem>>>(64, 1, d_out, d_chk2);
+    static float hc2[256 * 64];
+    cudaError_t e = cudaMemcpy(hc2, d_chk2, sizeof(hc2), cudaMemcpyDeviceToHost);
+    int bad = 0;
+    for (int r = 0; r < 256; ++r)
+      for (int n = 0; n < 64; ++n)
+        if (hc2[r * 64 + n] != (float)((n + 1) * ((r + (n & 15)) & 15))) ++bad;
+    printf("cta_group::2 check (M = 256 over a CTA pair, B rows [0,N/2) in CTA 0 and [N/2,N) in CTA 1, N = 64): %s, %d mismatches "
+           "(%s); D[1][0..3] = %g %g %g %g, D[129][32..35] = %g %g %g %g\n",
+           bad ? "MISMATCH" : "ok", bad, cudaGetErrorString(e), hc2[64], hc2[65], hc2[66], hc2[67], hc2[129 * 64 + 32],
+           hc2[129 * 64 + 33], hc2[129 * 64 + 34], hc2[129 * 64 + 35]);
+    if (e == cudaSuccess) {
+      printf("cta_group::2 dependent chain, cycles per MMA (M = 256):");
+      for (int N : {32, 64, 128, 208, 256}) {
+        mma2_probe_kernel<<<2, 128, smem>>>(N, 512, d_out, nullptr);
+        long long hh = 0;
+        if (cudaMemcpy(&hh, d_out, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { printf(" err"); break; }
+        printf("  N=%d: %.1f", N, (double)hh / 512);
+      }
+      printf("\n");
+    }
   }
   double* d_d;
   cudaMalloc(&d_d, 148 * 8 * 1024 * 8);
