@@ -416,7 +416,7 @@ struct FwdParams {
 };
 struct FwdMaps {
   CUtensorMap a_hi, a_lo;    // At [R, Kp], box 32 x 128
-  CUtensorMap b_hi[4], b_lo[4];  // Lt [L, Mp, Kp], boxes 32 x {128, 64, 32, 16} x 1
+  CUtensorMap b_hi[5], b_lo[5];  // Lt [L, Mp, Kp], boxes 32 x {128, 64, 32, 16, 8} x 1 (8: pair kernel only)
 };
 
 // CL = CTAs per cluster.  CL = 2: the two CTAs of a cluster work on two different 128-row tiles against the SAME gene
@@ -688,6 +688,247 @@ __global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward, cta_group::2 ("pair") variant -- EXPERIMENTAL, selected with GPSA_FWD_PAIR=1 (Mp = 208 only)
+// -------------------------------------------------------------------------------------------------
+// A 2-CTA cluster owns 256 rows: each CTA keeps its own 128-row A tile (shared memory hi + lo, TMEM copy of A_hi for
+// NTS K steps) and its own half of the accumulator rows in its own TMEM, but only HALF of every factor block: with
+// N = 32 (kb + 1) for both K steps of block kb, CTA 0 stores rows [0, N/2) and CTA 1 rows [N/2, N) of the block at the
+// same ring offset (1024 kb (kb+1)) -- so the ring holds TWO genes in the space one took.  The leader's single thread issues tcgen05.mma.cta_group::2 (M = 256); the peer's
+// TMA completes on the LEADER's `full` barrier; `empty`, `tfull`, `a_empty` are multicast commits to both CTAs;
+// `tempty` and `ta_full` of the leader collect the arrivals of both CTAs' epilogue warps (remote mbarrier.arrive).
+// Per SM the TMA write stream into shared memory is halved (56 KB per gene instead of 112 KB), which is what bounds
+// the single-CTA kernel.
+template <int NTS>
+__global__ void __launch_bounds__(256, 1) tc_qf_fwd_pair_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA_hi = smem;
+  uint8_t* sA_lo = smem + p.nkb * FA_BYTES;
+  uint8_t* ring = smem + 2 * p.nkb * FA_BYTES;  // block kb: [hi: N/2 x 32 | lo: N/2 x 32] at 1024 kb (kb+1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ring_bytes);
+  // the ring holds TWO genes (parity gp of the running gene count): barrier index gp * 8 + kb
+  uint64_t* full = bars;                     // [16] leader only: both CTAs' TMA bytes
+  uint64_t* empty = bars + 2 * FWD_MAXSLOT;  // [16] per CTA, multicast commit of the leader
+  uint64_t* tfull = bars + 4 * FWD_MAXSLOT;  // [2]  per CTA, multicast commit
+  uint64_t* tempty = tfull + 2;              // [2]  leader only: 4 warps x 2 CTAs
+  uint64_t* a_full = tempty + 2;             // per CTA (own A tile)
+  uint64_t* a_empty = a_full + 1;            // per CTA, multicast commit
+  uint64_t* ta_full = a_empty + 1;           // leader only: 4 warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm.a_hi);
+    prefetch_tmap(&tm.a_lo);
+    for (int i = 0; i < 5; ++i) { prefetch_tmap(&tm.b_hi[i]); prefetch_tmap(&tm.b_lo[i]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2 * FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(ta_full, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int crank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+  const int n_rp = (p.n_rt + 1) / 2;
+  const int n_items = n_rp * p.gsplit;
+  const int Mp = p.Mp, nkb = p.nkb;
+  const int gene_bytes = p.ring_bytes >> 1;  // one gene of this CTA's half blocks (a multiple of 1024)
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A tile, own half of every factor block =====
+    uint32_t aphase = 0;
+    int gc = 0;  // genes produced so far: ring half gc & 1, barrier phase (gc >> 1) & 1
+    const bool leader = elect_one();
+    for (int item = cid; item < n_items; item += ncl) {
+      const int rt = (item % n_rp) * 2 + crank, gs = item / n_rp;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      mbar_wait_u(a_empty, aphase ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(a_full, 2 * nkb * FA_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) {
+          tma_load_2d(sA_hi + kb * FA_BYTES, &tm.a_hi, a_full, kb * FK, rt * TM);
+          tma_load_2d(sA_lo + kb * FA_BYTES, &tm.a_lo, a_full, kb * FK, rt * TM);
+        }
+      }
+      aphase ^= 1;
+      for (int g = g0; g < g1; ++g, ++gc) {
+        const int gp = gc & 1;
+        const uint32_t sphase = (uint32_t)(gc >> 1) & 1u;
+        for (int kb = nkb - 1; kb >= 0; --kb) {
+          const int nrows = min(FK * (kb + 1), Mp), hrows = nrows >> 1;
+          const int bi = gp * FWD_MAXSLOT + kb;
+          mbar_wait_u(&empty[bi], sphase ^ 1);
+          if (leader) {
+            if (crank == 0) mbar_arrive_expect_tx(&full[bi], 2 * nrows * FROW);  // hi + lo, both CTAs' halves
+            const uint32_t fbar = cluster_addr_of(&full[bi], 0);
+            uint8_t* dst = ring + gp * gene_bytes + 1024 * kb * (kb + 1);
+            const int r0 = crank * hrows;
+            int row = 0;
+#pragma unroll
+            for (int hsel = 0; hsel < 5; ++hsel) {
+              const int hgt = 128 >> hsel;
+              for (; row + hgt <= hrows; row += hgt) {
+                tma_load_3d_2sm(dst + row * FROW, &tm.b_hi[hsel], fbar, kb * FK, r0 + row, g);
+                tma_load_3d_2sm(dst + (hrows + row) * FROW, &tm.b_lo[hsel], fbar, kb * FK, r0 + row, g);
+              }
+            }
+          }
+        }
+      }
+    }
+    // drain (as if two more genes were produced): the last multicast commits of the leader have arrived here
+    // before this CTA exits
+    for (int i = 0; i < 2; ++i, ++gc)
+      for (int kb = 0; kb < nkb; ++kb) mbar_wait_u(&empty[(gc & 1) * FWD_MAXSLOT + kb], ((uint32_t)(gc >> 1) & 1u) ^ 1u);
+  } else if (warp == 1 && crank == 0) {
+    // ===== MMA issuer (pair leader only) =====
+    int acc = 0, gc = 0;
+    uint32_t acc_phase = 0, aphase = 0;
+    const uint32_t DHI = (uint32_t)(make_desc_sw64(0) >> 32);
+    const uint32_t a_hi0 = (uint32_t)make_desc_sw64(smem_u32(sA_hi));
+    const uint32_t a_lo0 = (uint32_t)make_desc_sw64(smem_u32(sA_lo));
+    const uint32_t ring0 = (uint32_t)make_desc_sw64(smem_u32(ring));
+    constexpr uint32_t idesc0 = make_idesc_bf16(2 * TM, 0);
+    const bool leader = elect_one();
+    for (int item = cid; item < n_items; item += ncl) {
+      const int gs = item / n_rp;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      mbar_wait_u(a_full, aphase);
+      mbar_wait_u(ta_full, aphase);  // both CTAs: A tile landed and A_hi copied into TMEM
+      aphase ^= 1;
+      tc_fence_after();
+      for (int g = g0; g < g1; ++g, ++gc) {
+        const int gp = gc & 1;
+        const uint32_t sphase = (uint32_t)(gc >> 1) & 1u;
+        const uint32_t ringg = ring0 + (uint32_t)((gp * gene_bytes) >> 4);
+        mbar_wait_u(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * TN;
+#pragma unroll
+        for (int kb = FWD_MAXKB - 1; kb >= 0; --kb) {
+          if (kb >= nkb) continue;
+          const int bi = gp * FWD_MAXSLOT + kb;
+          mbar_wait_u(&full[bi], sphase);
+          tc_fence_after();
+          const int nrows = (kb + 1 < nkb) ? FK * (kb + 1) : Mp;
+          const uint32_t b_hi = ringg + (uint32_t)((1024 * kb * (kb + 1)) >> 4);
+          const uint32_t b_lo = b_hi + ((uint32_t)((nrows >> 1) * FROW) >> 4);
+          const uint32_t idesc = idesc0 | ((uint32_t)(nrows >> 3) << 17);  // same N for both K steps of the block
+          if (leader) {
+#pragma unroll
+            for (int k = FK / UMMA_K - 1; k >= 0; --k) {
+              const int k0 = kb * FK + k * UMMA_K;
+              if (k0 >= Mp) continue;
+              const uint32_t accum = (k0 != Mp - UMMA_K) ? 1u : 0u;
+              const uint32_t aoff = (uint32_t)((kb * FA_BYTES) >> 4) + (uint32_t)(k * UMMA_K * 2 >> 4);
+              const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
+              const int ks = kb * (FK / UMMA_K) + k;
+              if (ks < NTS) {
+                const uint32_t a_t = tmem_base + (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
+                umma2_bf16_ts(d, a_t, desc64(b_hi + boff, DHI), idesc, accum);
+                umma2_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
+                umma2_bf16_ts(d, a_t, desc64(b_lo + boff, DHI), idesc, 1u);
+              } else {
+                umma2_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
+                umma2_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
+                umma2_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
+              }
+            }
+            umma2_commit_mc(&empty[bi]);
+          }
+        }
+        if (leader) umma2_commit_mc(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (leader) umma2_commit_mc(a_empty);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue (both CTAs): own TMEM rows -> q2; arrivals go to the LEADER's barriers =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0, ta_phase = 0;
+    const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
+    const uint32_t ta_leader = cluster_addr_of(ta_full, 0);
+    const uint32_t te_leader[2] = {cluster_addr_of(&tempty[0], 0), cluster_addr_of(&tempty[1], 0)};
+    for (int item = cid; item < n_items; item += ncl) {
+      const int rt = (item % n_rp) * 2 + crank, gs = item / n_rp;
+      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
+      const long row = (long)rt * TM + q * 32 + lane;
+      if (NTS > 0) {
+        mbar_wait(a_full, ta_phase);
+        ta_phase ^= 1;
+        const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
+#pragma unroll
+        for (int ks = 0; ks < NTS; ++ks) {
+          const uint8_t* src = sA_hi + (ks >> 1) * FA_BYTES + rl * FROW;
+          const int c = (ks & 1) * 2;
+          const uint4 v0 = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+          const uint4 v1 = *reinterpret_cast<const uint4*>(src + (((c + 1) ^ sw) << 4));
+          const uint32_t col = (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
+          tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + col, v0, v1);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ta_leader);
+      for (int g = g0; g < g1; ++g) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
+            s0 = fmaf(x, x, s0);
+            s1 = fmaf(y, y, s1);
+          }
+        }
+        if (rem16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + n32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
+            s0 = fmaf(x, x, s0);
+            s1 = fmaf(y, y, s1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(te_leader[acc]);
+        if (row < p.R) p.q2[row * p.L + g] = s0 + s1;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -1168,7 +1409,7 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   {
     const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
     const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
-    for (int hsel = 0; hsel < 4; ++hsel) {
+    for (int hsel = 0; hsel < 5; ++hsel) {
       const uint32_t box[3] = {(uint32_t)FK, (uint32_t)(128 >> hsel), 1};
       if (make_tmap(&maps.b_hi[hsel], lt_hi, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) ||
           make_tmap(&maps.b_lo[hsel], lt_lo, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
@@ -1222,6 +1463,44 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   // first 4 K steps if 32 columns are free next to the accumulator.  GPSA_FWD_TMEM_A=0/4 overrides (experiments).
   static const int want_ta = [] { const char* e = getenv("GPSA_FWD_TMEM_A"); return e ? atoi(e) : 12; }();
   const bool ta = want_ta > 0 && gr && (TN - f.Mp) >= 32 && f.Mp >= 5 * UMMA_K;
+  // EXPERIMENTAL cta_group::2 kernel (GPSA_FWD_PAIR=1): Mp = 208, at least two row tiles
+  static const int want_pair = [] { const char* e = getenv("GPSA_FWD_PAIR"); return e ? atoi(e) : 0; }();
+  if (want_pair && f.Mp == 208 && p.n_rt >= 2) {
+    FwdParams q = p;
+    q.ring_bytes = 2 * (1024 * (f.nkb - 1) * f.nkb + f.Mp * FROW);  // two genes of this CTA's half blocks
+    const int smem_pair = fixed + 256 + q.ring_bytes;                 // + room for the 32 ring barriers
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      if (cudaFuncSetAttribute(tc_qf_fwd_pair_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair) != cudaSuccess)
+        return GPSA_ERR_CUDA;
+      pair_attr = true;
+    }
+    const int n_rp = (q.n_rt + 1) / 2, ncl_max = sm_count() / 2;
+    q.gsplit = 1;
+    if (n_rp < ncl_max) {
+      q.gsplit = (ncl_max + n_rp - 1) / n_rp;
+      if (q.gsplit > L) q.gsplit = L;
+    }
+    q.genes_per = (L + q.gsplit - 1) / q.gsplit;
+    q.gsplit = (L + q.genes_per - 1) / q.genes_per;
+    const int n_items = n_rp * q.gsplit;
+    const int ncl = n_items < ncl_max ? n_items : ncl_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_pair;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_qf_fwd_pair_kernel<12>, maps, q) != cudaSuccess) return GPSA_ERR_CUDA;
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
+  }
   // clusters of 2 CTAs (multicast factor stream) whenever there are at least two row tiles per gene range
   static const int want_cl = [] { const char* e = getenv("GPSA_FWD_CLUSTER"); return e ? atoi(e) : 2; }();
   const int cl = (want_cl >= 2 && p.n_rt >= 2) ? 2 : 1;
