@@ -4,6 +4,7 @@ expression.  Tolerance: the engine multiplies bf16 (hi, lo) splits in three pass
 carries ~2^-16 relative error instead of fp32's 2^-24; sums of K such terms are checked scale-relative
 (max |err| / max |ref|) at 1e-4, the tolerance BASELINE.json's north_star states for the ELBO path."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -14,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 f32, f64, u8 = torch.float32, torch.float64, torch.uint8
 TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -197,3 +199,37 @@ def test_vectorised_elementwise_kernels_match_scalar(L):
                             outs[0]):
         # the A-bar product accumulates with atomics (run-to-run order) and G-bar amplifies it through K^-1: 1e-4
         assert relerr(x1, x0) < (1e-4 if name in ("G", "Gtilde", "log_ls", "log_var") else 1e-5), name
+
+
+@pytest.mark.skipif(os.environ.get("GPSA_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: exercises the experimental cta_group::2 forward kernel (GPSA_FWD_PAIR=1)")
+@pytest.mark.parametrize("R,Lg", [(700, 37), (640, 9), (4096, 64), (129, 3)])
+def test_pair_forward_kernel_experimental(R, Lg):
+    """The cta_group::2 forward kernel is selected by an environment variable that the library reads once, so each
+    case runs in its own process: even / odd row-tile counts, more / fewer pair items than clusters."""
+    import subprocess
+    import sys
+
+    code = f"""
+import os, sys, ctypes as C, torch
+sys.path.insert(0, {os.path.join(ROOT, "spatial-alignment_b200")!r})
+from gpsa import _lib, _ops
+M, R, Lg = 200, {R}, {Lg}
+g = torch.Generator().manual_seed(R + Lg)
+A = torch.randn(M, R, generator=g) * 0.3
+Osq = torch.randn(Lg, M, M, generator=g) * 0.1
+Omega, Ltril, L64, hld, info = _ops.omega_prepare(Osq.cuda())
+ref = torch.einsum("mr,pmk,kr->rp", A.double(), Omega.double().cpu(), A.double())
+lib = _lib.lib()
+ws = _lib.tc_workspace(M, R, Lg, Ltril)
+q2 = torch.full((R, Lg), float("nan"), device="cuda")
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+assert lib.gpsa_quadform_fwd_tc(M, R, Lg, A.cuda().data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(), st) == 0
+torch.cuda.synchronize()
+err = float((q2.cpu().double() - ref).abs().max() / ref.abs().max())
+print("relerr", err)
+assert err < 1e-4, err
+"""
+    env = dict(os.environ, GPSA_FWD_PAIR="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
