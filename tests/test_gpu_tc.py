@@ -233,3 +233,43 @@ assert err < 1e-4, err
     env = dict(os.environ, GPSA_FWD_PAIR="1")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("GPSA_TEST_FULLSIZE", "0") != "1",
+                    reason="opt-in (GPSA_TEST_FULLSIZE=1): C3-sized quadratic form, ~6 GB of device memory")
+def test_quadform_fwd_full_size_properties(L):
+    """BASELINE.json's C3 shape (M = 200, R = S*N = 128 000, L = 2000) through size-independent properties:
+    (1) a random sample of entries against float64, (2) partition invariance -- a sub-block of rows x genes computed
+    on its own equals the same entries of the full result, (3) q2 >= 0 (it is a squared norm)."""
+    from gpsa import _ops
+
+    M, R, Lg = 200, 128000, 2000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, R, device="cuda", generator=g) * 0.3
+    Osq = torch.randn(Lg, M, M, device="cuda", generator=g) * 0.1
+    Omega, Ltril, L64, hld, info = _ops.omega_prepare(Osq)
+    del L64
+    lib = L.lib()
+    ws = ws_for(L, M, R, Lg)
+    q2 = torch.full((R, Lg), float("nan"), device="cuda")
+    assert lib.gpsa_quadform_fwd_tc(M, R, Lg, A.data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    stream()) == 0
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(q2).all()) and float(q2.min()) >= 0.0
+    # (1) sampled parity
+    rows = torch.randint(0, R, (96,), device="cuda", generator=g)
+    genes = torch.randint(0, Lg, (48,), device="cuda", generator=g)
+    ref = torch.einsum("mr,pmk,kr->rp", A[:, rows].double(), Omega[genes].double(), A[:, rows].double())
+    got = q2[rows][:, genes].double()
+    assert float((got - ref).abs().max() / ref.abs().max()) < TOL
+    # (2) partition invariance: rows [4096, 5120) x genes [100, 164) on their own
+    r0, r1, p0, p1 = 4096, 5120, 100, 164
+    As = A[:, r0:r1].contiguous()
+    Ls = Ltril[p0:p1].contiguous()
+    ws2 = ws_for(L, M, r1 - r0, p1 - p0)
+    q2s = torch.full((r1 - r0, p1 - p0), float("nan"), device="cuda")
+    assert lib.gpsa_quadform_fwd_tc(M, r1 - r0, p1 - p0, As.data_ptr(), Ls.data_ptr(), q2s.data_ptr(), ws2.data_ptr(),
+                                    ws2.numel(), stream()) == 0
+    torch.cuda.synchronize()
+    full = q2[r0:r1, p0:p1]
+    assert float((q2s - full).abs().max() / full.abs().max()) < 1e-5
