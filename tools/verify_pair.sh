@@ -7,6 +7,9 @@
 set -x
 mkdir -p gpurun_out
 GPSA_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q -k pair 2>&1 | tail -3
+# the opt-in C3-sized property test, default kernel and pair kernel (make it unconditional once it has passed here)
+GPSA_TEST_FULLSIZE=1 timeout 300 python -m pytest tests/test_gpu_tc.py -m gpu -q -k full_size 2>&1 | tail -3
+GPSA_FWD_PAIR=1 GPSA_TEST_FULLSIZE=1 timeout 300 python -m pytest tests/test_gpu_tc.py -m gpu -q -k full_size 2>&1 | tail -3
 GPSA_FWD_PAIR=1 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for v in 0 1; do
   GPSA_FWD_PAIR=$v timeout 120 python tools/bench_quadform.py --which fwd --reps 3 2>&1 | tail -1
