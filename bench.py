@@ -8,10 +8,16 @@ Prints ONE JSON line (rank 0).  metric = spot-samples/s = iters/s x S x N_spots 
 `value` is device-timed with inputs resident in HBM, `e2e` is the same iteration driven from pinned
 HOST buffers (H2D copy of coordinates + outputs and a D2H read of the loss every step).  `roofline`
 covers the dominant kernels (the implicit-feature quadratic-form GEMMs) timed live with CUDA events
-inside the library; `cpu_baseline` is the CPU restatement of the reference (oracle/) timed on this
-box's host cores on a bounded sample.  `--impl reference` prints that CPU arm as its own line.
+inside the library; `cpu_baseline` is the UNMODIFIED reference (baseline/_ref) timed on this box's host
+cores on a bounded sample.  `--impl reference` prints that CPU arm as its own line.
+
+Without --config the headline is C3 (the configuration the metric is quoted on) and, at N = 1, the line also
+carries `other_configs`: C1 and C2 (whole iteration replayed from a CUDA graph, next to the reference's own eager
+PyTorch path on the same GPU) and C4 (the largest single-GPU shape), each with ms_per_step, roofline and clocks.
+C5 is an 8-GPU job: `bench.py --gpus 8 --config c5` under torchrun.
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -35,16 +41,20 @@ CONFIGS = {
     "c4": dict(V=8, Nv=10000, D=3, P=500, M=256, S=8, kernel="rbf", desc="3-D serial sections: 8 views x 10k spots x 500 genes"),
     "c5": dict(V=8, Nv=50000, D=2, P=5000, M=512, S=16, kernel="rbf", desc="large-N scaling: 8 views x 50k spots x 5k genes"),
 }
+GENE_BLOCK = 256  # granularity of the per-gene noise streams of make_data
 
 
 # --------------------------------------------------------------------------------------------------
 # synthetic data: jittered grid on [0,10]^2, views >= 1 warped by a smooth random
-# field, outputs = random-Fourier-feature draws of an RBF GP + noise, z-scored per gene per view
+# field, outputs = random-Fourier-feature draws of an RBF GP + noise, z-scored per gene per view.
+# Coordinates do not depend on the gene count, and every gene's column depends only on (seed, view, gene):
+# a rank that owns genes [lo, hi) generates exactly its slice of the same matrix.
 # --------------------------------------------------------------------------------------------------
-def make_data(cfg, seed, genes=None):
+def make_data(cfg, seed, genes=None, gene_range=None):
     rng = np.random.default_rng(seed)
     V, Nv, D = cfg["V"], cfg["Nv"], cfg["D"]
     P = genes if genes is not None else cfg["P"]
+    lo, hi = gene_range if gene_range is not None else (0, P)
     side = int(math.ceil(math.sqrt(Nv)))
     base = np.stack(np.meshgrid(np.linspace(0, 10, side), np.linspace(0, 10, side)), -1).reshape(-1, 2)
     Xs, Ys = [], []
@@ -52,12 +62,17 @@ def make_data(cfg, seed, genes=None):
     ph_w = rng.uniform(0, 2 * np.pi, 16)
     om_y = rng.standard_normal((64, 2))
     ph_y = rng.uniform(0, 2 * np.pi, 64)
-    W = rng.standard_normal((64, P)).astype(np.float32) * math.sqrt(2.0 / 64)
+    W = np.random.default_rng([seed, 7]).standard_normal((64, P)).astype(np.float32)[:, lo:hi] * math.sqrt(2.0 / 64)
     for v in range(V):
         keep = rng.permutation(base.shape[0])[:Nv]
         x = base[np.sort(keep)] + rng.uniform(-0.3, 0.3, (Nv, 2)) * (10.0 / side)
         feats = np.cos(x @ om_y.T + ph_y).astype(np.float32)
-        y = feats @ W + 0.03 * rng.standard_normal((Nv, P)).astype(np.float32)
+        y = feats @ W
+        for b in range(lo // GENE_BLOCK, (hi + GENE_BLOCK - 1) // GENE_BLOCK):
+            g0, g1 = b * GENE_BLOCK, min(P, (b + 1) * GENE_BLOCK)
+            nz = np.random.default_rng([seed, 100 + v, b]).standard_normal((Nv, g1 - g0), dtype=np.float32)
+            a0, a1 = max(g0, lo), min(g1, hi)
+            y[:, a0 - lo:a1 - lo] += 0.03 * nz[:, a0 - g0:a1 - g0]
         y = (y - y.mean(0)) / (y.std(0) + 1e-6)
         if v > 0:
             amp = rng.standard_normal((16, 2)) * 0.3 / 4.0
@@ -83,13 +98,12 @@ def flops_iter(cfg, genes=None):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle restatement of the reference on the box's host cores
+# CPU arm
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_rate(cfg, seed, budget_s=25.0, log=None):
-    """Times fwd + loss + bwd of the reference's algorithm (oracle/gpsa_oracle.py, float32, materialising
-    the [S,L,N,M] tensor exactly like gpsa/models/vgpsa.py:193-196) with every host thread.  Configs whose
-    full shape cannot be materialised (C3: 205 GB) are timed at a few small gene counts and extrapolated
-    linearly in the gene count, as BASELINE.md 5 prescribes.  Returns (spot_samples_per_s, description)."""
+def cpu_reference_rate(cfg, seed, budget_s=25.0):
+    """Fallback when baseline/_ref is absent: the oracle restatement of the reference (oracle/gpsa_oracle.py, float32,
+    materialising the [S,L,N,M] tensor exactly like gpsa/models/vgpsa.py:193-196) on every host thread.
+    Returns (spot_samples_per_s, description, measured_s, extrapolated)."""
     import torch
 
     from oracle import gpsa_oracle as orc
@@ -99,7 +113,7 @@ def cpu_reference_rate(cfg, seed, budget_s=25.0, log=None):
     N = V * Nv
     full_bytes = 4.0 * S * cfg["P"] * N * M
     small = full_bytes < 2e9
-    gene_counts = [cfg["P"]] if small else [1, 2]
+    gene_counts = [cfg["P"]] if small else [1, 2, 3]
     times = []
     t_start = time.time()
     for Pg in gene_counts:
@@ -121,58 +135,84 @@ def cpu_reference_rate(cfg, seed, budget_s=25.0, log=None):
             if (small and it >= 3 and time.time() - t_start > budget_s) or (not small and it >= 1):
                 break
         times.append(float(np.median(reps)))
-        if log is not None:
-            log.append((Pg, times[-1]))
     if small:
-        t_full = times[0]
-        sample = f"full {cfg['desc']}: median of {len(reps)} iterations"
-    else:
-        c = (times[1] - times[0]) / (gene_counts[1] - gene_counts[0])
-        c = max(c, 1e-6)
-        t0 = times[0] - c * gene_counts[0]
-        t_full = t0 + c * cfg["P"]
-        sample = (f"P={gene_counts} genes timed ({times[0]:.2f}s, {times[1]:.2f}s per iteration; the full shape needs a "
-                  f"{full_bytes/1e9:.0f} GB [S,P,N,M] tensor), linear extrapolation to P={cfg['P']}: {t_full:.1f} s/iter")
-    return S * N / t_full, sample
+        return S * N / times[0], f"oracle port, full {cfg['desc']}: median of {len(reps)} iterations", times[0], False
+    c, t0 = np.polyfit(gene_counts, times, 1)
+    c = max(float(c), 1e-6)
+    t_full = float(t0) + c * cfg["P"]
+    sample = (f"oracle port timed at P={gene_counts} genes ({', '.join(f'{t:.2f}s' for t in times)} per iteration; the full shape "
+              f"needs a {full_bytes/1e9:.0f} GB [S,P,N,M] tensor), linear fit extrapolated to P={cfg['P']}: {t_full:.1f} s/iter")
+    return S * N / t_full, sample, times[-1], True
 
 
 def reference_rate(cfg, config_name, seed, steps, warmup):
     """The reference arm: the UNMODIFIED reference (baseline/_ref, installed from /root/reference with pip --target)
     driven through its own public API on this box's host cores by baseline/reference_arm.py, in a subprocess with
-    CUDA hidden.  Configurations whose [S,P,N,M] tensor cannot exist (C3: 205 GB) are timed at two small gene
-    counts and extrapolated linearly in P.  Falls back to the oracle port when baseline/_ref is absent.
-    Returns (spot_samples_per_s, kind, sample, cores)."""
+    CUDA hidden.  Configurations whose [S,P,N,M] tensor cannot exist (C3: 205 GB) are timed at P = 2, 4, 8 genes and
+    a least-squares line t0 + c P is extrapolated to the named gene count; the result says so.
+    Returns a dict: rate, kind, sample, cores, steps_run, warmup_run, measured_ms (a directly measured step: the full
+    shape, or the largest timed gene count), extrapolated (bool), fit (dict or None)."""
     S, N = cfg["S"], cfg["V"] * cfg["Nv"]
     full_bytes = 4.0 * S * cfg["P"] * N * cfg["M"]
     small = full_bytes < 2e9
-    genes = [cfg["P"]] if small else [2, 6]
+    genes = [cfg["P"]] if small else [2, 4, 8]
     script = os.path.join(ROOT, "baseline", "reference_arm.py")
     if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gpsa")):
-        steps = max(1, min(steps, 50 if small else 3))
-        warmup = max(1, min(warmup, 10 if small else 1))
-        cmd = [sys.executable, script, "--config", config_name, "--genes", ",".join(map(str, genes)), "--steps", str(steps),
-               "--warmup", str(warmup), "--seed", str(seed)]
+        steps_run = max(1, min(steps, 50 if small else 3))
+        warmup_run = max(1, min(warmup, 10 if small else 1))
+        cmd = [sys.executable, script, "--config", config_name, "--genes", ",".join(map(str, genes)), "--steps", str(steps_run),
+               "--warmup", str(warmup_run), "--seed", str(seed)]
         try:
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
             out = json.loads(res.stdout.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001
             out = {"unavailable": f"reference arm failed: {e}"}
         if "runs" in out:
             t = [r["s_per_step"] for r in out["runs"]]
+            base = (f"unmodified reference (baseline/_ref) through its own API, median of {steps_run} steps after {warmup_run} "
+                    f"warm-up, anomaly detection off, {out['torch_threads']} threads")
             if small:
-                t_full = t[0]
-                sample = (f"unmodified reference (baseline/_ref), full {config_name} shape, median of {steps} steps after "
-                          f"{warmup} warm-up, anomaly detection off, {out['torch_threads']} threads")
-            else:
-                c = max((t[1] - t[0]) / (genes[1] - genes[0]), 1e-6)
-                t_full = t[0] + c * (cfg["P"] - genes[0])
-                sample = (f"unmodified reference (baseline/_ref) timed at P={genes} genes ({t[0]:.2f} s, {t[1]:.2f} s per step, "
-                          f"median of {steps}, anomaly detection off, {out['torch_threads']} threads); the full shape needs a "
-                          f"{full_bytes/1e9:.0f} GB [S,P,N,M] tensor, so linear extrapolation in P to P={cfg['P']}: "
-                          f"{t_full:.1f} s/step")
-            return S * N / t_full, "reference", sample, out["cores"]
-    rate, sample = cpu_reference_rate(cfg, seed)
-    return rate, "port", "baseline/_ref unavailable -> oracle port: " + sample, os.cpu_count()
+                return dict(rate=S * N / t[0], kind="reference", sample=f"{base}, full {config_name} shape", cores=out["cores"],
+                            steps_run=steps_run, warmup_run=warmup_run, measured_ms=1e3 * t[0], extrapolated=False, fit=None)
+            # the fit uses the FASTEST step at each gene count (least disturbed by other host activity; favours the
+            # reference); a non-positive slope means the timings were disturbed beyond use -> flagged, two-point slope
+            t = [r.get("s_min", r["s_per_step"]) for r in out["runs"]]
+            c, t0 = np.polyfit(genes, t, 1)
+            reliable = c > 0
+            if not reliable:
+                c = max((max(t) - min(t)) / (genes[-1] - genes[0]), 1e-6)
+                t0 = min(t) - c * genes[0]
+            c = float(c)
+            resid = [float(ti - (t0 + c * g)) for g, ti in zip(genes, t)]
+            t_full = float(t0) + c * cfg["P"]
+            base = base.replace("median of", "fastest of") + ("" if reliable else " [FIT UNRELIABLE: timings not monotone in P]")
+            sample = (f"{base}; timed at P={genes} genes ({', '.join(f'{ti:.2f} s' for ti in t)} per step): the full shape needs a "
+                      f"{full_bytes/1e9:.0f} GB [S,P,N,M] tensor, so value = least-squares fit t0 + c*P (t0={t0:.2f} s, c={c:.4f} s/gene, "
+                      f"residuals {', '.join(f'{r:+.3f}' for r in resid)} s) EXTRAPOLATED to P={cfg['P']}: {t_full:.1f} s/step")
+            return dict(rate=S * N / t_full, kind="reference", sample=sample, cores=out["cores"], steps_run=steps_run,
+                        warmup_run=warmup_run, measured_ms=1e3 * t[-1], extrapolated=True,
+                        fit={"genes": genes, "s_per_step": t, "t0_s": float(t0), "s_per_gene": c, "residuals_s": resid,
+                             "extrapolated_s_per_step": t_full})
+    rate, sample, meas, extra = cpu_reference_rate(cfg, seed)
+    return dict(rate=rate, kind="port", sample="baseline/_ref unavailable -> " + sample, cores=os.cpu_count(), steps_run=1,
+                warmup_run=1, measured_ms=1e3 * meas, extrapolated=extra, fit=None)
+
+
+def gpu_eager_reference(config_name, seed):
+    """The UNMODIFIED reference run through its own eager PyTorch path on this box's GPU (C1/C2 fit): the 'same box,
+    library kernels' bar of SURVEY.md 8(d).  Returns a dict or None."""
+    script = os.path.join(ROOT, "baseline", "reference_arm.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gpsa")):
+        return None
+    try:
+        res = subprocess.run([sys.executable, script, "--config", config_name, "--steps", "20", "--warmup", "5", "--seed",
+                              str(seed), "--device=cuda"], capture_output=True, text=True, timeout=300)
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+        r = out["runs"][0]
+        return {"ms_per_step": 1e3 * r["s_per_step"], "steps": r["steps"],
+                "what": "unmodified reference (baseline/_ref), eager PyTorch on this GPU, wall clock around step() incl. loss.item()"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -214,21 +254,22 @@ def summarise_clocks(lines):
     return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(cfg, seed, genes_slice=None, device="cuda"):
+def build_model(cfg, seed, genes_slice=None, device="cuda", kmeans=None, gene_range=None):
     """Construct the public-API model on synthetic data.  Inducing locations are initialised from a random
-    subset of the spots instead of KMeans for the large configs (init is outside the timed region)."""
+    subset of the spots instead of KMeans for the large configs (init is outside the timed region); `kmeans`
+    overrides that choice.  `gene_range` = (lo, hi): generate only that slice of the outputs (gene sharding)."""
     import torch
 
     import gpsa
 
-    X, Y, nl = make_data(cfg, seed)
+    X, Y, nl = make_data(cfg, seed, gene_range=gene_range)
     if genes_slice is not None:
         Y = np.ascontiguousarray(Y[:, genes_slice])
     kern = gpsa.rbf_kernel if cfg["kernel"] == "rbf" else gpsa.matern12_kernel
     data_dict = {"expression": {"spatial_coords": torch.from_numpy(X), "outputs": torch.from_numpy(Y), "n_samples_list": nl}}
     np.random.seed(seed)
     torch.manual_seed(seed)
-    use_kmeans = cfg["V"] * cfg["Nv"] <= 20000
+    use_kmeans = (cfg["V"] * cfg["Nv"] <= 20000) if kmeans is None else bool(kmeans)
     model = gpsa.VariationalGPSA(data_dict, n_spatial_dims=cfg["D"], m_X_per_view=cfg["M"], m_G=cfg["M"],
                                  data_init=use_kmeans, n_latent_gps={"expression": None},
                                  mean_function="identity_fixed", kernel_func_warp=kern, kernel_func_data=kern,
@@ -245,70 +286,29 @@ def build_model(cfg, seed, genes_slice=None, device="cuda"):
     return model, data_dict, X, Y, nl
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the whole iteration from one CUDA graph (gpsa.graph.GraphedIteration); for the "
-                         "launch-bound toy configurations c1/c2")
-    ap.add_argument("--genes", type=int, default=None,
-                    help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
-                         "the JSON line is then NOT the named configuration and says so")
-    ap.add_argument("--engine", type=int, default=None, help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 (default: auto)")
-    args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    if args.genes is not None:
-        cfg["P"] = args.genes
-        cfg["desc"] += f" [REDUCED to {args.genes} genes: profiling aid, not the named configuration]"
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    S, N = cfg["S"], cfg["V"] * cfg["Nv"]
-    workload = (f"{args.config}: {cfg['desc']}, D={cfg['D']}, M_X=M_G={cfg['M']}, S={cfg['S']}, {cfg['kernel']}, "
-                f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step")
+def load_traffic(config_name, kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this round
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None when that config was not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(config_name, {}).get(kernel_key)
+        return (e["bytes_per_launch"], e["source"]) if e else (None, None)
+    except Exception:  # noqa: BLE001
+        return None, None
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        rate, kind, sample, cores = reference_rate(cfg, args.config, args.seed, args.steps, args.warmup)
-        line = {
-            "impl": "reference", "metric": "spot_samples_per_s", "value": rate, "unit": "spot-samples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * S * N / rate,
-            "iters_per_s": rate / (S * N), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
-            "cpu_baseline": {"value": rate, "unit": "spot-samples/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": rate, "unit": "spot-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
-        return
 
+# --------------------------------------------------------------------------------------------------
+def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, with_e2e=True):
+    """Build the model of one configuration, time `steps` iterations after `warmup`, return the measured fields."""
     import torch
     import torch.distributed as dist
 
     from gpsa import _lib, _ops
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("GPSA_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.engine is not None:
-        _ops.ENGINE["value"] = args.engine
-
-    # gene sharding across ranks: rank r owns a contiguous slice of the output genes
-    P = cfg["P"]
     from gpsa.parallel import gene_range
 
+    S, N, P = cfg["S"], cfg["V"] * cfg["Nv"], cfg["P"]
     lo, hi = gene_range(P, world, rank)
-    genes_slice = slice(lo, hi) if world > 1 else None
-    model, data_dict, X, Y, nl = build_model(cfg, args.seed, genes_slice)
+    model, data_dict, X, Y, nl = build_model(cfg, args.seed, gene_range=(lo, hi) if world > 1 else None)
     sharder = None
     if world > 1:
         from gpsa import parallel
@@ -317,7 +317,7 @@ def main():
     data_dev = {"expression": {"spatial_coords": data_dict["expression"]["spatial_coords"].cuda(),
                                "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
-    use_graph = args.graph and world == 1
+    use_graph = use_graph and world == 1
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=use_graph, fused=True)
     x_dev, y_dev = data_dev["expression"]["spatial_coords"], data_dev["expression"]["outputs"]
     graphed = None
@@ -348,7 +348,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for it in range(args.warmup):
+    for it in range(warmup):
         step(it)
     barrier()
 
@@ -362,14 +362,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for it in range(args.steps):
-        loss = step(args.warmup + it)
+    for it in range(steps):
+        loss = step(warmup + it)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.gpsa_launch_count() - n0
-    import ctypes as C
-
     counts = (C.c_int * 4)()
     tot_ms = (C.c_double * 4)()
     lib.gpsa_prof_read(counts, tot_ms)
@@ -380,84 +378,196 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
-    ms_step = ms / args.steps
-    value = S * N / (ms_step * 1e-3)
+    ms_step = ms / steps
+    out = {"ms_per_step": ms_step, "value": S * N / (ms_step * 1e-3), "iters_per_s": 1e3 / ms_step,
+           "clocks": summarise_clocks(clock_lines), "cuda_graph": bool(use_graph),
+           # under a CUDA graph the library's launchers ran once, at capture: `launches_per_replay` is that count
+           "gpu_launches": int(launches) if not use_graph else int(getattr(graphed, "launches", 0)) * steps}
 
     # ---- e2e: same iteration from pinned host buffers + D2H read of the loss, every step
-    x_pin = data_dict["expression"]["spatial_coords"].pin_memory()
-    y_pin = data_dict["expression"]["outputs"].pin_memory()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    host_loss = 0.0
-    for it in range(args.steps):
-        x_dev.copy_(x_pin, non_blocking=True)
-        y_dev.copy_(y_pin, non_blocking=True)
-        host_loss = float(step(args.warmup + args.steps + it).item())
-    t1.record()
-    barrier()
-    te = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+    host_loss = float(loss.item())
+    if with_e2e:
+        x_pin = data_dict["expression"]["spatial_coords"].pin_memory()
+        y_pin = data_dict["expression"]["outputs"].pin_memory()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for it in range(steps):
+            x_dev.copy_(x_pin, non_blocking=True)
+            y_dev.copy_(y_pin, non_blocking=True)
+            host_loss = float(step(warmup + steps + it).item())
+        t1.record()
+        barrier()
+        te = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": S * N / (float(te) / steps * 1e-3), "unit": "spot-samples/s",
+                      "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 4}
+    out["loss_last"] = host_loss
+
+    # ---- roofline of the dominant kernels
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks
+                else "fallback (B200_PROFILING.md ~1.4 PF sustained)")
+    local_genes = (hi - lo) if world > 1 else P
+    f_iter, f_q2 = flops_iter(cfg, genes=local_genes)
+    q_ms = sum(tot_ms[i] for i in range(3))
+    q_launch = sum(counts[i] for i in range(3))
+    names = ["fwd", "bwd_alpha", "bwd_omega"]
+    engine = _ops.pick_engine(cfg["M"], S * N, local_genes)
+    tc = engine in _ops.TC_ENGINES
+    kern = {"fwd": "tc_gemm_kernel<4> (implicit-feature forward)" if engine == 2 else "tc_qf_fwd_kernel",
+            "bwd_alpha": "tc_gemm_kernel<1>", "bwd_omega": "tc_gemm_kernel<2>"}
+    per = {n: tot_ms[i] / max(counts[i], 1) for i, n in enumerate(names)}
+    f_one = f_q2 / 3.0  # algorithmic (symmetric-minimum) flops of ONE of the three products, per launch
+    passes = 3 if tc else 1
+    products = {n: {"kernel": kern[n] if tc else "feat_*_kernel (fp32 SIMT)", "ms_per_launch": per[n] if per[n] > 0 else None,
+                    "algorithmic_tflops": f_one / (per[n] * 1e-3) / 1e12 if per[n] > 0 else None,
+                    "issued_tflops": passes * f_one / (per[n] * 1e-3) / 1e12 if per[n] > 0 else None} for n in names}
+    dom = max(names, key=lambda n: per[n])
+    achieved = products[dom]["algorithmic_tflops"]
+    traffic, traffic_src = load_traffic(config_name if (world == 1 and args.genes is None) else "", dom) if tc else (None, None)
+    out["roofline"] = {
+        "bound": "tensor", "kernel": f"{products[dom]['kernel']} ({dom}: dominant of the three quadratic-form products)",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+        "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+        "note": ("achieved counts ALGORITHMIC flops (M(M+1) per (sample, spot, gene)); the tcgen05 engine issues 3 bf16 MMA "
+                 "passes per product for fp32-class accuracy, so the tensor pipe runs at `issued_tflops` and the ceiling of "
+                 "`frac` is 1/3") if tc else "launch-latency-bound configuration: ~1e8 flop behind ~250 dependent kernels",
+        "frac_issued": (passes * achieved / peak_tf) if achieved else None,
+        "products": products, "share_of_step": q_ms / ms if ms > 0 else None, "launches": int(q_launch),
+        "all_three_algorithmic_tflops": (f_q2 * steps) / (q_ms * 1e-3) / 1e12 if q_ms > 0 else None,
+        "engine": ("tcgen05, bf16 hi/lo split x 3 passes, fp32 accumulate in TMEM" if tc else "fp32 SIMT (exact fp32 accumulate)"),
+        "whole_step_tflops": f_iter / (ms_step * 1e-3) / 1e12,
+        "whole_step_frac": f_iter / (ms_step * 1e-3) / 1e12 / peak_tf,
+    }
+    out["sharding"] = ("none" if world == 1 else
+                       f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads")
+    del model, opt, graphed, sharder, data_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def workload_of(name, cfg):
+    return (f"{name}: {cfg['desc']}, D={cfg['D']}, M_X=M_G={cfg['M']}, S={cfg['S']}, {cfg['kernel']}, "
+            f"fixed_view_idx=0; one step = forward + loss_fn + backward + Adam.step")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="default: c3 as the headline plus other_configs (c1, c2, c4) at one GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip other_configs")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole iteration from one CUDA graph (gpsa.graph.GraphedIteration); for the "
+                         "launch-bound toy configurations c1/c2")
+    ap.add_argument("--genes", type=int, default=None,
+                    help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
+                         "the JSON line is then NOT the named configuration and says so")
+    ap.add_argument("--engine", type=int, default=None,
+                    help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 / Cholesky-form forward, 2 tcgen05 / feature-form forward (default: auto)")
+    args = ap.parse_args()
+    config_name = args.config or "c3"
+    cfg = dict(CONFIGS[config_name])
+    if args.genes is not None:
+        cfg["P"] = args.genes
+        cfg["desc"] += f" [REDUCED to {args.genes} genes: profiling aid, not the named configuration]"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    S, N = cfg["S"], cfg["V"] * cfg["Nv"]
+    workload = workload_of(config_name, cfg)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = reference_rate(cfg, config_name, args.seed, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": "spot_samples_per_s", "value": r["rate"], "unit": "spot-samples/s",
+            "n_gpus": args.gpus, "steps": r["steps_run"], "warmup": r["warmup_run"],
+            "requested_steps": args.steps, "requested_warmup": args.warmup,
+            # ms_per_step is a MEASURED step (the full shape, or the largest gene count that was timed); `value` of a
+            # configuration the reference cannot materialise comes from the fit and is flagged as extrapolated
+            "ms_per_step": r["measured_ms"], "value_is_extrapolated": r["extrapolated"],
+            "extrapolated_ms_per_step": (1e3 * S * N / r["rate"]) if r["extrapolated"] else None, "fit": r["fit"],
+            "iters_per_s": r["rate"] / (S * N), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": r["rate"], "unit": "spot-samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["rate"], "unit": "spot-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gpsa import _ops
+
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = S * N / (float(te) / args.steps * 1e-3)
+        # stdout carries the ONE JSON line: NCCL's own log (NCCL_DEBUG=INFO/VERSION, whatever the caller set) goes to
+        # stderr instead of being silenced, so rank / transport lines stay countable
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.engine is not None:
+        _ops.ENGINE["value"] = args.engine
+
+    main_res = run_config(config_name, cfg, args, args.steps, args.warmup, args.graph, world, rank)
+
+    others = None
+    if args.config is None and world == 1 and not args.no_others and args.genes is None:
+        others = []
+        for name, k, w, graph in (("c1", 50, 10, True), ("c2", 50, 10, True), ("c4", min(args.steps, 5), 3, False)):
+            ocfg = dict(CONFIGS[name])
+            try:
+                r = run_config(name, ocfg, args, k, w, graph, 1, 0, with_e2e=False)
+                entry = {"config": {"workload": workload_of(name, ocfg)}, "steps": k, "warmup": w,
+                         "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "spot-samples/s",
+                         "iters_per_s": r["iters_per_s"], "cuda_graph": r["cuda_graph"], "roofline": r["roofline"],
+                         "clocks": r["clocks"], "loss_last": r["loss_last"]}
+                if graph:
+                    entry["gpu_eager_baseline"] = gpu_eager_reference(name, args.seed)
+            except Exception as e:  # noqa: BLE001
+                entry = {"config": {"workload": workload_of(name, ocfg)}, "error": f"{type(e).__name__}: {e}"[:300]}
+            others.append(entry)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md ~1.4 PF sustained)"
-    local_genes = (hi - lo) if world > 1 else P
-    f_iter, f_q2 = flops_iter(cfg, genes=local_genes)
-    q_ms = sum(tot_ms[i] for i in range(3))
-    q_launch = sum(counts[i] for i in range(3))
-    names = ["fwd", "bwd_alpha", "bwd_omega"]
-    kern = {"fwd": "tc_qf_fwd_kernel<2,1,12>", "bwd_alpha": "tc_gemm_kernel<1>", "bwd_omega": "tc_gemm_kernel<2>"}
-    per = {n: tot_ms[i] / max(counts[i], 1) for i, n in enumerate(names)}
-    f_one = f_q2 / 3.0  # algorithmic (symmetric-minimum) flops of ONE of the three products, per launch
-    tc = (_ops.pick_engine(cfg["M"], S * N, local_genes) == 1)
-    passes = 3 if tc else 1
-    products = {n: {"kernel": kern[n] if tc else "feat_*_kernel (fp32 SIMT)", "ms_per_launch": per[n],
-                    "algorithmic_tflops": f_one / (per[n] * 1e-3) / 1e12 if per[n] > 0 else None,
-                    "issued_tflops": passes * f_one / (per[n] * 1e-3) / 1e12 if per[n] > 0 else None} for n in names}
-    dom = max(names, key=lambda n: per[n])
-    achieved = products[dom]["algorithmic_tflops"]
-    roofline = {
-        "bound": "tensor", "kernel": f"{products[dom]['kernel']} ({dom}: dominant of the three quadratic-form products)",
-        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-        "peak_source": peak_src,
-        "traffic": 3.30e9 if (tc and args.config == "c3" and dom == "fwd" and world == 1 and args.genes is None) else None,
-        "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r1c_fwd_ncu_summary.txt" if tc else None,
-        "note": ("achieved counts ALGORITHMIC flops (M(M+1) per (sample, spot, gene)); the tcgen05 engine issues 3 bf16 MMA "
-                 "passes per product for fp32-class accuracy, so the tensor pipe runs at `issued_tflops`"),
-        "frac_issued": (passes * achieved / peak_tf) if achieved else None,
-        "products": products, "share_of_step": q_ms / ms if ms > 0 else None, "launches": int(q_launch),
-        "all_three_algorithmic_tflops": (f_q2 * args.steps) / (q_ms * 1e-3) / 1e12 if q_ms > 0 else None,
-        "engine": "tcgen05, bf16 hi/lo split x 3 passes, fp32 accumulate in TMEM" if tc else "fp32 SIMT (exact fp32 accumulate)",
-        "whole_step_tflops": f_iter / (ms_step * 1e-3) / 1e12,
-    }
     cpu = None
     if not args.no_cpu_baseline:
-        rate, kind, sample, cores = reference_rate(cfg, args.config, args.seed, 2, 1)
-        cpu = {"value": rate, "unit": "spot-samples/s", "cores": cores, "kind": kind, "sample": sample}
+        r = reference_rate(cfg, config_name, args.seed, 2, 1)
+        cpu = {"value": r["rate"], "unit": "spot-samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "value_is_extrapolated": r["extrapolated"]}
     line = {
-        "metric": "spot_samples_per_s", "value": value, "unit": "spot-samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "arithmetic": "fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; MxM factorisations fp64", "l2": "working set (Omega_sqt 320 MB, F/eps/var 1 GB each at c3) far exceeds the 126 MB L2",
-                   "optimizer": "torch.optim.Adam(lr=1e-2, fused=True)", "cuda_graph": bool(use_graph), "sharding": "none" if world == 1 else f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"},
-        "e2e": {"value": e2e_value, "unit": "spot-samples/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
-                "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "clocks": summarise_clocks(clock_lines), "loss_last": host_loss,
+        "metric": "spot_samples_per_s", "value": main_res["value"], "unit": "spot-samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "iters_per_s": main_res["iters_per_s"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload,
+                   "arithmetic": "fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; MxM factorisations fp64",
+                   "l2": "working set (Omega_sqt 320 MB, F/eps/var 1 GB each at c3) far exceeds the 126 MB L2",
+                   "optimizer": "torch.optim.Adam(lr=1e-2, fused=True)", "cuda_graph": main_res["cuda_graph"],
+                   "sharding": main_res["sharding"]},
+        "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
+        "cpu_baseline": cpu, "clocks": main_res["clocks"], "loss_last": main_res["loss_last"],
     }
+    if others is not None:
+        line["other_configs"] = others
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

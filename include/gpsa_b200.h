@@ -121,6 +121,10 @@ int gpsa_tc_supported(int M);
 size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L);
 int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws, size_t ws_bytes,
                          cudaStream_t stream);
+/* The same forward in the implicit-feature form the backward products use: q2 = Phi(A) W(Omega), Phi generated on the
+ * fly, no Cholesky factor needed.  This is the form the data layer uses (engine 2). */
+int gpsa_quadform_fwd_feat_tc(int M, long R, int L, const float* A, const float* Omega, float* q2, void* ws,
+                              size_t ws_bytes, cudaStream_t stream);
 int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float* G, const float* Omega, float* Abar,
                                void* ws, size_t ws_bytes, cudaStream_t stream);
 int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, const float* G, float* H, void* ws,
@@ -217,7 +221,8 @@ typedef struct {
   float* var;             /* out [R,L] marginal variances (saved) */
   double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
   double* ws64;           /* 2*M*M doubles */
-  int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 */
+  int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 with the ||a^T L||^2 forward,
+                             2 = tcgen05 split-bf16 with the implicit-feature forward (default for large shapes) */
   const float* Ltril;     /* [L,M,M] chol(Omega) from gpsa_omega_prepare (engine 1 only) */
   void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;

@@ -330,13 +330,24 @@ def loss_fn(params, cfg: Config, cache, F_samples, outputs):
     return -ll + kl  # :540
 
 
-def elbo_and_grads(params_np, cfg: Config, X_np, Y_np, S, eps, dtype=torch.float64, materialise=True, G_test=None):
+def elbo_and_grads(params_np, cfg: Config, X_np, Y_np, S, eps, dtype=torch.float64, materialise=True, G_test=None,
+                   device="cpu"):
     """One full hot-path iteration (forward + loss + backward) at `dtype`.
 
     Returns (out, cache, loss, grads) with everything detached.  This is the
     function the parity tests call; at float64 it is the ground truth the
     tolerance rule of SURVEY 7.5 is anchored on.
+
+    `device`: where torch evaluates the restatement.  "cpu" everywhere except the
+    benchmark-sized parity tests (tests/test_gpu_fullsize.py), which pass "cuda" so
+    that the float64 truth of a 128 000-row case takes seconds instead of minutes;
+    it is the same code either way (torch factory calls follow the device context).
     """
+    with torch.device(device):
+        return _elbo_and_grads(params_np, cfg, X_np, Y_np, S, eps, dtype, materialise, G_test)
+
+
+def _elbo_and_grads(params_np, cfg: Config, X_np, Y_np, S, eps, dtype, materialise, G_test):
     params = {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=True) for k, v in params_np.items()}
     X = {m: torch.tensor(np.asarray(v), dtype=dtype) for m, v in X_np.items()}
     Y = {m: torch.tensor(np.asarray(v), dtype=dtype) for m, v in Y_np.items()}

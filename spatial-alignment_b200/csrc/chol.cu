@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(256) potrf_kernel(int M, T* A, long stride, T*
   __shared__ T red[32];
   ld = block_sum<T>(ld, red);
   if (tid == 0) {
-    if (half_logdet) half_logdet[blockIdx.x] = ld;
+    // a non-positive pivot poisons the log-determinant: the KL terms, hence the loss, become NaN on the device, so a
+    // failed factorisation cannot pass silently even when nobody reads `info` (torch.cholesky raises on the host)
+    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (T)NAN : ld;
     if (info) info[blockIdx.x] = s_bad;
   }
 }
@@ -373,7 +375,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) potrf_packed_kernel(int M, T* A
   __shared__ T red[32];
   ld = block_sum<T>(ld, red);
   if (tid == 0) {
-    if (half_logdet) half_logdet[blockIdx.x] = ld;
+    // a non-positive pivot poisons the log-determinant: the KL terms, hence the loss, become NaN on the device, so a
+    // failed factorisation cannot pass silently even when nobody reads `info` (torch.cholesky raises on the host)
+    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (T)NAN : ld;
     if (info) info[blockIdx.x] = s_bad;
   }
 }
@@ -503,11 +507,12 @@ int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
   const size_t psm = packed_smem<T>(M, 0);
   if (!no_packed && psm <= 226 * 1024) {
-    static size_t attr = 0;
-    if (psm > 48 * 1024 && psm > attr) {
+    static size_t attr[GPSA_MAX_DEVICES] = {};
+    const int dev = gpsa_dev();
+    if (psm > 48 * 1024 && psm > attr[dev]) {
       if (cudaFuncSetAttribute(potrf_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
         return GPSA_ERR_CUDA;
-      attr = 226 * 1024;
+      attr[dev] = 226 * 1024;
     }
     potrf_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, A, (long)M * M, half_logdet, info);
     GPSA_LAUNCH_CHECK();
@@ -528,11 +533,12 @@ int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
   const size_t psm = packed_smem<T>(M, 2 * PB);
   if (!no_packed && psm <= 226 * 1024 && L != X) {
-    static size_t attr = 0;
-    if (psm > 48 * 1024 && psm > attr) {
+    static size_t attr[GPSA_MAX_DEVICES] = {};
+    const int dev = gpsa_dev();
+    if (psm > 48 * 1024 && psm > attr[dev]) {
       if (cudaFuncSetAttribute(trtri_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
         return GPSA_ERR_CUDA;
-      attr = 226 * 1024;
+      attr[dev] = 226 * 1024;
     }
     trtri_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, L, X, (long)M * M);
     GPSA_LAUNCH_CHECK();

@@ -32,6 +32,15 @@ void gpsa_prof_end(int slot, cudaStream_t st);
 
 static inline int gpsa_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute state is per DEVICE: the launchers that opt into large dynamic shared memory cache what they
+// have set in arrays indexed by the current device ordinal (one process may drive several GPUs)
+#define GPSA_MAX_DEVICES 64
+static inline int gpsa_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < GPSA_MAX_DEVICES) ? d : 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

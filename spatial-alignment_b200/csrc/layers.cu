@@ -1006,7 +1006,8 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   const long R = a->R;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine != 0 && (a->engine != 1 || !gpsa_tc_supported(M) || !a->Ltril || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine < 0 || a->engine > 2) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine != 0 && (!gpsa_tc_supported(M) || !a->tc_ws || (a->engine == 1 && !a->Ltril))) return GPSA_ERR_UNSUPPORTED;
   TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
                          a->ws64, st));
   TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
@@ -1014,7 +1015,7 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   kq_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->log_var, a->kq);
   GPSA_LAUNCH_CHECK();
   // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
-  if (a->engine == 1) {
+  if (a->engine >= 1) {
     TRY(gpsa_gemm_tc(R, L, M, 1, a->A, R, 0, 0, a->dlt, L, 0, 0, a->F, L, 0, 1.f, 0, 1, a->tc_ws, a->tc_ws_bytes, st));
   } else {
     TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
@@ -1025,9 +1026,13 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
     gpsa_prof_begin(0, st);
     TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
     gpsa_prof_end(0, st);
-  } else {
+  } else if (a->engine == 1) {
     gpsa_prof_begin(0, st);
     TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->var, a->tc_ws, a->tc_ws_bytes, st));
+    gpsa_prof_end(0, st);
+  } else {
+    gpsa_prof_begin(0, st);
+    TRY(gpsa_quadform_fwd_feat_tc(M, R, L, a->A, a->Omega, a->var, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   }
   const bool al16 = ((reinterpret_cast<uintptr_t>(a->eps) | reinterpret_cast<uintptr_t>(a->F) |
@@ -1053,7 +1058,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   const long R = a->R, MM = (long)M * M;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine != 0 && (a->engine != 1 || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine < 0 || a->engine > 2 || (a->engine != 0 && !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
   double* Kbar = a->ws64;
   double* P = a->ws64 + MM;
   double* T1 = a->ws64 + 2 * MM;
@@ -1072,7 +1077,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
     GPSA_LAUNCH_CHECK();
   }
   // delta-bar = A Fbar (+ kl_bar K^-1 delta)
-  if (a->engine == 1 && R <= 2000000000L) {
+  if (a->engine >= 1 && R <= 2000000000L) {
     TRY(gpsa_gemm_tc(M, L, (int)R, 1, a->A, R, 0, 1, a->F_bar, L, 0, 0, a->dlt_bar, L, 0, 1.f, 0, 0, a->tc_ws,
                      a->tc_ws_bytes, st));
   } else {
@@ -1084,7 +1089,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   if (a->kl_bar) TRY((axpy_dev<double, float>(st, (long)M * L, 1.0, a->kl_bar, a->KD, a->dlt_bar)));
   // Abar = q1bar o B + delta Fbar^T + 2 (sum_p Gm Omega_p) a
   TRY(colscale<float>(st, M, R, a->q1bar, a->B, a->Abar, 0));
-  if (a->engine == 1) {
+  if (a->engine >= 1) {
     TRY(gpsa_gemm_tc(R, M, L, 1, a->F_bar, L, 0, 1, a->dlt, L, 0, 1, a->Abar, R, 0, 1.f, 1, 1, a->tc_ws, a->tc_ws_bytes, st));
   } else {
     TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,

@@ -45,11 +45,13 @@ constexpr int NSTAGE = 2;
 constexpr int OPER_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
 constexpr int RAW_BYTES = 8192;  // Omega-bar only: 4 row groups x 2 halves of [8 rows x 32 r] fp32, 128B-swizzled
 
-enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_SUMSQ = 3 };
+enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_SUMSQ = 3, MODE_FWD = 4 };
 constexpr int N_GEN_WARPS = 8;
-__host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode == MODE_OMEGA ? RAW_BYTES : 0); }
+// modes whose A operand is generated on the fly from TMA-staged raw rows of A (never stored)
+__host__ __device__ constexpr bool mode_gen(int mode) { return mode == MODE_OMEGA || mode == MODE_FWD; }
+__host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode_gen(mode) ? RAW_BYTES : 0); }
 __host__ __device__ constexpr int gemm_smem(int mode) { return NSTAGE * stage_bytes(mode) + 1024 /*alignment*/ + 256 /*barriers*/; }
-__host__ __device__ constexpr int gemm_threads(int mode) { return mode == MODE_OMEGA ? 256 + 32 * N_GEN_WARPS : 256; }
+__host__ __device__ constexpr int gemm_threads(int mode) { return mode_gen(mode) ? 256 + 32 * N_GEN_WARPS : 256; }
 
 struct GemmParams {
   int n_mt, n_nt, group_m, n_split, kblocks, kb_per;
@@ -89,7 +91,18 @@ __device__ __forceinline__ int item_batch(const GemmParams& p, int item) {
 // -------------------------------------------------------------------------------------------------
 // generic 128 x 256 x K tile GEMM, C = (A_hi + A_lo)(B_hi + B_lo)^T in three bf16 passes
 // -------------------------------------------------------------------------------------------------
-// In MODE_OMEGA tmA_hi is the fp32 map of A [M, R] (box 32 r x 8 rows) the generators read from; tmA_lo is unused.
+// In MODE_OMEGA / MODE_FWD tmA_hi is the fp32 map of A [M, R] (box 32 r x 8 rows) the generators read from; tmA_lo is
+// unused.
+//
+// MODE_FWD is the forward quadratic form as the same implicit-feature GEMM the two backward products use:
+//     q2[r, p] = sum_{(i,j)} Phi[r,(i,j)] W[(i,j), p],   Phi[r,(i,j)] = a_r[i] a_r[j],  W = c_b Omega_p[i,j]
+// (reference gpsa/models/vgpsa.py:193-196; the Cholesky factor of Omega is not needed for it).
+// Output tile = 128 rows r x 256 genes, K runs over the nblk 8x8 feature blocks (I, J) in feat.cu order.  Per K block
+// the producer stages the two 8-row groups a[I*8.., r0..r0+127] and a[J*8.., ...] (8 KB, fp32) and the 256 x 64 block of
+// the packed W^T (hi, lo); the generator warps (thread = row r, two threads per row) multiply, split to bf16 (hi, lo)
+// and write the swizzled K-major A operand.  Measured against fp64 the three-pass feature form is as accurate as the
+// ||a^T L||^2 form (2-3e-6 scale-relative at C3-like operands, tests/test_gpu_tc.py) and runs at the issue rate of the
+// plain GEMM core instead of the shrinking-N triangular stream.
 template <int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -110,13 +123,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi);
-    if (MODE != MODE_OMEGA) prefetch_tmap(&tmA_lo);
+    if (!mode_gen(MODE)) prefetch_tmap(&tmA_lo);
     prefetch_tmap(&tmB_hi);
     prefetch_tmap(&tmB_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], MODE == MODE_OMEGA ? 1 + N_GEN_WARPS : 1);  // TMA expect_tx arrive (+ generator warps)
+      mbar_init(&full[s], mode_gen(MODE) ? 1 + N_GEN_WARPS : 1);  // TMA expect_tx arrive (+ generator warps)
       mbar_init(&empty[s], 1);
       mbar_init(&rawfull[s], 1);
     }
@@ -152,12 +165,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           grow[2 * q + 1] = J * FB;
         }
       }
+      int fI = 0, fJ = 0;  // MODE_FWD: feature block (I, J) of K block kb (feat.cu order: J runs from I to nb - 1)
       for (int kb = kb0; kb < kb1; ++kb) {
         uint8_t* st = smem + stage * STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], MODE == MODE_OMEGA ? 2 * B_TILE_BYTES : OPER_BYTES);
-          if (MODE == MODE_TEST && p.batch > 0) {
+          mbar_arrive_expect_tx(&full[stage], mode_gen(MODE) ? 2 * B_TILE_BYTES : OPER_BYTES);
+          if (MODE == MODE_FWD) {
+            // raw rows of A for this feature block: group 0 = rows I*8.., group 1 = rows J*8.., four 32-r boxes each
+            mbar_arrive_expect_tx(&rawfull[stage], RAW_BYTES);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tma_load_2d(st + OPER_BYTES + c * 1024, &tmA_hi, &rawfull[stage], mt * TM + c * 32, fI * FB);
+              tma_load_2d(st + OPER_BYTES + (4 + c) * 1024, &tmA_hi, &rawfull[stage], mt * TM + c * 32, fJ * FB);
+            }
+          } else if (MODE == MODE_TEST && p.batch > 0) {
             const int bz = item_batch(p, item);
             tma_load_3d(st, &tmA_hi, &full[stage], kb * BK, mt * TM, bz);
             tma_load_3d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM, bz);
@@ -185,6 +207,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         __syncwarp();
+        if (MODE == MODE_FWD && ++fJ == p.nb) { ++fI; fJ = fI; }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
@@ -256,10 +279,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         if (row < p.Mrows) atomicAdd(&p.C[row * p.ldc + nt / p.halves], s0 + s1);
-      } else if (MODE == MODE_TEST || MODE == MODE_OMEGA) {
+      } else if (MODE == MODE_TEST || MODE == MODE_OMEGA || MODE == MODE_FWD) {
         float* Cb = p.C + (MODE == MODE_TEST ? (long)item_batch(p, item) * p.sC : 0);
         const float alpha = MODE == MODE_TEST ? p.alpha : 1.f;
-        const bool vec4 = MODE == MODE_TEST && !p.accumulate && !p.trans_add && (p.ldc & 3) == 0 &&
+        const bool vec4 = (MODE == MODE_TEST || MODE == MODE_FWD) && !p.accumulate && !p.trans_add && (p.ldc & 3) == 0 &&
                           ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
 #pragma unroll 1
         for (int c = 0; c < TN / 32; ++c) {
@@ -378,6 +401,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           split_pair(u1.x * w1.x, u1.y * w1.y, hi.z, lo.z);
           split_pair(u1.z * w1.z, u1.w * w1.w, hi.w, lo.w);
           const uint32_t off = sw128_offset(t, 4 * h + c);
+          *reinterpret_cast<uint4*>(st + off) = hi;
+          *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (MODE == MODE_FWD && warp >= 8) {
+    // ===== feature-operand generators, forward =====
+    // A-operand row t = row r of the tile, its 64 K columns = features (il, jl) of block (I, J): phi = a_I[il][r] a_J[jl][r].
+    // Thread (t, h) writes the four 16-byte chunks il = 4h .. 4h+3 (chunk il = the eight jl of one il) of row t.
+    // Raw layout: box c = t / 32 of group g at OPER_BYTES + (4g + c) KB, 8 rows (m) x 32 r fp32, 128B-swizzled: lanes of
+    // a warp read consecutive r of ONE row m -> 32 distinct banks.
+    const int gt = threadIdx.x - 256;
+    const int t = gt & (TM - 1);
+    const int h = gt >> 7;
+    const int rc = t & 31;
+    const uint32_t boxI = OPER_BYTES + (uint32_t)(t >> 5) * 1024, boxJ = boxI + 4096;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int mt, nt, ks;
+      decode_item(p, item, mt, nt, ks);
+      const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        mbar_wait(&rawfull[stage], phase);  // armed only after the MMA released this stage
+        float aJ[FB];
+#pragma unroll
+        for (int jl = 0; jl < FB; ++jl)
+          aJ[jl] = *reinterpret_cast<const float*>(st + boxJ + jl * 128 + ((((rc >> 2) ^ jl) << 4) | ((rc & 3) << 2)));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int il = 4 * h + c;
+          const float ai = *reinterpret_cast<const float*>(st + boxI + il * 128 + ((((rc >> 2) ^ il) << 4) | ((rc & 3) << 2)));
+          uint4 hi, lo;
+          split_pair(ai * aJ[0], ai * aJ[1], hi.x, lo.x);
+          split_pair(ai * aJ[2], ai * aJ[3], hi.y, lo.y);
+          split_pair(ai * aJ[4], ai * aJ[5], hi.z, lo.z);
+          split_pair(ai * aJ[6], ai * aJ[7], hi.w, lo.w);
+          const uint32_t off = sw128_offset(t, il);
           *reinterpret_cast<uint4*>(st + off) = hi;
           *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off) = lo;
         }
@@ -1007,6 +1073,38 @@ __global__ void __launch_bounds__(256) pack_Wt_kernel(int M, int L, int Lp, cons
   }
 }
 
+// Wg[p, (b, il, jl)] = c_b Omega[p, i, j]: the same packed symmetric features, gene-major / feature-contiguous (the
+// K-major B operand of the forward feature GEMM).  One CTA per gene; for a fixed block row I the blocks (I, I..nb-1)
+// are contiguous in the feature order, one thread per (J, il) writes the eight jl of its chunk as one 16-byte store.
+__global__ void __launch_bounds__(256) pack_Wg_kernel(int M, long NF, const float* __restrict__ Omega,
+                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int nb = feat_nb(M);
+  const int p = blockIdx.x;
+  const float* Om = Omega + (long)p * M * M;
+  uint4* oh = reinterpret_cast<uint4*>(hi + (long)p * NF);
+  uint4* ol = reinterpret_cast<uint4*>(lo + (long)p * NF);
+  long chunk0 = 0;  // 16-byte chunk index of block (I, I)
+  for (int I = 0; I < nb; ++I) {
+    const int nch = (nb - I) * FB;  // chunks of this block row: (J - I) * 8 + il
+    for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
+      const int J = I + ch / FB, il = ch % FB;
+      const int i = I * FB + il, j0 = J * FB;
+      const float c = (I == J) ? 1.f : 2.f;
+      float v[FB];
+#pragma unroll
+      for (int jl = 0; jl < FB; ++jl) v[jl] = (i < M && j0 + jl < M) ? c * Om[(long)i * M + j0 + jl] : 0.f;
+      uint4 h, l;
+      split_pair(v[0], v[1], h.x, l.x);
+      split_pair(v[2], v[3], h.y, l.y);
+      split_pair(v[4], v[5], h.z, l.z);
+      split_pair(v[6], v[7], h.w, l.w);
+      oh[chunk0 + ch] = h;
+      ol[chunk0 + ch] = l;
+    }
+    chunk0 += nch;
+  }
+}
+
 // row-major split: out[r, p] = G[r, p], pitch Lp
 __global__ void pack_G_kernel(long R, int L, int Lp, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
                               __nv_bfloat16* __restrict__ lo) {
@@ -1159,13 +1257,14 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 }
 
 int sm_count() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
+  static int n[GPSA_MAX_DEVICES] = {};
+  const int dev = gpsa_dev();
+  if (n[dev] == 0) {
+    int v = 148;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
+    n[dev] = v;
+  }
+  return n[dev];
 }
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1180,6 +1279,15 @@ FwdLayout fwd_layout(int M, long R, int L) {
   f.at = al256((size_t)R * f.Kp * 2);
   f.lt = al256((size_t)L * f.Mp * f.Kp * 2);
   f.total = 2 * f.at + 2 * f.lt;
+  return f;
+}
+struct FeatFwdLayout { long NF; size_t wg, apad, total; };
+FeatFwdLayout featfwd_layout(int M, long R, int L) {
+  FeatFwdLayout f;
+  f.NF = feat_nblk(M) * FBK;
+  f.wg = al256((size_t)L * f.NF * 2);
+  f.apad = (R % 4 == 0) ? 0 : al256((size_t)M * rup(R, 4) * 4);  // TMA needs a 16-byte row pitch: padded copy of A
+  f.total = 2 * f.wg + f.apad;
   return f;
 }
 struct AlphaLayout { int Lp; long NF; size_t g, w, total; };
@@ -1205,12 +1313,13 @@ OmegaLayout omega_layout(int M, long R, int L) {
 template <int MODE>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                 const GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[GPSA_MAX_DEVICES] = {};
+  const int dev = gpsa_dev();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE)) !=
         cudaSuccess)
       return GPSA_ERR_CUDA;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int n_items = p.n_mt * p.n_nt * p.n_split * (p.batch > 0 ? p.batch : 1);
   const int grid = n_items < sm_count() ? n_items : sm_count();
@@ -1240,7 +1349,8 @@ extern "C" size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch);
 extern "C" size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L) {
   if (M <= 0 || R <= 0 || L <= 0) return 0;
   size_t m = fwd_layout(M, R, L).total;
-  const size_t c[] = {alpha_layout(M, R, L).total, omega_layout(M, R, L).total, gpsa_gemm_tc_ws_bytes(R, L, M, 1),
+  const size_t c[] = {featfwd_layout(M, R, L).total, alpha_layout(M, R, L).total, omega_layout(M, R, L).total,
+                      gpsa_gemm_tc_ws_bytes(R, L, M, 1),
                       gpsa_gemm_tc_ws_bytes(M, L, (int)(R > 2000000000L ? 2000000000L : R), 1), gpsa_gemm_tc_ws_bytes(R, M, L, 1),
                       gpsa_gemm_tc_ws_bytes(M, M, M, L)};
   for (size_t v : c) m = v > m ? v : m;
@@ -1418,10 +1528,12 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   }
   FwdParams p = {};
   p.Mp = f.Mp; p.nkb = f.nkb; p.L = L; p.R = R; p.q2 = q2;
+#ifdef GPSA_DEBUG  // timing experiments only (skip the epilogue / the factor loads): never in the shipped library
   {
     static const int dbg = [] { const char* e = getenv("GPSA_TC_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
   }
+#endif
   p.n_rt = gpsa_cdiv(R, TM);
   // split the gene range when there are too few row tiles to fill the machine
   p.gsplit = 1;
@@ -1447,7 +1559,8 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
     p.ring_bytes = p.nslot * p.slot_bytes;
   }
   const int smem_bytes = fixed + p.ring_bytes;
-  static int attr_bytes = 0;
+  static int attr_bytes_dev[GPSA_MAX_DEVICES] = {};
+  int& attr_bytes = attr_bytes_dev[gpsa_dev()];
   if (smem_bytes > attr_bytes) {
     if (cudaFuncSetAttribute(tc_qf_fwd_kernel<1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
         cudaFuncSetAttribute(tc_qf_fwd_kernel<2, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
@@ -1469,7 +1582,8 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
     FwdParams q = p;
     q.ring_bytes = 2 * (1024 * (f.nkb - 1) * f.nkb + f.Mp * FROW);  // two genes of this CTA's half blocks
     const int smem_pair = fixed + 256 + q.ring_bytes;                 // + room for the 32 ring barriers
-    static bool pair_attr = false;
+    static bool pair_attr_dev[GPSA_MAX_DEVICES] = {};
+    bool& pair_attr = pair_attr_dev[gpsa_dev()];
     if (!pair_attr) {
       if (cudaFuncSetAttribute(tc_qf_fwd_pair_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair) != cudaSuccess)
         return GPSA_ERR_CUDA;
@@ -1559,6 +1673,47 @@ extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const 
   return GPSA_OK;
 }
 
+// fp32 TMA map of A [M, R] (box 32 r x 8 rows, 128-byte swizzle) for the generator modes; a 16-byte row pitch is
+// required, so an R that is not a multiple of 4 goes through a padded copy in `pad` (apad bytes)
+static int make_raw_map(CUtensorMap* tm, int M, long R, const float* A, void* pad, cudaStream_t st) {
+  const float* Asrc = A;
+  long pitch = R;
+  if (R % 4 != 0) {
+    pitch = rup(R, 4);
+    float* Ap = reinterpret_cast<float*>(pad);
+    if (cudaMemcpy2DAsync(Ap, pitch * 4, A, R * 4, R * 4, M, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return GPSA_ERR_CUDA;
+    Asrc = Ap;
+  }
+  const uint64_t dims[2] = {(uint64_t)R, (uint64_t)M}, str[1] = {(uint64_t)pitch * 4};
+  const uint32_t box[2] = {32, 8};
+  return make_tmap(tm, Asrc, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
+// Forward quadratic form in its implicit-feature form (MODE_FWD above): q2 [R, L] = Phi(A) W(Omega).
+extern "C" int gpsa_quadform_fwd_feat_tc(int M, long R, int L, const float* A, const float* Omega, float* q2, void* ws,
+                                         size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
+  if (!gpsa_tc_supported(M)) return GPSA_ERR_UNSUPPORTED;
+  const FeatFwdLayout f = featfwd_layout(M, R, L);
+  if (ws_bytes < f.total) return GPSA_ERR_ARG;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  __nv_bfloat16 *wg_hi = (__nv_bfloat16*)w, *wg_lo = (__nv_bfloat16*)(w + f.wg);
+  pack_Wg_kernel<<<L, 256, 0, st>>>(M, f.NF, Omega, wg_hi, wg_lo);
+  GPSA_LAUNCH_CHECK();
+  CUtensorMap tb_hi, tb_lo, ta_raw;
+  if (make_tmap_2d(&tb_hi, wg_hi, f.NF, L, f.NF, TN) || make_tmap_2d(&tb_lo, wg_lo, f.NF, L, f.NF, TN)) return GPSA_ERR_CUDA;
+  if (make_raw_map(&ta_raw, M, R, A, w + 2 * f.wg, st)) return GPSA_ERR_CUDA;
+  GemmParams p = {};
+  p.n_mt = gpsa_cdiv(R, TM);
+  p.n_nt = gpsa_cdiv(L, TN);
+  p.group_m = p.n_mt;  // all row tiles of one 256-gene panel run together: the packed W panel (NF x 256 x 4 B) is shared through L2
+  p.kblocks = (int)feat_nblk(M);
+  set_split(p, 1);     // the K loop walks the feature blocks from (0, 0): no split
+  p.Mrows = R; p.Ncols = L; p.C = q2; p.ldc = L; p.alpha = 1.f;
+  p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
+  return launch_gemm<MODE_FWD>(ta_raw, ta_raw, tb_hi, tb_lo, p, st);
+}
+
 extern "C" int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float* G, const float* Omega,
                                           float* Abar, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
@@ -1610,20 +1765,7 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
   }
   CUtensorMap tb_hi, tb_lo, ta_raw;
   if (make_tmap_2d(&tb_hi, gt_hi, R, L, o.Rp, TN) || make_tmap_2d(&tb_lo, gt_lo, R, L, o.Rp, TN)) return GPSA_ERR_CUDA;
-  {
-    const float* Asrc = A;
-    long pitch = R;
-    if (o.apad) {
-      pitch = rup(R, 4);
-      float* Ap = reinterpret_cast<float*>(w + 2 * o.gt);
-      if (cudaMemcpy2DAsync(Ap, pitch * 4, A, R * 4, R * 4, M, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return GPSA_ERR_CUDA;
-      Asrc = Ap;
-    }
-    const uint64_t dims[2] = {(uint64_t)R, (uint64_t)M}, str[1] = {(uint64_t)pitch * 4};
-    const uint32_t box[2] = {32, 8};
-    if (make_tmap(&ta_raw, Asrc, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return GPSA_ERR_CUDA;
-  }
+  if (make_raw_map(&ta_raw, M, R, A, w + 2 * o.gt, st)) return GPSA_ERR_CUDA;
   const long NF = feat_nblk(M) * FBK;
   GemmParams p = {};
   p.n_mt = gpsa_cdiv(NF, TM);

@@ -117,6 +117,7 @@ SIGNATURES = {
     "gpsa_tc_supported": [I],
     "gpsa_quadform_tc_ws_bytes": [I, LNG, I],
     "gpsa_quadform_fwd_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
+    "gpsa_quadform_fwd_feat_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
     "gpsa_quadform_bwd_alpha_tc": [I, LNG, I, P, P, P, P, P, C.c_size_t, P],
     "gpsa_quadform_bwd_omega_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
     "gpsa_tc_gemm_test": [I, I, I, P, P, P, I, P, C.c_size_t, P],
@@ -143,8 +144,37 @@ def check(rc, what):
         raise GPSALibraryError(f"{what} failed: {_ERR.get(rc, rc)}")
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device).  The autograd Functions in
+    _ops.py run under torch.cuda.device(<their tensors' device>), so the two agree."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device_of(argpos=0):
+    """Decorator for autograd.Function.forward/backward: run the body with the CUDA device of the first tensor
+    argument current, so that allocations, the stream and the library's per-device state all refer to the device
+    the data lives on (a model on cuda:1 in a process whose current device is cuda:0)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args):
+            dev = None
+            for a in args[argpos:]:
+                if torch.is_tensor(a) and a.is_cuda:
+                    dev = a.device
+                    break
+            if dev is None:
+                for t in getattr(args[0], "saved_tensors", ()) if argpos else ():
+                    if torch.is_tensor(t) and t.is_cuda:
+                        dev = t.device
+                        break
+            if dev is None:
+                return fn(*args)
+            with torch.cuda.device(dev):
+                return fn(*args)
+        return wrapped
+    return deco
 
 
 def ptr(t, dtype=torch.float32):

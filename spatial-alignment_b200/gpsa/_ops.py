@@ -6,22 +6,24 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import DataBwdArgs, DataFwdArgs, WarpBwdArgs, WarpFwdArgs, check, lib, ptr, stream
+from ._lib import DataBwdArgs, DataFwdArgs, WarpBwdArgs, WarpFwdArgs, check, lib, on_device_of, ptr, stream
 
 f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
 KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12, "matern32": _lib.KIND_MATERN32}
 
-# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16, "auto" = tcgen05 whenever the shape can
-# fill 128-row MMA tiles (the SIMT engine stays for the launch-bound toy configurations)
+# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16 with the ||a^T L||^2 forward, 2 = tcgen05 split-bf16
+# with the implicit-feature forward (all three products on the same generator GEMM core); "auto" = engine 2 whenever
+# the shape can fill 128-row MMA tiles (the SIMT engine stays for the launch-bound toy configurations)
 ENGINE = {"value": "auto"}
+TC_ENGINES = (1, 2)
 
 
 def pick_engine(M, R, L):
     e = ENGINE["value"]
     if e == "auto":
-        return 1 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
-    if e == 1 and not lib().gpsa_tc_supported(int(M)):
+        return 2 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
+    if e in TC_ENGINES and not lib().gpsa_tc_supported(int(M)):
         raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} yet (16 <= M <= 512)")
     return int(e)
 
@@ -65,6 +67,7 @@ class KernelMatrix(torch.autograd.Function):
     """K[m, r] = k(x1[m], x2[r]) for x1 [M,D], x2 [R,D]; differentiable in all four tensors."""
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, kind, x1, x2, log_ls, log_var):
         x1, x2 = _c(x1.detach()), _c(x2.detach())
         log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
@@ -80,6 +83,7 @@ class KernelMatrix(torch.autograd.Function):
         return K
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, Kbar):
         x1, x2, log_ls, log_var = ctx.saved_tensors
         M, D = x1.shape
@@ -107,7 +111,10 @@ def kernel_matrix(kind_name, x1, x2, log_ls, log_var):
         raise NotImplementedError("x1 must be [n1, D] or share x2's batch dimensions")
     batch = x2.shape[:-2]
     n2, D = x2.shape[-2:]
-    K = KernelMatrix.apply(kind, x1, x2.reshape(-1, D), log_ls.reshape(-1)[:1], log_var.reshape(-1)[:1])
+    if log_ls.numel() != 1 or log_var.numel() != 1:
+        raise ValueError("gpsa_b200's fused covariance functions take ONE lengthscale and ONE output variance "
+                         f"(got {log_ls.numel()} and {log_var.numel()} elements); per-dimension lengthscales are not supported")
+    K = KernelMatrix.apply(kind, x1, x2.reshape(-1, D), log_ls.reshape(1), log_var.reshape(1))
     if len(batch) == 0:
         return K
     n1 = x1.shape[0]
@@ -118,6 +125,11 @@ def kernel_matrix(kind_name, x1, x2, log_ls, log_var):
 def omega_prepare(Osq):
     """Omega = Osq Osq^T + 1e-5 I (fp32 copy), its Cholesky factor (fp32 copy and the fp64 original),
     fp64 half log-dets, info flags."""
+    with torch.cuda.device(Osq.device):
+        return _omega_prepare(Osq)
+
+
+def _omega_prepare(Osq):
     B, M, _ = Osq.shape
     Omega, Ltril = _new(Osq, B, M, M), _new(Osq, B, M, M)
     L64 = _new(Osq, B, M, M, dtype=f64)
@@ -126,6 +138,24 @@ def omega_prepare(Osq):
     check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(L64, f64), ptr(hld, f64),
                                    ptr(info, i32), stream()), "omega_prepare")
     return Omega, Ltril, L64, hld, info
+
+
+class OmegaFromSqt(torch.autograd.Function):
+    """Omega = Osq Osq^T + 1e-5 I as a differentiable op (reference gpsa/models/vgpsa.py:206-210 is plain autograd)."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, Osq):
+        Osq = _c(Osq.detach())
+        ctx.save_for_backward(Osq)
+        return _omega_prepare(Osq)[0]
+
+    @staticmethod
+    @on_device_of(1)
+    def backward(ctx, Obar):
+        (Osq,) = ctx.saved_tensors
+        sym = _c(0.5 * (Obar + Obar.transpose(-1, -2)))  # omega_grad expects a symmetric Omega-bar
+        return omega_grad(Osq, None, sym, None)
 
 
 def omega_grad(Osq, L64, Obar, coef, tc=False):
@@ -153,6 +183,7 @@ class WarpLayer(torch.autograd.Function):
     """
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, meta, Xtilde, delta_G, Osq_G, log_ls, log_var, *xe):
         Xtilde, delta_G, Osq_G = _c(Xtilde.detach()), _c(delta_G.detach()), _c(Osq_G.detach())
         log_ls, log_var = _c(log_ls.detach()), _c(log_var.detach())
@@ -196,6 +227,9 @@ class WarpLayer(torch.autograd.Function):
                     side[k % len(side)].wait_stream(cur)
                     st = C.c_void_p(side[k % len(side)].cuda_stream)
                 check(lib().gpsa_warp_view_fwd(C.byref(a), st), "warp_view_fwd")
+            # `var` is written on the side stream and used nowhere else: it has to outlive the join below, or its block
+            # returns to the current stream's allocator pool while this view's chain is still running
+            keep.append(var)
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
         if overlap:
@@ -210,6 +244,7 @@ class WarpLayer(torch.autograd.Function):
         return (kl.to(f32).reshape(()), Lk_all, Ltril_G, info_all, *outs)
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, kl_bar, _1, _2, _3, *gouts):
         meta = ctx.meta
         Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, L64_G, *saved = ctx.saved_tensors
@@ -288,6 +323,7 @@ class DataLayer(torch.autograd.Function):
     """
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps):
         Gtilde, delta_F, Osq_F = _c(Gtilde.detach()), _c(delta_F.detach()), _c(Osq_F.detach())
         log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
@@ -305,7 +341,7 @@ class DataLayer(torch.autograd.Function):
         A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, R)
         engine = pick_engine(M, R, L)
         W = _new(G, _lib.feat_count(M), L) if engine == 0 else _new(G, 1)
-        tc_ws = _lib.tc_workspace(M, R, L, G) if engine == 1 else None
+        tc_ws = _lib.tc_workspace(M, R, L, G) if engine in TC_ENGINES else None
         KD = _new(G, M, L, dtype=f64)
         Fo, var = _new(G, S, N, L), _new(G, R, L)
         kl = _zeros(G, 1, dtype=f64)
@@ -328,6 +364,7 @@ class DataLayer(torch.autograd.Function):
         return Fo, kl.to(f32).reshape(()), Lk, Ltril, info_all
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, F_bar, kl_bar, _1, _2, _3):
         meta = ctx.meta
         (Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
@@ -347,7 +384,7 @@ class DataLayer(torch.autograd.Function):
         Abar, Cm = _new(dev, M, R), _new(dev, M, R)
         engine = ctx.engine
         H = _new(dev, _lib.feat_count(M), L)
-        tc_ws = _lib.tc_workspace(M, R, L, dev) if engine == 1 else None
+        tc_ws = _lib.tc_workspace(M, R, L, dev) if engine in TC_ENGINES else None
         ws64 = _new(dev, 3 * M * M, dtype=f64)
         a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
                         log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G), eps=ptr(eps),
@@ -361,7 +398,7 @@ class DataLayer(torch.autograd.Function):
         check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
         del tc_ws
-        Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine == 1))
+        Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
         hyp = acc_hyp.to(f32)
         return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar, None
 
@@ -372,6 +409,7 @@ class GaussianLL(torch.autograd.Function):
     (reference gpsa/models/vgpsa.py:217, :532-538).  F [S,N,P], Y [N,P], log_noise: 1 element."""
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, F, Y, log_noise):
         F, Y, log_noise = _c(F.detach()), _c(Y.detach()), _c(log_noise.detach().reshape(1))
         S, N, P = F.shape
@@ -383,6 +421,7 @@ class GaussianLL(torch.autograd.Function):
         return acc.to(f32).reshape(())
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, ll_bar):
         F, Y, log_noise = ctx.saved_tensors
         S, N, P = F.shape

@@ -30,9 +30,14 @@ class GraphedIteration:
                 self._iteration()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+
+        n0 = _lib.lib().gpsa_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._iteration()
+        # kernels of THIS library inside one replay (its launchers ran exactly once, during capture)
+        self.launches = int(_lib.lib().gpsa_launch_count() - n0)
 
     def _iteration(self):
         out = self.model.forward(self.X, view_idx=self.view_idx, Ns=self.Ns, S=self.S)

@@ -98,7 +98,9 @@ class VariationalGPSA(GPSA):
             all_X = torch.cat([data_dict[mod]["spatial_coords"] for mod in self.modality_names])
             km = KMeans(n_clusters=self.m_G)
             km.fit(all_X.detach().cpu().numpy())
-            self.Gtilde = nn.Parameter(torch.tensor(km.cluster_centers_))
+            # float32 even when the coordinates came in as float64 (the library is fp32 at this boundary; the
+            # reference's Gtilde would follow the KMeans dtype and then fail in its own float32 matmuls)
+            self.Gtilde = nn.Parameter(torch.tensor(km.cluster_centers_).float())
         elif grid_init:  # reference :94-121 (2-D only)
             if D == 2:
                 coords = data_dict[self.modality_names[0]]["spatial_coords"].cpu().numpy()
@@ -182,9 +184,15 @@ class VariationalGPSA(GPSA):
         return val
 
     def get_Omega_from_Omega_sqt(self, Omega_sqt):
-        """Omega_sqt Omega_sqt^T + 1e-5 I (reference :206-210)."""
-        Omega = _ops.omega_prepare(Omega_sqt.detach().contiguous())[0]
-        return Omega
+        """Omega_sqt Omega_sqt^T + 1e-5 I (reference :206-210), differentiable in Omega_sqt like the reference's."""
+        return _ops.OmegaFromSqt.apply(Omega_sqt)
+
+    def compute_mean_and_var(self, *args, **kwargs):
+        """Reference :174-204 is an internal helper of forward(); here its arithmetic lives inside the fused warp /
+        data layer kernels (gpsa_warp_view_fwd, gpsa_data_layer_fwd) and is not exposed as a separate torch op."""
+        raise NotImplementedError(
+            "compute_mean_and_var is fused into gpsa_b200's warp / data layer kernels; call forward() "
+            "(see INTEGRATION.md, 'API differences')")
 
     # ----------------------------------------------------------------------------------------------
     def forward(self, X_spatial, view_idx, Ns, S=1, prediction_mode=False, G_test=None, _eps=None):
@@ -323,11 +331,40 @@ class VariationalGPSA(GPSA):
         self._info = infos
         if _DEBUG_CHECKS:
             self.check_factorisations()
+        else:
+            self._deferred_factorisation_check(infos)
 
         if G_test is not None:
             return (G_means, G_samples, self.F_latent_samples, self.F_observed_samples,
                     self.F_latent_samples_test, self.F_observed_samples_test)
         return G_means, G_samples, self.F_latent_samples, self.F_observed_samples
+
+    def _deferred_factorisation_check(self, infos):
+        """Sync-free stand-in for the exception torch.cholesky raises in the reference: the `info` flags of this
+        forward are copied to pinned host memory asynchronously; a later forward (normally the next one) finds them
+        arrived and raises.  Independently of this, a failed factorisation makes the loss NaN on the device
+        (csrc/chol.cu), so it can never pass silently."""
+        pend = getattr(self, "_pending_info", None)
+        if pend is not None and pend[1].query():
+            self._pending_info = None
+            if bool(pend[0].any()):
+                bad = int(torch.nonzero(pend[0])[0, 0])
+                raise RuntimeError(f"VariationalGPSA.forward: a Cholesky factorisation of an earlier forward met a "
+                                   f"non-positive pivot (flag {bad}): a K_uu or Omega matrix is not positive-definite")
+            pend = None
+        if pend is not None or torch.cuda.is_current_stream_capturing():
+            return
+        n = sum(int(i.numel()) for i in infos)
+        host = getattr(self, "_info_host", None)
+        if host is None or host.numel() < n:
+            host = self._info_host = torch.zeros(max(n, 64), dtype=torch.int32).pin_memory()
+        o = 0
+        for i in infos:
+            host[o:o + i.numel()].copy_(i, non_blocking=True)
+            o += int(i.numel())
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending_info = (host[:n], ev)
 
     def check_factorisations(self):
         """Raise if any Cholesky of the last forward met a non-positive pivot (torch.cholesky raises
@@ -368,6 +405,3 @@ class VariationalGPSA(GPSA):
             LL = LL + _ops.GaussianLL.apply(F, Y.to(F.device, torch.float32), self.noise_variance[idx:idx + 1])
         return -LL + self._kl
 
-
-if __name__ == "__main__":
-    pass

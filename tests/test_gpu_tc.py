@@ -62,7 +62,7 @@ def _problem(M, R, Lg, seed):
 
 
 @pytest.mark.parametrize("M,R,Lg", [(64, 128, 1), (64, 1000, 5), (200, 700, 37), (256, 2049, 9), (50, 300, 3),
-                                    (100, 4096, 300), (512, 700, 5), (320, 300, 3)])
+                                    (100, 4096, 300), (512, 700, 5), (320, 300, 3), (37, 130, 2), (200, 1027, 260)])
 def test_quadform_tc_fwd_bwd(L, M, R, Lg):
     from gpsa import _ops
 
@@ -82,6 +82,13 @@ def test_quadform_tc_fwd_bwd(L, M, R, Lg):
                                     stream()) == 0
     torch.cuda.synchronize()
     assert relerr(q2.cpu(), q2r.detach()) < TOL
+
+    # the implicit-feature forward (engine 2: what the data layer runs) on the same operands
+    q2f = torch.full((R, Lg), float("nan"), device="cuda")
+    assert lib.gpsa_quadform_fwd_feat_tc(M, R, Lg, a.data_ptr(), Omega.data_ptr(), q2f.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), stream()) == 0
+    torch.cuda.synchronize()
+    assert relerr(q2f.cpu(), q2r.detach()) < TOL
 
     nf = L.feat_count(M)
     H = torch.full((nf, Lg), float("nan"), device="cuda")
@@ -108,8 +115,8 @@ def test_tc_unsupported_M(L):
 
 @pytest.mark.parametrize("kind", ["rbf", "matern12"])
 def test_data_layer_engines_agree(L, kind):
-    """The whole data layer (forward samples, KL, every gradient) with the tcgen05 engine against the fp32
-    SIMT engine on the same inputs."""
+    """The whole data layer (forward samples, KL, every gradient) with both tcgen05 engines (1: ||a^T L||^2 forward,
+    2: implicit-feature forward) against the fp32 SIMT engine on the same inputs."""
     from gpsa import _ops
 
     g = torch.Generator().manual_seed(11)
@@ -122,7 +129,7 @@ def test_data_layer_engines_agree(L, kind):
     Fbar = torch.randn(S, N, Lg, generator=g)
     ls, var = torch.tensor([0.3]), torch.tensor([0.1])
     outs = {}
-    for engine in (0, 1):
+    for engine in (0, 1, 2):
         _ops.ENGINE["value"] = engine
         try:
             leaves = [t.clone().cuda().requires_grad_() for t in (Gt, ls, var, dlt, Osq, G)]
@@ -133,8 +140,9 @@ def test_data_layer_engines_agree(L, kind):
         finally:
             _ops.ENGINE["value"] = "auto"
     names = ["F", "kl", "Gtilde", "log_ls", "log_var", "delta", "Omega_sqt", "G"]
-    for name, x0, x1 in zip(names, outs[0], outs[1]):
-        assert relerr(x1, x0) < 2e-4, name
+    for engine in (1, 2):
+        for name, x0, x1 in zip(names, outs[0], outs[engine]):
+            assert relerr(x1, x0) < 2e-4, (engine, name)
 
 
 @pytest.mark.parametrize("Mr,Nc,K,batch,arm,brm,out_mode,split", [
@@ -235,12 +243,11 @@ assert err < 1e-4, err
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
-@pytest.mark.skipif(os.environ.get("GPSA_TEST_FULLSIZE", "0") != "1",
-                    reason="opt-in (GPSA_TEST_FULLSIZE=1): C3-sized quadratic form, ~6 GB of device memory")
-def test_quadform_fwd_full_size_properties(L):
-    """BASELINE.json's C3 shape (M = 200, R = S*N = 128 000, L = 2000) through size-independent properties:
-    (1) a random sample of entries against float64, (2) partition invariance -- a sub-block of rows x genes computed
-    on its own equals the same entries of the full result, (3) q2 >= 0 (it is a squared norm)."""
+def test_quadform_full_size_properties(L):
+    """BASELINE.json's C3 shape (M = 200, R = S*N = 128 000, L = 2000) -- the shape bench.py times -- for all three
+    products, through size-independent properties: (1) a random sample of entries against float64, (2) partition
+    invariance -- a sub-block of rows x genes computed on its own equals the same entries of the full result,
+    (3) q2 >= 0 up to round-off (it is a squared norm).  ~7 GB of device memory, a few seconds."""
     from gpsa import _ops
 
     M, R, Lg = 200, 128000, 2000
@@ -248,28 +255,67 @@ def test_quadform_fwd_full_size_properties(L):
     A = torch.randn(M, R, device="cuda", generator=g) * 0.3
     Osq = torch.randn(Lg, M, M, device="cuda", generator=g) * 0.1
     Omega, Ltril, L64, hld, info = _ops.omega_prepare(Osq)
-    del L64
+    del L64, Osq
     lib = L.lib()
     ws = ws_for(L, M, R, Lg)
-    q2 = torch.full((R, Lg), float("nan"), device="cuda")
-    assert lib.gpsa_quadform_fwd_tc(M, R, Lg, A.data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    stream()) == 0
-    torch.cuda.synchronize()
-    assert bool(torch.isfinite(q2).all()) and float(q2.min()) >= 0.0
-    # (1) sampled parity
     rows = torch.randint(0, R, (96,), device="cuda", generator=g)
     genes = torch.randint(0, Lg, (48,), device="cuda", generator=g)
     ref = torch.einsum("mr,pmk,kr->rp", A[:, rows].double(), Omega[genes].double(), A[:, rows].double())
-    got = q2[rows][:, genes].double()
-    assert float((got - ref).abs().max() / ref.abs().max()) < TOL
-    # (2) partition invariance: rows [4096, 5120) x genes [100, 164) on their own
     r0, r1, p0, p1 = 4096, 5120, 100, 164
     As = A[:, r0:r1].contiguous()
-    Ls = Ltril[p0:p1].contiguous()
     ws2 = ws_for(L, M, r1 - r0, p1 - p0)
-    q2s = torch.full((r1 - r0, p1 - p0), float("nan"), device="cuda")
-    assert lib.gpsa_quadform_fwd_tc(M, r1 - r0, p1 - p0, As.data_ptr(), Ls.data_ptr(), q2s.data_ptr(), ws2.data_ptr(),
-                                    ws2.numel(), stream()) == 0
+    for form in ("feat", "chol"):
+        q2 = torch.full((R, Lg), float("nan"), device="cuda")
+        q2s = torch.full((r1 - r0, p1 - p0), float("nan"), device="cuda")
+        if form == "feat":
+            Os = Omega[p0:p1].contiguous()
+            assert lib.gpsa_quadform_fwd_feat_tc(M, R, Lg, A.data_ptr(), Omega.data_ptr(), q2.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), stream()) == 0
+            assert lib.gpsa_quadform_fwd_feat_tc(M, r1 - r0, p1 - p0, As.data_ptr(), Os.data_ptr(), q2s.data_ptr(),
+                                                 ws2.data_ptr(), ws2.numel(), stream()) == 0
+        else:
+            Ls = Ltril[p0:p1].contiguous()
+            assert lib.gpsa_quadform_fwd_tc(M, R, Lg, A.data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), stream()) == 0
+            assert lib.gpsa_quadform_fwd_tc(M, r1 - r0, p1 - p0, As.data_ptr(), Ls.data_ptr(), q2s.data_ptr(),
+                                            ws2.data_ptr(), ws2.numel(), stream()) == 0
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(q2).all()), form
+        assert float(q2.min()) >= -1e-5 * float(q2.max()), form                         # (3)
+        got = q2[rows][:, genes].double()
+        assert float((got - ref).abs().max() / ref.abs().max()) < TOL, form            # (1)
+        full = q2[r0:r1, p0:p1]
+        assert float((q2s - full).abs().max() / full.abs().max()) < 1e-5, form         # (2)
+        del q2, q2s
+    del Ltril
+
+    # ---- backward products at the same shape: G = dLoss/dq2 [R, L]
+    G = torch.randn(R, Lg, device="cuda", generator=g)
+    # A-bar[:, r] = 2 sum_p G[r,p] Omega_p a_r, checked on sampled rows (all 2000 genes contribute to each)
+    Abar = torch.zeros(M, R, device="cuda")
+    assert lib.gpsa_quadform_bwd_alpha_tc(M, R, Lg, A.data_ptr(), G.data_ptr(), Omega.data_ptr(), Abar.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), stream()) == 0
     torch.cuda.synchronize()
-    full = q2[r0:r1, p0:p1]
-    assert float((q2s - full).abs().max() / full.abs().max()) < 1e-5
+    rs = rows[:24]
+    refA = torch.zeros(M, rs.numel(), dtype=f64, device="cuda")
+    for c0 in range(0, Lg, 250):  # chunked over genes: keeps the float64 temporaries small
+        Oc = Omega[c0:c0 + 250].double()
+        refA += 2.0 * torch.einsum("rp,pmk,kr->mr", G[rs, c0:c0 + 250].double(), Oc, A[:, rs].double())
+    gotA = Abar[:, rs].double()
+    assert float((gotA - refA).abs().max() / refA.abs().max()) < TOL
+    assert bool(torch.isfinite(Abar).all())
+    del Abar
+    # Omega-bar_p = sum_r G[r,p] a_r a_r^T, checked on sampled genes (all 128 000 rows contribute to each)
+    nf = L.feat_count(M)
+    H = torch.full((nf, Lg), float("nan"), device="cuda")
+    Obar = torch.empty(Lg, M, M, device="cuda")
+    assert lib.gpsa_quadform_bwd_omega_tc(M, R, Lg, A.data_ptr(), G.data_ptr(), H.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          stream()) == 0
+    assert lib.gpsa_feat_unpack(M, Lg, H.data_ptr(), None, 0.0, None, Obar.data_ptr(), stream()) == 0
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(Obar).all())
+    Ad = A.double()
+    for pgene in genes[:6].tolist():
+        refO = (Ad * G[:, pgene].double()[None, :]) @ Ad.T
+        gotO = Obar[pgene].double()
+        assert float((gotO - refO).abs().max() / refO.abs().max()) < TOL, pgene
