@@ -197,8 +197,11 @@ typedef struct {
 int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t stream);
 
 /* ---- data layer, one modality -------------------------------------------------------------------
- * Replaces gpsa/models/vgpsa.py:390-426 (K_uu, K_uf for all S samples, compute_mean_and_var in its
- * 3-D branch :192-204, F = mu + sqrt(var) eps) and the modality's KL term (:520-530). */
+ * Replaces gpsa/models/vgpsa.py:390-421 (K_uu, K_uf for all S samples, compute_mean_and_var in its 3-D branch
+ * :192-204 up to the predictive moments) and the modality's KL term (:520-530).  Outputs the predictive mean,
+ * the quadratic form q2[r,p] = a_r^T Omega_p a_r and kq[r] = sigma^2 - a_r^T K a_r; the marginal variance is
+ * var = kq + q2 + 2e-5 and the reparameterised sample F = mean + sqrt(var) eps (:423-426) is the SAMPLING STAGE below,
+ * either materialised (gpsa_sample_fwd / _bwd) or fused with the likelihood (gpsa_sample_ll_fused). */
 typedef struct {
   int kind, D, M, L;
   long R;                 /* S*N rows */
@@ -208,23 +211,22 @@ typedef struct {
   const float* Omega;     /* [L,M,M] from gpsa_omega_prepare */
   const double* hld_Omega; /* [L] */
   const float* G;         /* G_samples flattened [R,D] */
-  const float* eps;       /* [R,L] */
   float *Lk, *Kinv;       /* out [M,M] each (fp32) */
   double* Kinv64;         /* out [M,M] fp64 (saved) */
   double* hld_K;
   int* info;
   float *A, *B;           /* out [M,R] (saved) */
   float* kq;              /* out [R]  K_ff - a^T K a */
-  float* W;               /* out [gpsa_feat_count(M), L] (saved) */
+  float* W;               /* out [gpsa_feat_count(M), L] (saved; engine 0 only) */
   double* KD;             /* out fp64 [M,L] K^-1 delta (saved) */
-  float* F;               /* out [R,L] latent samples */
-  float* var;             /* out [R,L] marginal variances (saved) */
+  float* mean;            /* out [R,L] predictive mean */
+  float* q2;              /* out [R,L] quadratic form */
   double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
   double* ws64;           /* 2*M*M doubles */
   int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 with the ||a^T L||^2 forward,
                              2 = tcgen05 split-bf16 with the implicit-feature forward (default for large shapes) */
   const float* Ltril;     /* [L,M,M] chol(Omega) from gpsa_omega_prepare (engine 1 only) */
-  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  void* tc_ws;            /* engines 1, 2: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;
 } gpsa_data_fwd_args;
 int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
@@ -232,13 +234,14 @@ int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
 typedef struct {
   int kind, D, M, L;
   long R;
-  const float *Gt, *log_ls, *log_var, *dlt, *Omega, *G, *eps;
+  const float *Gt, *log_ls, *log_var, *dlt, *Omega, *G;
   const float* Kinv;
   const double* Kinv64;
   const float *A, *B, *W;
   const double* KD;
-  const float* var;
-  const float* F_bar;     /* [R,L] */
+  const float* mean_bar;  /* [R,L] upstream gradient of the predictive mean */
+  const float* q2_bar;    /* [R,L] upstream gradient of the quadratic form (= of the marginal variance) */
+  const float* kq_bar;    /* [R]   upstream gradient of kq (= sum_p q2_bar[r,p] when var = kq + q2 + const) */
   const float* kl_bar;    /* device scalar */
   float* G_bar;           /* out [R,D] */
   double* acc_Gt;         /* fp64 [M,D] ADDED to */
@@ -246,16 +249,39 @@ typedef struct {
   float* dlt_bar;         /* out [M,L] */
   float* Obar;            /* out [L,M,M]  (feed to gpsa_omega_grad) */
   /* scratch */
-  float* Gm;              /* [R,L] dLoss/dvar */
   float* q1bar;           /* [R] */
   float *Abar, *C;        /* [M,R] each */
   float* H;               /* [gpsa_feat_count(M), L] */
   double* ws64;           /* 3*M*M doubles */
   int engine;
-  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  void* tc_ws;            /* engines 1, 2: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;
 } gpsa_data_bwd_args;
 int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t stream);
+
+/* ---- sampling stage ---------------------------------------------------------------------------------
+ * Materialised form (reference gpsa/models/vgpsa.py:197-204, :423-426): in: F = mean, var = q2;
+ * out: var = kq[r] + q2 + 2e-5 (jitter added twice like the reference), F = mean + sqrt(var) eps.  R = S*N rows. */
+int gpsa_sample_fwd(long R, int L, const float* kq, const float* eps, float* F, float* var, cudaStream_t stream);
+/* q2_bar[r,p] = F_bar eps / (2 sqrt(var)),  kq_bar[r] = sum_p q2_bar[r,p]   (mean_bar = F_bar) */
+int gpsa_sample_bwd(long R, int L, const float* F_bar, const float* eps, const float* var, float* q2_bar, float* kq_bar,
+                    cudaStream_t stream);
+/* Counter-based standard-normal noise: out[(s*N + n)*L + p] = the draw of (sample samp_off + s, spot n, gene gene_off + p)
+ * under the 64-bit seed *key (device memory) -- Philox4x32-10 + Box-Muller, identical to what gpsa_sample_ll_fused
+ * draws in-kernel, independent of how genes / samples are sharded.  Stands in for torch.randn at vgpsa.py:423. */
+int gpsa_philox_normal(long N, int S, int L, const long long* key, int gene_off, int samp_off, float* out,
+                       cudaStream_t stream);
+/* Fused form: sampling + Gaussian negative log-likelihood + its gradients in one pass (vgpsa.py:423-426, :532-538).
+ * in:  mean_U = predictive mean [S*N, L], q2_Gu = quadratic form [S*N, L], kq [S*N], Y [N, L], log_noise (device scalar);
+ *      noise: eps [S*N, L] if non-NULL, else drawn in-kernel from *key (see gpsa_philox_normal).
+ * out (IN PLACE): mean_U = d(-LL)/dF = -(Y - F)/(sigma^2 S),  q2_Gu = d(-LL)/dvar = U eps / (2 sqrt(var)),
+ *      kqb [S*N] = sum_p q2_Gu,  nll_acc += -LL (fp64),  noise_acc += d(-LL)/dlog_noise (fp64).
+ * sigma = exp(*log_noise) + 1e-5 is used as the Normal SCALE exactly as the reference does (:217, :534). */
+int gpsa_sample_ll_fused(long N, int S, int L, const float* kq, const float* Y, const float* log_noise, const float* eps,
+                         const long long* key, int gene_off, int samp_off, float* mean_U, float* q2_Gu, float* kqb,
+                         double* nll_acc, double* noise_acc, cudaStream_t stream);
+/* x[0..n) *= *scale unless *scale == 1 (device scalar): the upstream gradient of loss.backward() is exactly 1. */
+int gpsa_scale_if_not_one(long n, const float* scale, float* x, cudaStream_t stream);
 
 /* ---- Gaussian log-likelihood ----------------------------------------------------------------------
  * ll_acc += sum_{r,p} log N(Y[n,p]; F[r,p], sigma) / S,  sigma = exp(*log_noise) + 1e-5 used as the
@@ -266,6 +292,44 @@ int gpsa_gaussian_ll_fwd(long N, int P, int S, const float* F, const float* Y, c
 /* F_bar[r,p] = ll_bar * dLL/dF,  acc_noise += ll_bar * dLL/dlog_noise (fp64).  ll_bar: device scalar. */
 int gpsa_gaussian_ll_bwd(long N, int P, int S, const float* F, const float* Y, const float* log_noise,
                          const float* ll_bar, float* F_bar, double* acc_noise, cudaStream_t stream);
+
+/* ---- linear model of coregionalisation (LMC), reference gpsa/models/vgpsa.py:167-172, :428-432 ---------------
+ * Materialised: F_obs [R,P] = F_lat [R,L] W [L,P] and its backward (W_bar overwritten). */
+int gpsa_lmc_fwd(long R, int L, int P, const float* F_lat, const float* W, float* F_obs, cudaStream_t stream);
+int gpsa_lmc_bwd(long R, int L, int P, const float* F_lat, const float* W, const float* F_obs_bar, float* F_lat_bar,
+                 float* W_bar, cudaStream_t stream);
+/* Fused with the Gaussian negative log-likelihood of Y [N,P] (no [S,N,P] tensor is formed), for L <= gpsa_lmc_max_latent():
+ * nll_acc += -LL, noise_acc += d(-LL)/dlog_noise, F_lat_bar [S*N,L] = d(-LL)/dF_lat, W_bar [L,P] = d(-LL)/dW (both overwritten). */
+int gpsa_lmc_max_latent(void);
+int gpsa_lmc_ll_fused(long N, int S, int L, int P, const float* F_lat, const float* W, const float* Y,
+                      const float* log_noise, float* F_lat_bar, float* W_bar, double* nll_acc, double* noise_acc,
+                      cudaStream_t stream);
+
+/* ---- optimiser step and initialisation -------------------------------------------
+ * Adam exactly as torch.optim.Adam(lr, betas, eps) with weight_decay = 0, amsgrad = False, maximize = False -- the
+ * optimiser every reference training loop uses (examples/grid_example.py:59,76) -- as one launch over up to
+ * GPSA_ADAM_MAX_TENSORS parameter tensors.  `step` is a DEVICE array of `count` floats holding the number of steps each
+ * tensor has taken so far; the call increments them first (so the launch pair can be captured in a CUDA graph).
+ * g[k] == NULL skips tensor k (its step count does not advance, as in torch). */
+#define GPSA_ADAM_MAX_TENSORS 24
+typedef struct {
+  int count;
+  float* p[GPSA_ADAM_MAX_TENSORS];        /* parameters, updated in place */
+  const float* g[GPSA_ADAM_MAX_TENSORS];  /* gradients */
+  float* m[GPSA_ADAM_MAX_TENSORS];        /* exp_avg */
+  float* v[GPSA_ADAM_MAX_TENSORS];        /* exp_avg_sq */
+  long n[GPSA_ADAM_MAX_TENSORS];          /* elements */
+  float lr, beta1, beta2, eps;
+  float* step;
+} gpsa_adam_args;
+int gpsa_adam_step(const gpsa_adam_args* a, cudaStream_t stream);
+
+/* Lloyd's k-means on spot coordinates X [N,D] (D <= 3): `iters` assign + update rounds starting from `centres` [K,D]
+ * (in/out), then one more assignment; assign [N] int, sums: scratch K*(D+1) doubles, inertia: 1 double (sum of squared
+ * distances to the final centres).  An empty cluster keeps its centre.  Replaces sklearn.cluster.KMeans in the
+ * data_init branch of gpsa/models/vgpsa.py:61-92 for large inputs. */
+int gpsa_kmeans_lloyd(long N, int D, int K, const float* X, float* centres, int iters, int* assign, double* sums,
+                      double* inertia, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -350,14 +350,12 @@ __global__ void __launch_bounds__(256) sample_fwd_rows4_kernel(long R, int L4, c
   }
 }
 
-// one warp per row r: Gm[r,p] = Fbar*eps/(2 sqrt(var)); q1bar[r] = -sum_p Gm; acc_hyp[1] += sigma2 * sum Gm
+// one warp per row r: Gm[r,p] = Fbar*eps/(2 sqrt(var)) = dLoss/dq2; kq_bar[r] = sum_p Gm[r,p] = dLoss/dkq
 __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const float* __restrict__ Fbar,
                                                          const float* __restrict__ eps, const float* __restrict__ var,
-                                                         const float* __restrict__ log_var, float* __restrict__ Gm,
-                                                         float* __restrict__ q1bar, double* acc_hyp) {
+                                                         float* __restrict__ Gm, float* __restrict__ kq_bar) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-  double tot = 0.0;
   for (long r = (long)blockIdx.x * (blockDim.x >> 5) + warp; r < R; r += nwarps) {
     float s = 0.f;
     for (int p = lane; p < L; p += 32) {
@@ -367,26 +365,16 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(long R, int L, const fl
       s += g;
     }
     s = warp_sum(s);
-    if (lane == 0) { q1bar[r] = -s; tot += (double)s; }
-  }
-  __shared__ double red[8];
-  if (lane == 0) red[warp] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    atomicAdd(&acc_hyp[1], t * exp((double)log_var[0]));
+    if (lane == 0) kq_bar[r] = s;
   }
 }
 
 // 128-bit variant of sample_bwd_kernel (L % 4 == 0)
 __global__ void __launch_bounds__(256) sample_bwd4_kernel(long R, int L4, const float4* __restrict__ Fbar,
                                                           const float4* __restrict__ eps, const float4* __restrict__ var,
-                                                          const float* __restrict__ log_var, float4* __restrict__ Gm,
-                                                          float* __restrict__ q1bar, double* acc_hyp) {
+                                                          float4* __restrict__ Gm, float* __restrict__ kq_bar) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-  double tot = 0.0;
   for (long r = (long)blockIdx.x * (blockDim.x >> 5) + warp; r < R; r += nwarps) {
     float s = 0.f;
     for (int p = lane; p < L4; p += 32) {
@@ -399,16 +387,23 @@ __global__ void __launch_bounds__(256) sample_bwd4_kernel(long R, int L4, const 
       s += (g.x + g.y) + (g.z + g.w);
     }
     s = warp_sum(s);
-    if (lane == 0) { q1bar[r] = -s; tot += (double)s; }
+    if (lane == 0) kq_bar[r] = s;
   }
-  __shared__ double red[8];
-  if (lane == 0) red[warp] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    atomicAdd(&acc_hyp[1], t * exp((double)log_var[0]));
+}
+
+// kq[r] = sigma2 - q1[r]:  q1bar[r] = -kq_bar[r];  acc_hyp[1] += sigma2 * sum_r kq_bar[r]
+__global__ void __launch_bounds__(256) kq_bwd_kernel(long R, const float* __restrict__ kq_bar,
+                                                     const float* __restrict__ log_var, float* __restrict__ q1bar,
+                                                     double* acc_hyp) {
+  double tot = 0.0;
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
+    const float k = kq_bar[r];
+    q1bar[r] = -k;
+    tot += (double)k;
   }
+  __shared__ double red[32];
+  tot = block_sum<double>(tot, red);
+  if (threadIdx.x == 0) atomicAdd(&acc_hyp[1], tot * exp((double)log_var[0]));
 }
 
 // KL(q(u_p) || p(u)) summed over genes: one CTA per gene.
@@ -1016,34 +1011,25 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   GPSA_LAUNCH_CHECK();
   // predictive mean  F[r,p] = sum_m A[m,r] delta[m,p]   (vgpsa.py:182-184 with mu_x = mu_z = 0)
   if (a->engine >= 1) {
-    TRY(gpsa_gemm_tc(R, L, M, 1, a->A, R, 0, 0, a->dlt, L, 0, 0, a->F, L, 0, 1.f, 0, 1, a->tc_ws, a->tc_ws_bytes, st));
+    TRY(gpsa_gemm_tc(R, L, M, 1, a->A, R, 0, 0, a->dlt, L, 0, 0, a->mean, L, 0, 1.f, 0, 1, a->tc_ws, a->tc_ws_bytes, st));
   } else {
-    TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->F, L, 0,
+    TRY((gemm_strided<float, float, float, float>(st, (int)R, L, M, 1.0, a->A, 1, R, 0, a->dlt, L, 1, 0, 0.0, a->mean, L, 0,
                                                   1)));
   }
   if (a->engine == 0) {
     TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
     gpsa_prof_begin(0, st);
-    TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->var, st));
+    TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->q2, st));
     gpsa_prof_end(0, st);
   } else if (a->engine == 1) {
     gpsa_prof_begin(0, st);
-    TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->var, a->tc_ws, a->tc_ws_bytes, st));
+    TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->q2, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   } else {
     gpsa_prof_begin(0, st);
-    TRY(gpsa_quadform_fwd_feat_tc(M, R, L, a->A, a->Omega, a->var, a->tc_ws, a->tc_ws_bytes, st));
+    TRY(gpsa_quadform_fwd_feat_tc(M, R, L, a->A, a->Omega, a->q2, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   }
-  const bool al16 = ((reinterpret_cast<uintptr_t>(a->eps) | reinterpret_cast<uintptr_t>(a->F) |
-                      reinterpret_cast<uintptr_t>(a->var)) & 15) == 0;
-  if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
-    sample_fwd_rows4_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(
-        R, L / 4, a->kq, reinterpret_cast<const float4*>(a->eps), reinterpret_cast<float4*>(a->F),
-        reinterpret_cast<float4*>(a->var));
-  else if (L >= 128) sample_fwd_rows_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(R, L, a->kq, a->eps, a->F, a->var);
-  else sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, a->kq, a->eps, a->F, a->var);
-  GPSA_LAUNCH_CHECK();
   // KD = K^-1 delta (fp64)
   TRY((gemm_nn<double, double, float, double>(st, M, L, M, 1.0, a->Kinv64, M, a->dlt, L, 0.0, a->KD, L)));
   if (a->kl_acc) {
@@ -1062,47 +1048,36 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   double* Kbar = a->ws64;
   double* P = a->ws64 + MM;
   double* T1 = a->ws64 + 2 * MM;
-  {
-    long b = (R + 7) / 8;
-    if (b > 148 * 8) b = 148 * 8;
-    const bool al16 = ((reinterpret_cast<uintptr_t>(a->F_bar) | reinterpret_cast<uintptr_t>(a->eps) |
-                        reinterpret_cast<uintptr_t>(a->var) | reinterpret_cast<uintptr_t>(a->Gm)) & 15) == 0;
-    if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
-      sample_bwd4_kernel<<<(int)b, 256, 0, st>>>(R, L / 4, reinterpret_cast<const float4*>(a->F_bar),
-                                                 reinterpret_cast<const float4*>(a->eps),
-                                                 reinterpret_cast<const float4*>(a->var), a->log_var,
-                                                 reinterpret_cast<float4*>(a->Gm), a->q1bar, a->acc_hyp);
-    else
-      sample_bwd_kernel<<<(int)b, 256, 0, st>>>(R, L, a->F_bar, a->eps, a->var, a->log_var, a->Gm, a->q1bar, a->acc_hyp);
-    GPSA_LAUNCH_CHECK();
-  }
+  // var = kq + q2 + 2 off with kq = sigma2 - q1:  q1bar = -kq_bar, d/dlog_var += sigma2 sum kq_bar
+  kq_bwd_kernel<<<grid_for(R, 256, 148 * 4), 256, 0, st>>>(R, a->kq_bar, a->log_var, a->q1bar, a->acc_hyp);
+  GPSA_LAUNCH_CHECK();
   // delta-bar = A Fbar (+ kl_bar K^-1 delta)
   if (a->engine >= 1 && R <= 2000000000L) {
-    TRY(gpsa_gemm_tc(M, L, (int)R, 1, a->A, R, 0, 1, a->F_bar, L, 0, 0, a->dlt_bar, L, 0, 1.f, 0, 0, a->tc_ws,
+    TRY(gpsa_gemm_tc(M, L, (int)R, 1, a->A, R, 0, 1, a->mean_bar, L, 0, 0, a->dlt_bar, L, 0, 1.f, 0, 0, a->tc_ws,
                      a->tc_ws_bytes, st));
   } else {
     const int split = pick_split(M, L, R, 1, tile_of<float>(M, L));
     if (cudaMemsetAsync(a->dlt_bar, 0, sizeof(float) * (size_t)M * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
-    TRY((gemm_strided<float, float, float, float>(st, M, L, R, 1.0, a->A, R, 1, 0, a->F_bar, L, 1, 0, 1.0, a->dlt_bar,
+    TRY((gemm_strided<float, float, float, float>(st, M, L, R, 1.0, a->A, R, 1, 0, a->mean_bar, L, 1, 0, 1.0, a->dlt_bar,
                                                   L, 0, 1, split)));
   }
   if (a->kl_bar) TRY((axpy_dev<double, float>(st, (long)M * L, 1.0, a->kl_bar, a->KD, a->dlt_bar)));
   // Abar = q1bar o B + delta Fbar^T + 2 (sum_p Gm Omega_p) a
   TRY(colscale<float>(st, M, R, a->q1bar, a->B, a->Abar, 0));
   if (a->engine >= 1) {
-    TRY(gpsa_gemm_tc(R, M, L, 1, a->F_bar, L, 0, 1, a->dlt, L, 0, 1, a->Abar, R, 0, 1.f, 1, 1, a->tc_ws, a->tc_ws_bytes, st));
+    TRY(gpsa_gemm_tc(R, M, L, 1, a->mean_bar, L, 0, 1, a->dlt, L, 0, 1, a->Abar, R, 0, 1.f, 1, 1, a->tc_ws, a->tc_ws_bytes, st));
   } else {
-    TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->F_bar, 1, L, 0, 1.0, a->Abar,
+    TRY((gemm_strided<float, float, float, float>(st, M, (int)R, L, 1.0, a->dlt, L, 1, 0, a->mean_bar, 1, L, 0, 1.0, a->Abar,
                                                   R, 0, 1)));
   }
   gpsa_prof_begin(1, st);
-  if (a->engine == 0) TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->Gm, a->W, a->Abar, st));
-  else TRY(gpsa_quadform_bwd_alpha_tc(M, R, L, a->A, a->Gm, a->Omega, a->Abar, a->tc_ws, a->tc_ws_bytes, st));
+  if (a->engine == 0) TRY(gpsa_quadform_bwd_alpha_f32(M, R, L, a->A, a->q2_bar, a->W, a->Abar, st));
+  else TRY(gpsa_quadform_bwd_alpha_tc(M, R, L, a->A, a->q2_bar, a->Omega, a->Abar, a->tc_ws, a->tc_ws_bytes, st));
   gpsa_prof_end(1, st);
   // Omega-bar = sum_r Gm a a^T (+ 0.5 kl_bar K^-1)
   gpsa_prof_begin(2, st);
-  if (a->engine == 0) TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->Gm, a->H, st));
-  else TRY(gpsa_quadform_bwd_omega_tc(M, R, L, a->A, a->Gm, a->H, a->tc_ws, a->tc_ws_bytes, st));
+  if (a->engine == 0) TRY(gpsa_quadform_bwd_omega_f32(M, R, L, a->A, a->q2_bar, a->H, st));
+  else TRY(gpsa_quadform_bwd_omega_tc(M, R, L, a->A, a->q2_bar, a->H, a->tc_ws, a->tc_ws_bytes, st));
   gpsa_prof_end(2, st);
   TRY(gpsa_feat_unpack(M, L, a->H, a->kl_bar ? a->Kinv : nullptr, 0.5f, a->kl_bar, a->Obar, st));
   // C = K^-1 Abar ; Kbar = -K^-1 (Abar A^T) ; Bbar = C + q1bar o A
@@ -1121,6 +1096,54 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->C, a->acc_Gt, a->G_bar, nullptr,
                              a->acc_hyp, st));
   return prior_bwd(a->kind, D, M, a->Gt, a->log_ls, a->log_var, Kbar, a->acc_Gt, a->acc_hyp, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear model of coregionalisation, materialised form: F_obs [R,P] = F_lat [R,L] W [L,P]  (vgpsa.py:428-432)
+extern "C" int gpsa_lmc_fwd(long R, int L, int P, const float* F_lat, const float* W, float* F_obs, cudaStream_t st) {
+  if (R <= 0 || L <= 0 || P <= 0) return GPSA_OK;
+  if (R > 2000000000L) return GPSA_ERR_UNSUPPORTED;
+  return gemm_strided<float, float, float, float>(st, (int)R, P, L, 1.0, F_lat, L, 1, 0, W, P, 1, 0, 0.0, F_obs, P, 0, 1);
+}
+// F_lat_bar = F_obs_bar W^T,  W_bar = F_lat^T F_obs_bar (split over the R rows)
+extern "C" int gpsa_lmc_bwd(long R, int L, int P, const float* F_lat, const float* W, const float* F_obs_bar,
+                            float* F_lat_bar, float* W_bar, cudaStream_t st) {
+  if (R <= 0 || L <= 0 || P <= 0) return GPSA_OK;
+  if (R > 2000000000L) return GPSA_ERR_UNSUPPORTED;
+  TRY((gemm_strided<float, float, float, float>(st, (int)R, L, P, 1.0, F_obs_bar, P, 1, 0, W, 1, P, 0, 0.0, F_lat_bar, L, 0, 1)));
+  const int split = pick_split(L, P, R, 1, tile_of<float>(L, P));
+  if (cudaMemsetAsync(W_bar, 0, sizeof(float) * (size_t)L * P, st) != cudaSuccess) return GPSA_ERR_CUDA;
+  return gemm_strided<float, float, float, float>(st, L, P, R, 1.0, F_lat, 1, L, 0, F_obs_bar, P, 1, 0, 1.0, W_bar, P, 0, 1, split);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling stage between the data layer and the likelihood (materialised form; the fused form is sample.cu)
+extern "C" int gpsa_sample_fwd(long R, int L, const float* kq, const float* eps, float* F, float* var, cudaStream_t st) {
+  if (R <= 0 || L <= 0) return GPSA_OK;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(var)) & 15) == 0;
+  if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
+    sample_fwd_rows4_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(
+        R, L / 4, kq, reinterpret_cast<const float4*>(eps), reinterpret_cast<float4*>(F), reinterpret_cast<float4*>(var));
+  else if (L >= 128) sample_fwd_rows_kernel<<<(int)(R < 148 * 16 ? R : 148 * 16), 256, 0, st>>>(R, L, kq, eps, F, var);
+  else sample_fwd_kernel<<<grid_for(R * L), 256, 0, st>>>(R * L, L, kq, eps, F, var);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
+}
+
+extern "C" int gpsa_sample_bwd(long R, int L, const float* F_bar, const float* eps, const float* var, float* q2_bar,
+                               float* kq_bar, cudaStream_t st) {
+  if (R <= 0 || L <= 0) return GPSA_OK;
+  long b = (R + 7) / 8;
+  if (b > 148 * 8) b = 148 * 8;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(F_bar) | reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(var) |
+                      reinterpret_cast<uintptr_t>(q2_bar)) & 15) == 0;
+  if (L >= 128 && (L & 3) == 0 && al16 && !g_no_vec4)
+    sample_bwd4_kernel<<<(int)b, 256, 0, st>>>(R, L / 4, reinterpret_cast<const float4*>(F_bar), reinterpret_cast<const float4*>(eps),
+                                               reinterpret_cast<const float4*>(var), reinterpret_cast<float4*>(q2_bar), kq_bar);
+  else
+    sample_bwd_kernel<<<(int)b, 256, 0, st>>>(R, L, F_bar, eps, var, q2_bar, kq_bar);
+  GPSA_LAUNCH_CHECK();
+  return GPSA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

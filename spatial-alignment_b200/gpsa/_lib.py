@@ -68,9 +68,9 @@ class WarpBwdArgs(C.Structure):
 class DataFwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
-        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P), ("eps", P),
+        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P),
         ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
-        ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("F", P), ("var", P),
+        ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("mean", P), ("q2", P),
         ("kl_acc", P), ("ws64", P), ("engine", I), ("Ltril", P), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
     ]
 
@@ -78,12 +78,23 @@ class DataFwdArgs(C.Structure):
 class DataBwdArgs(C.Structure):
     _fields_ = [
         ("kind", I), ("D", I), ("M", I), ("L", I), ("R", LNG),
-        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("G", P), ("eps", P),
-        ("Kinv", P), ("Kinv64", P), ("A", P), ("B", P), ("W", P), ("KD", P), ("var", P),
-        ("F_bar", P), ("kl_bar", P),
+        ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("G", P),
+        ("Kinv", P), ("Kinv64", P), ("A", P), ("B", P), ("W", P), ("KD", P),
+        ("mean_bar", P), ("q2_bar", P), ("kq_bar", P), ("kl_bar", P),
         ("G_bar", P), ("acc_Gt", P), ("acc_hyp", P), ("dlt_bar", P), ("Obar", P),
-        ("Gm", P), ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("ws64", P),
+        ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("ws64", P),
         ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
+    ]
+
+
+ADAM_MAX_TENSORS = 24
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [
+        ("count", I), ("p", P * ADAM_MAX_TENSORS), ("g", P * ADAM_MAX_TENSORS), ("m", P * ADAM_MAX_TENSORS),
+        ("v", P * ADAM_MAX_TENSORS), ("n", LNG * ADAM_MAX_TENSORS), ("lr", F), ("beta1", F), ("beta2", F), ("eps", F),
+        ("step", P),
     ]
 
 
@@ -125,6 +136,17 @@ SIGNATURES = {
     "gpsa_warp_view_bwd": [C.POINTER(WarpBwdArgs), P],
     "gpsa_data_layer_fwd": [C.POINTER(DataFwdArgs), P],
     "gpsa_data_layer_bwd": [C.POINTER(DataBwdArgs), P],
+    "gpsa_sample_fwd": [LNG, I, P, P, P, P, P],
+    "gpsa_sample_bwd": [LNG, I, P, P, P, P, P, P],
+    "gpsa_philox_normal": [LNG, I, I, P, I, I, P, P],
+    "gpsa_sample_ll_fused": [LNG, I, I, P, P, P, P, P, I, I, P, P, P, P, P, P],
+    "gpsa_scale_if_not_one": [LNG, P, P, P],
+    "gpsa_lmc_fwd": [LNG, I, I, P, P, P, P],
+    "gpsa_lmc_bwd": [LNG, I, I, P, P, P, P, P, P],
+    "gpsa_lmc_max_latent": [],
+    "gpsa_lmc_ll_fused": [LNG, I, I, I, P, P, P, P, P, P, P, P, P],
+    "gpsa_adam_step": [C.POINTER(AdamArgs), P],
+    "gpsa_kmeans_lloyd": [LNG, I, I, P, P, I, P, P, P, P],
     "gpsa_gaussian_ll_fwd": [LNG, I, I, P, P, P, P, P],
     "gpsa_gaussian_ll_bwd": [LNG, I, I, P, P, P, P, P, P, P],
 }

@@ -315,83 +315,87 @@ class WarpLayer(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
-class DataLayer(torch.autograd.Function):
-    """One modality of the data GP (reference gpsa/models/vgpsa.py:390-426, KL :520-530).
+class DataLayerPre(torch.autograd.Function):
+    """One modality of the data GP up to its predictive moments (reference gpsa/models/vgpsa.py:390-421, KL :520-530).
 
-    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D], eps [S,N,L])
-      -> (F_latent [S,N,L], KL_F, Kuu_chol_F, Omega_tril_F, info)
+    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D])
+      -> (mean [S,N,L], q2 [S,N,L], kq [S,N], KL_F, Kuu_chol_F, Omega_tril_F, info)
+    with q2[s,n,p] = a^T Omega_p a (the hot contraction) and kq = sigma^2 - a^T K a; the marginal variance is
+    kq + q2 + 2e-5 and the sample F = mean + sqrt(var) eps is the sampling stage (SampleF / SampleNLL below).
+    meta = dict(kind=int, with_kl=bool[, omega=omega_prepare(Omega_sqt_F)])
     """
 
     @staticmethod
     @on_device_of(1)
-    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps):
+    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G):
         Gtilde, delta_F, Osq_F = _c(Gtilde.detach()), _c(delta_F.detach()), _c(Osq_F.detach())
         log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
-        G, eps = _c(G.detach()), _c(eps.detach())
+        G = _c(G.detach())
         M, D = Gtilde.shape
         L = delta_F.shape[1]
         S, N = G.shape[0], G.shape[1]
         R = S * N
         kind = meta["kind"]
         pre = meta.get("omega")
-        Omega, Ltril, L64, hld, info_O = pre if pre is not None else omega_prepare(Osq_F)
+        Omega, Ltril, L64, hld, info_O = pre if pre is not None else _omega_prepare(Osq_F)
         Lk, Kinv, Kinv64 = _new(G, M, M), _new(G, M, M), _new(G, M, M, dtype=f64)
         hldK = _zeros(G, 1, dtype=f64)
         info = _zeros(G, 1, dtype=i32)
-        A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, R)
+        A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, S, N)
         engine = pick_engine(M, R, L)
         W = _new(G, _lib.feat_count(M), L) if engine == 0 else _new(G, 1)
         tc_ws = _lib.tc_workspace(M, R, L, G) if engine in TC_ENGINES else None
         KD = _new(G, M, L, dtype=f64)
-        Fo, var = _new(G, S, N, L), _new(G, R, L)
+        mean, q2 = _new(G, S, N, L), _new(G, S, N, L)
         kl = _zeros(G, 1, dtype=f64)
         ws64 = _new(G, 2 * M * M, dtype=f64)
         a = DataFwdArgs(kind=kind, D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls), log_var=ptr(log_var),
-                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld, f64), G=ptr(G), eps=ptr(eps),
+                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld, f64), G=ptr(G),
                         Lk=ptr(Lk), Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), hld_K=ptr(hldK, f64),
-                        info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), F=ptr(Fo),
-                        var=ptr(var),
+                        info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), mean=ptr(mean),
+                        q2=ptr(q2),
                         kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
                         engine=engine, Ltril=ptr(Ltril), tc_ws=ptr(tc_ws, torch.uint8),
                         tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
         check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
         ctx.meta = meta
         ctx.engine = engine
-        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
-                              var)
+        ctx.dims = (S, N)
+        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64, Kinv, Kinv64, A, B, W, KD)
         info_all = torch.cat([info_O, info])
         ctx.mark_non_differentiable(Lk, Ltril, info_all)
-        return Fo, kl.to(f32).reshape(()), Lk, Ltril, info_all
+        return mean, q2, kq, kl.to(f32).reshape(()), Lk, Ltril, info_all
 
     @staticmethod
     @on_device_of(1)
-    def backward(ctx, F_bar, kl_bar, _1, _2, _3):
+    def backward(ctx, mean_bar, q2_bar, kq_bar, kl_bar, _1, _2, _3):
         meta = ctx.meta
-        (Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, Omega, L64, Kinv, Kinv64, A, B, W, KD,
-         var) = ctx.saved_tensors
+        Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64, Kinv, Kinv64, A, B, W, KD = ctx.saved_tensors
         M, D = Gtilde.shape
         L = delta_F.shape[1]
-        S, N = G.shape[0], G.shape[1]
+        S, N = ctx.dims
         R = S * N
         dev = G
         use_kl = meta["with_kl"] and kl_bar is not None
         klb = _c(kl_bar.to(f32).reshape(1)) if use_kl else None
-        F_bar = _c(F_bar) if F_bar is not None else _zeros(dev, S, N, L)
+        mean_bar = _c(mean_bar) if mean_bar is not None else _zeros(dev, S, N, L)
+        q2_bar = _c(q2_bar) if q2_bar is not None else _zeros(dev, S, N, L)
+        kq_bar = _c(kq_bar) if kq_bar is not None else _zeros(dev, S, N)
         G_bar = _new(dev, S, N, D)
         acc_Gt, acc_hyp = _zeros(dev, M, D, dtype=f64), _zeros(dev, 2, dtype=f64)
         dlt_bar, Obar = _new(dev, M, L), _new(dev, L, M, M)
-        Gm, q1bar = _new(dev, R, L), _new(dev, R)
+        q1bar = _new(dev, R)
         Abar, Cm = _new(dev, M, R), _new(dev, M, R)
         engine = ctx.engine
         H = _new(dev, _lib.feat_count(M), L)
         tc_ws = _lib.tc_workspace(M, R, L, dev) if engine in TC_ENGINES else None
         ws64 = _new(dev, 3 * M * M, dtype=f64)
         a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
-                        log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G), eps=ptr(eps),
+                        log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G),
                         Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), A=ptr(A), B=ptr(B), W=ptr(W), KD=ptr(KD, f64),
-                        var=ptr(var),
-                        F_bar=ptr(F_bar), kl_bar=ptr(klb), G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
-                        acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar), Gm=ptr(Gm),
+                        mean_bar=ptr(mean_bar), q2_bar=ptr(q2_bar), kq_bar=ptr(kq_bar), kl_bar=ptr(klb),
+                        G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
+                        acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar),
                         q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), ws64=ptr(ws64, f64),
                         engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
                         tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
@@ -400,7 +404,174 @@ class DataLayer(torch.autograd.Function):
         del tc_ws
         Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
         hyp = acc_hyp.to(f32)
-        return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar, None
+        return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar
+
+
+class SampleF(torch.autograd.Function):
+    """Materialised sampling stage: F = mean + sqrt(kq + q2 + 2e-5) eps  (reference gpsa/models/vgpsa.py:197-204, :423-426).
+
+    The kernel works IN PLACE on the buffers of `mean` and `q2` (outputs of DataLayerPre that nothing else reads): the
+    returned F aliases `mean`, and the marginal variance saved for the backward aliases `q2`."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, mean, q2, kq, eps):
+        S, N, L = mean.shape
+        F, var = mean.detach(), q2.detach()
+        if not (F.is_contiguous() and var.is_contiguous()):
+            raise _lib.GPSALibraryError("SampleF expects the contiguous outputs of DataLayerPre")
+        kq, eps = _c(kq.detach()), _c(eps.detach())
+        check(lib().gpsa_sample_fwd(S * N, L, ptr(kq), ptr(eps), ptr(F), ptr(var), stream()), "sample_fwd")
+        ctx.save_for_backward(eps, var)
+        return F
+
+    @staticmethod
+    @on_device_of(1)
+    def backward(ctx, F_bar):
+        eps, var = ctx.saved_tensors
+        S, N, L = var.shape
+        F_bar = _c(F_bar)
+        q2_bar, kq_bar = _new(var, S, N, L), _new(var, S, N)
+        check(lib().gpsa_sample_bwd(S * N, L, ptr(F_bar), ptr(eps), ptr(var), ptr(q2_bar), ptr(kq_bar), stream()),
+              "sample_bwd")
+        return F_bar, q2_bar, kq_bar, None
+
+
+def philox_normal(key, S, N, L, gene_off=0, samp_off=0):
+    """eps [S,N,L] of the counter-based generator the fused sampling stage draws from in-kernel (same numbers)."""
+    with torch.cuda.device(key.device):
+        out = torch.empty(S, N, L, dtype=f32, device=key.device)
+        check(lib().gpsa_philox_normal(N, S, L, ptr(key, torch.int64), int(gene_off), int(samp_off), ptr(out), stream()),
+              "philox_normal")
+    return out
+
+
+class SampleNLL(torch.autograd.Function):
+    """Fused sampling stage + Gaussian negative log-likelihood (reference gpsa/models/vgpsa.py:423-426, :532-538):
+        -sum log N(Y; mean + sqrt(kq + q2 + 2e-5) eps, sigma) / S
+    One pass over the two [S,N,L] buffers; eps comes from `eps` [S,N,L] if given, else from Philox keyed by
+    (key, sample, spot, global gene).  F, eps and var are never stored: the buffers of `mean` and `q2` are overwritten
+    IN PLACE with d(-LL)/dF and d(-LL)/dvar, which is all the backward needs.
+
+    forward(meta, mean, q2, kq, Y [N,L], log_noise, eps | None, key | None) -> -LL (0-dim)
+    meta = dict(gene_off=int, samp_off=int)
+    """
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, meta, mean, q2, kq, Y, log_noise, eps, key):
+        S, N, L = mean.shape
+        U, Gu = mean.detach(), q2.detach()
+        if not (U.is_contiguous() and Gu.is_contiguous()):
+            raise _lib.GPSALibraryError("SampleNLL expects the contiguous outputs of DataLayerPre")
+        Y, log_noise, kq = _c(Y.detach()), _c(log_noise.detach().reshape(1)), _c(kq.detach())
+        if Y.shape != (N, L):
+            raise ValueError(f"outputs have shape {tuple(Y.shape)}, F_samples imply {(N, L)}")
+        eps = _c(eps.detach()) if eps is not None else None
+        kqb = _new(U, S, N)
+        acc = _zeros(U, 2, dtype=f64)  # [-LL, d(-LL)/dlog_noise]
+        check(lib().gpsa_sample_ll_fused(N, S, L, ptr(kq), ptr(Y), ptr(log_noise), ptr(eps),
+                                         ptr(key, torch.int64) if key is not None else None,
+                                         int(meta.get("gene_off", 0)), int(meta.get("samp_off", 0)), ptr(U), ptr(Gu),
+                                         ptr(kqb), acc.data_ptr(), acc.data_ptr() + 8, stream()), "sample_ll_fused")
+        ctx.save_for_backward(U, Gu, kqb, acc)
+        ctx.used = False
+        return acc[0].to(f32)
+
+    @staticmethod
+    @on_device_of(1)
+    def backward(ctx, g):
+        if ctx.used:
+            raise RuntimeError("the fused sampling + likelihood stage overwrites its buffers in place: backward through "
+                               "it a second time needs a new forward (set model.fused_ll = False for retain_graph use)")
+        ctx.used = True
+        U, Gu, kqb, acc = ctx.saved_tensors
+        g = _c(g.to(f32).reshape(1))
+        st = stream()
+        # loss.backward() hands down exactly 1: the kernels then return after one load
+        for t in (U, Gu, kqb):
+            check(lib().gpsa_scale_if_not_one(t.numel(), ptr(g), ptr(t), st), "scale_if_not_one")
+        return None, U, Gu, kqb, None, (acc[1] * g).to(f32).reshape(1), None, None
+
+
+class LMCObserve(torch.autograd.Function):
+    """Linear model of coregionalisation, materialised: F_obs [S,N,P] = F_lat [S,N,L] @ W [L,P]
+    (reference gpsa/models/vgpsa.py:428-432), explicit forward and backward on the library's GEMM."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, F_lat, W):
+        F_lat, W = _c(F_lat.detach()), _c(W.detach())
+        S, N, L = F_lat.shape
+        P = W.shape[1]
+        if W.shape[0] != L:
+            raise ValueError(f"W has shape {tuple(W.shape)}, latent samples have {L} outputs")
+        out = _new(F_lat, S, N, P)
+        check(lib().gpsa_lmc_fwd(S * N, L, P, ptr(F_lat), ptr(W), ptr(out), stream()), "lmc_fwd")
+        ctx.save_for_backward(F_lat, W)
+        return out
+
+    @staticmethod
+    @on_device_of(1)
+    def backward(ctx, Fb):
+        F_lat, W = ctx.saved_tensors
+        S, N, L = F_lat.shape
+        P = W.shape[1]
+        Fb = _c(Fb)
+        Flb, Wb = _new(F_lat, S, N, L), _new(W, L, P)
+        check(lib().gpsa_lmc_bwd(S * N, L, P, ptr(F_lat), ptr(W), ptr(Fb), ptr(Flb), ptr(Wb), stream()), "lmc_bwd")
+        return Flb, Wb
+
+
+def lmc_fused_supported(L):
+    return int(L) <= int(lib().gpsa_lmc_max_latent())
+
+
+class LMCNLL(torch.autograd.Function):
+    """LMC fused with the Gaussian negative log-likelihood: -sum log N(Y; F_lat @ W, sigma) / S without forming the
+    [S,N,P] tensor (reference gpsa/models/vgpsa.py:428-432, :532-538).  forward(F_lat [S,N,L], W [L,P], Y [N,P], log_noise)."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, F_lat, W, Y, log_noise):
+        F_lat, W, Y = _c(F_lat.detach()), _c(W.detach()), _c(Y.detach())
+        log_noise = _c(log_noise.detach().reshape(1))
+        S, N, L = F_lat.shape
+        P = W.shape[1]
+        if Y.shape != (N, P) or W.shape[0] != L:
+            raise ValueError(f"outputs {tuple(Y.shape)} / loadings {tuple(W.shape)} do not match samples {(S, N, L)}")
+        Flb, Wb = _new(F_lat, S, N, L), _new(W, L, P)
+        acc = _zeros(F_lat, 2, dtype=f64)
+        check(lib().gpsa_lmc_ll_fused(N, S, L, P, ptr(F_lat), ptr(W), ptr(Y), ptr(log_noise), ptr(Flb), ptr(Wb),
+                                      acc.data_ptr(), acc.data_ptr() + 8, stream()), "lmc_ll_fused")
+        ctx.save_for_backward(Flb, Wb, acc)
+        ctx.used = False
+        return acc[0].to(f32)
+
+    @staticmethod
+    @on_device_of(1)
+    def backward(ctx, g):
+        if ctx.used:
+            raise RuntimeError("the fused LMC likelihood keeps its gradients in place: a second backward needs a new forward")
+        ctx.used = True
+        Flb, Wb, acc = ctx.saved_tensors
+        g = _c(g.to(f32).reshape(1))
+        for t in (Flb, Wb):
+            check(lib().gpsa_scale_if_not_one(t.numel(), ptr(g), ptr(t), stream()), "scale_if_not_one")
+        return Flb, Wb, None, (acc[1] * g).to(f32).reshape(1)
+
+
+class DataLayer:
+    """DataLayerPre followed by the materialised sampling stage: the reference's data layer as one callable.
+
+    apply(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D], eps [S,N,L])
+      -> (F_latent [S,N,L], KL_F, Kuu_chol_F, Omega_tril_F, info)
+    """
+
+    @staticmethod
+    def apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps):
+        mean, q2, kq, kl, Lk, Ltril, info = DataLayerPre.apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G)
+        return SampleF.apply(mean, q2, kq, eps), kl, Lk, Ltril, info
 
 
 # --------------------------------------------------------------------------------------------------

@@ -14,7 +14,12 @@ from sklearn.cluster import KMeans
 
 from .gpsa import GPSA
 from .. import _ops
-from ..util.util import matern12_kernel, matern32_kernel, rbf_kernel
+from ..lazy import LazySamples
+from ..util.util import kmeans_gpu, matern12_kernel, matern32_kernel, rbf_kernel
+
+# data_init=True: inputs with more spots than this are clustered on the GPU (gpsa.util.kmeans_gpu) instead of with the
+# host KMeans the reference calls; below it the reference's seeded behaviour is reproduced exactly
+KMEANS_HOST_MAX = 20000
 
 _DEBUG_CHECKS = os.environ.get("GPSA_B200_CHECK", "0") == "1"
 
@@ -82,7 +87,20 @@ class VariationalGPSA(GPSA):
         self.fixed_view_idx = fixed_view_idx
         V, D = self.n_views, self.n_spatial_dims
 
-        if data_init:  # reference :61-92
+        n_points = sum(int(data_dict[mod]["spatial_coords"].shape[0]) for mod in self.modality_names)
+        if data_init and n_points > KMEANS_HOST_MAX and torch.cuda.is_available():
+            # reference :61-92 with sklearn's host KMeans replaced by Lloyd's iterations on the GPU (gpsa.util.kmeans_gpu):
+            # at C4 / C5 sizes the host fit is seconds to minutes and dominates the time to the first iteration.
+            # Seeded by numpy's global generator, like the reference's KMeans (random_state=None).
+            Xtilde = torch.zeros([V, self.m_X_per_view, D])
+            for vv in range(V):
+                xs = [data_dict[mod]["spatial_coords"][self.view_idx[mod][vv], :] for mod in self.modality_names]
+                curr_X = torch.cat(xs, dim=0)
+                Xtilde[vv] = kmeans_gpu(curr_X, self.m_X_per_view, seed=int(np.random.randint(1 << 31)))[0].cpu()
+            self.Xtilde = nn.Parameter(Xtilde.clone())
+            all_X = torch.cat([data_dict[mod]["spatial_coords"] for mod in self.modality_names])
+            self.Gtilde = nn.Parameter(kmeans_gpu(all_X, self.m_G, seed=int(np.random.randint(1 << 31)))[0].cpu())
+        elif data_init:  # reference :61-92
             Xtilde = torch.zeros([V, self.m_X_per_view, D])
             for vv in range(V):
                 xs = [data_dict[mod]["spatial_coords"][self.view_idx[mod][vv], :] for mod in self.modality_names]
@@ -156,7 +174,25 @@ class VariationalGPSA(GPSA):
         self.register_buffer("_kl_mask", kl_mask, persistent=False)
         self._idx_cache = {}
         self._kl = None
-        self._kl_G_scale = 1.0  # 1/world under gene sharding (gpsa.parallel), so that local losses SUM to the ELBO
+        # weights of the loss terms under gpsa.parallel (all 1 on a single GPU), chosen so that the local losses of the
+        # ranks SUM to the negative ELBO: replicated terms carry 1/world, a rank's share of the samples carries S_loc/S
+        self._kl_G_scale = 1.0
+        self._kl_F_scale = {mod: 1.0 for mod in self.modality_names}
+        self._nll_scale = 1.0
+        self._sample_shard = None  # (rank, world): this rank evaluates its contiguous share of the S Monte-Carlo samples
+        # --- execution knobs of the B200 path (not part of the reference's constructor) ---
+        # rng_mode: where the data layer's noise eps_F [S,N,L] comes from when forward() is not handed explicit noise.
+        #   "philox" (default): drawn INSIDE the fused kernels from a counter-based generator keyed by
+        #       (seed, sample, spot, global gene); the 64-bit seed is itself drawn from torch's CUDA generator, so
+        #       torch.manual_seed governs it.  Nothing [S,N,L]-sized is materialised, and the draw does not depend on how
+        #       genes are sharded over ranks.
+        #   "torch": torch.randn(S, N, L) in the reference's draw order.
+        self.rng_mode = "philox"
+        # fused_ll: forward() returns lazy handles for F_samples, and loss_fn() on such a handle runs the fused
+        # sampling + likelihood kernel (gpsa/lazy.py).  False: forward() returns plain tensors like the reference.
+        self.fused_ll = True
+        self._gene_off = {mod: 0 for mod in self.modality_names}  # global index of this rank's first gene (gpsa.parallel)
+        self._gen = 0
 
     # ----------------------------------------------------------------------------------------------
     def _is_fixed(self, vv):
@@ -210,6 +246,15 @@ class VariationalGPSA(GPSA):
             raise RuntimeError("VariationalGPSA.forward needs the model on a CUDA device: gpsa_b200 has no CPU path")
         V, D, mods = self.n_views, self.n_spatial_dims, self.modality_names
         S = int(S)
+        S_total, s0 = S, 0
+        if self._sample_shard is not None:  # gpsa.parallel.SampleSharding: this rank's samples are [s0, s0 + S) of S_total
+            from ..parallel import gene_range as _split
+
+            s0, s1 = _split(S_total, self._sample_shard[1], self._sample_shard[0])
+            S = s1 - s0
+            if S == 0:
+                raise ValueError(f"sample sharding needs S >= world size (S={S_total}, world={self._sample_shard[1]})")
+            self._nll_scale = S / S_total
 
         self.noise_variance_pos = torch.exp(self.noise_variance) + self.diagonal_offset  # reference :217
         self.mu_z_G = self.Xtilde * self._mu_z_scale  # identity mean; x100 on fixed views (:219-235)
@@ -231,12 +276,14 @@ class VariationalGPSA(GPSA):
         eps_G = {}
         for vv in free:
             if _eps is not None:
-                eps_G[vv] = _eps["G"][vv].to(dev, torch.float32)
+                eps_G[vv] = _eps["G"][vv].to(dev, torch.float32)[s0:s0 + S]
             else:
-                e = torch.empty(S, X_views[vv].shape[0], D, device=dev)
-                for ss in range(S):
+                # all S_total draws are made (reference order, :346-348) and this rank keeps its samples, so the
+                # Monte-Carlo draw does not depend on the world size
+                e = torch.empty(S_total, X_views[vv].shape[0], D, device=dev)
+                for ss in range(S_total):
                     e[ss].normal_()
-                eps_G[vv] = e
+                eps_G[vv] = e[s0:s0 + S] if S != S_total else e
 
         if not self._kl_mask_ready(free):
             self._set_kl_mask(free)
@@ -290,6 +337,7 @@ class VariationalGPSA(GPSA):
                 G_means[mod], G_samples[mod] = gm, gs
 
         # ---- data layer per modality (reference :390-435)
+        self._gen += 1
         self.curr_Omega_tril_F = {}
         self.F_latent_samples, self.F_observed_samples = {}, {}
         if G_test is not None:
@@ -302,18 +350,48 @@ class VariationalGPSA(GPSA):
             N = int(Ns[mod])
             Osq = self.Omega_sqt_F_dict[mod]
             pre = pre_F[mod] if mod in pre_F else _ops.omega_prepare(Osq.detach().contiguous())
-            eps_F = _eps["F"][mod].to(dev, torch.float32) if _eps is not None else torch.randn(S, N, L, device=dev)
-            F_lat, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayer.apply(
+            # noise of the sampling stage (reference :423): explicit, torch's stream, or a key for the in-kernel generator
+            eps_F, key = None, None
+            if _eps is not None:
+                eps_F = _eps["F"][mod].to(dev, torch.float32)[s0:s0 + S]
+            elif self.rng_mode == "torch":
+                eps_F = torch.randn(S_total, N, L, device=dev)[s0:s0 + S]
+            elif self.rng_mode == "philox":
+                key = torch.randint(-(1 << 62), 1 << 62, (1,), dtype=torch.int64, device=dev)
+            else:
+                raise ValueError(f"rng_mode must be 'philox' or 'torch', got {self.rng_mode!r}")
+            mean, q2, kq, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayerPre.apply(
                 {"kind": kind_d, "with_kl": True, "omega": pre},
                 self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod], Osq,
-                G_samples[mod], eps_F,
+                G_samples[mod],
             )
-            kl = kl + kl_F
+            kl = kl + (kl_F if self._kl_F_scale[mod] == 1.0 else kl_F * self._kl_F_scale[mod])
             infos.append(info_F)
             self.curr_Omega_tril_F[mod] = Ltril_F
             W = self.W_dict[mod] if self.n_latent_gps[mod] is not None else None
+            goff = int(self._gene_off.get(mod, 0))
+
+            def _sample(mean=mean, q2=q2, kq=kq, eps_F=eps_F, key=key, S=S, N=N, L=L, goff=goff, s0=s0):
+                e = eps_F if eps_F is not None else _ops.philox_normal(key, S, N, L, gene_off=goff, samp_off=s0)
+                return _ops.SampleF.apply(mean, q2, kq, e)
+
+            F_lat = LazySamples((S, N, L), torch.float32, dev, _sample, f"F_latent_samples[{mod!r}]")
+            if W is None:
+                F_obs = F_lat
+                if self.fused_ll:
+                    F_lat._fused = {"owner": self, "gen": self._gen, "mean": mean, "q2": q2, "kq": kq, "eps": eps_F,
+                                    "key": key, "gene_off": goff, "samp_off": s0, "consumed": False}
+            else:  # LMC (:428-432)
+                F_obs = LazySamples((S, N, self.Ps[mod]), torch.float32, dev,
+                                    lambda F_lat=F_lat, W=W: _ops.LMCObserve.apply(F_lat.materialise(), W),
+                                    f"F_observed_samples[{mod!r}]")
+                if self.fused_ll and _ops.lmc_fused_supported(L):
+                    F_obs._fused = {"owner": self, "gen": self._gen, "lmc": (F_lat, W), "consumed": False}
+            if not self.fused_ll:
+                F_lat = F_lat.materialise()
+                F_obs = F_lat if W is None else F_obs.materialise()
             self.F_latent_samples[mod] = F_lat
-            self.F_observed_samples[mod] = torch.matmul(F_lat, W) if W is not None else F_lat  # LMC (:428-432)
+            self.F_observed_samples[mod] = F_obs
             if G_test is not None:  # prediction at given aligned coordinates (reference :437-477)
                 Gt = G_test[mod].to(dev, torch.float32)
                 if _eps is not None:
@@ -326,7 +404,7 @@ class VariationalGPSA(GPSA):
                     Osq, Gt, eps_t,
                 )[0]
                 self.F_latent_samples_test[mod] = F_t
-                self.F_observed_samples_test[mod] = torch.matmul(F_t, W) if W is not None else F_t
+                self.F_observed_samples_test[mod] = _ops.LMCObserve.apply(F_t, W) if W is not None else F_t
         self._kl = kl
         self._info = infos
         if _DEBUG_CHECKS:
@@ -344,6 +422,8 @@ class VariationalGPSA(GPSA):
         forward are copied to pinned host memory asynchronously; a later forward (normally the next one) finds them
         arrived and raises.  Independently of this, a failed factorisation makes the loss NaN on the device
         (csrc/chol.cu), so it can never pass silently."""
+        if torch.cuda.is_current_stream_capturing():
+            return  # no event queries / host copies while a CUDA graph is being captured
         pend = getattr(self, "_pending_info", None)
         if pend is not None and pend[1].query():
             self._pending_info = None
@@ -352,7 +432,7 @@ class VariationalGPSA(GPSA):
                 raise RuntimeError(f"VariationalGPSA.forward: a Cholesky factorisation of an earlier forward met a "
                                    f"non-positive pivot (flag {bad}): a K_uu or Omega matrix is not positive-definite")
             pend = None
-        if pend is not None or torch.cuda.is_current_stream_capturing():
+        if pend is not None:
             return
         n = sum(int(i.numel()) for i in infos)
         host = getattr(self, "_info_host", None)
@@ -394,14 +474,44 @@ class VariationalGPSA(GPSA):
     # ----------------------------------------------------------------------------------------------
     def loss_fn(self, data_dict, F_samples):
         """Negative ELBO, reference gpsa/models/vgpsa.py:491-540: -LL/S-averaged + KL_G + KL_F, where the
-        KL terms are those of the most recent forward (they depend on the parameters only)."""
+        KL terms are those of the most recent forward (they depend on the parameters only).
+
+        F_samples[mod] may be the lazy handle forward() returned (fused sampling + likelihood kernel: the samples are
+        never written to memory) or any [S,N,P] tensor (plain Gaussian log-likelihood kernel), e.g. a handle that
+        was materialised because something else read it."""
         if self._kl is None:
             raise RuntimeError("loss_fn needs a preceding forward (it reads the factors cached there)")
-        LL = 0
+        nll = 0
         for mm, mod in enumerate(self.modality_names):
             Y = data_dict[mod]["outputs"]
             F = F_samples[mod]
             idx = self.noise_variance.shape[0] - self.n_modalities + mm  # quirk 6: index -n_modalities+mm (:534)
-            LL = LL + _ops.GaussianLL.apply(F, Y.to(F.device, torch.float32), self.noise_variance[idx:idx + 1])
-        return -LL + self._kl
+            log_noise = self.noise_variance[idx:idx + 1]
+            fz = getattr(F, "_fused", None) if isinstance(F, LazySamples) else None
+            live = (fz is not None and fz["owner"] is self and fz["gen"] == self._gen and not fz["consumed"]
+                    and not F.is_materialised)
+            if live and "lmc" in fz:
+                # LMC: the (small) latent samples are materialised, the [S,N,P] observed samples are not
+                fz["consumed"] = True
+                F_lat, W = fz["lmc"]
+                nll = nll + _ops.LMCNLL.apply(F_lat.materialise(), W, Y.to(F.device, torch.float32), log_noise)
+            elif live:
+                fz["consumed"] = True
+                Yd = Y.to(F.device, torch.float32)
+                S = F.shape[0]
+                nll = nll + _ops.SampleNLL.apply({"gene_off": fz["gene_off"], "samp_off": fz["samp_off"]}, fz["mean"],
+                                                 fz["q2"], fz["kq"], Yd, log_noise, fz["eps"], fz["key"])
+                # the buffer of `mean` now holds U = -(Y - F)/(sigma^2 S): a later read of the handle (plotting, tests)
+                # recovers the samples from it, detached: F = Y + sigma^2 S U
+                sigma = self.noise_variance_pos[idx].detach()
 
+                def _recover(U=fz["mean"], Yd=Yd, sigma=sigma, S=S):
+                    with torch.no_grad():
+                        return Yd.unsqueeze(0) + (sigma * sigma * S) * U.detach()
+
+                F._produce = _recover
+                fz["mean"] = fz["q2"] = fz["kq"] = fz["eps"] = None
+            else:
+                Ft = F.materialise() if isinstance(F, LazySamples) else F
+                nll = nll - _ops.GaussianLL.apply(Ft, Y.to(Ft.device, torch.float32), log_noise)
+        return (nll if self._nll_scale == 1.0 else nll * self._nll_scale) + self._kl

@@ -44,32 +44,37 @@ def shard_data_dict(data_dict, world, rank):
     return out
 
 
-def shard_state_dict(state_dict, world, rank):
-    """Slice a full (unsharded) reference/gpsa_b200 state_dict down to this rank's genes."""
+def shard_state_dict(state_dict, world, rank, n_latent_gps=None):
+    """Slice a full (unsharded) reference/gpsa_b200 state_dict down to this rank's genes.
+
+    Without LMC a gene owns Omega_sqt_F[p] and delta_F[:, p].  With LMC loadings (n_latent_gps[mod] set, pass the dict)
+    the latent GPs are replicated and only the observed outputs are sharded: W_dict[mod] [L, P] is sliced by columns."""
     out = {}
+    lmc = {m for m, k in (n_latent_gps or {}).items() if k is not None}
     for k, v in state_dict.items():
-        if k.startswith("Omega_sqt_F_dict."):
+        mod = k.split(".", 1)[1] if "." in k else None
+        if k.startswith("Omega_sqt_F_dict.") and mod not in lmc:
             lo, hi = gene_range(v.shape[0], world, rank)
             out[k] = v[lo:hi].clone()
-        elif k.startswith("delta_F_dict."):
+        elif k.startswith("delta_F_dict.") and mod not in lmc:
             lo, hi = gene_range(v.shape[1], world, rank)
             out[k] = v[:, lo:hi].clone()
         elif k.startswith("W_dict."):
-            raise NotImplementedError("gene sharding with LMC loadings (n_latent_gps) mixes genes across ranks; not supported")
+            if mod not in lmc:
+                raise ValueError("state_dict holds LMC loadings: pass n_latent_gps so that they can be sharded by output column")
+            lo, hi = gene_range(v.shape[1], world, rank)
+            out[k] = v[:, lo:hi].clone()
         else:
             out[k] = v.clone()
     return out
 
 
-class GeneSharding:
-    """Owns the flat gradient buffer of the shared parameters and the per-iteration all-reduce."""
+class _FlatAllReduce:
+    """Flat gradient buffer of the parameters every rank replicates, and the per-iteration all-reduce over it."""
 
-    def __init__(self, model, world, rank, group=None):
-        self.model, self.world, self.rank, self.group = model, int(world), int(rank), group
-        if any(model.n_latent_gps[m] is not None for m in model.modality_names):
-            raise NotImplementedError("gene sharding with LMC loadings (n_latent_gps) is not supported")
+    def _build_flat(self, model, names):
         named = dict(model.named_parameters())
-        self.shared = [(n, named[n]) for n in SHARED if n in named and named[n].requires_grad]
+        self.shared = [(n, named[n]) for n in names if n in named and named[n].requires_grad]
         total = sum(p.numel() for _, p in self.shared)
         ref = self.shared[0][1]
         # [shared grads ..., local loss]: the trailing slot carries the scalar loss so that logging needs no second collective
@@ -78,6 +83,33 @@ class GeneSharding:
         for _, p in self.shared:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+
+
+class GeneSharding(_FlatAllReduce):
+    """Gene (output) sharding: owns the flat gradient buffer of the shared parameters and the per-iteration all-reduce.
+
+    Modalities with LMC loadings (n_latent_gps set) shard the OBSERVED outputs -- W's columns and the data's columns --
+    and replicate the latent GPs: their Omega_sqt_F / delta_F join the shared parameters and their KL term carries
+    1/world, like the warp layer's."""
+
+    def __init__(self, model, world, rank, group=None):
+        self.model, self.world, self.rank, self.group = model, int(world), int(rank), group
+        names = list(SHARED)
+        # global index of this rank's first gene, per modality: the in-kernel noise of the sampling stage is keyed by
+        # the GLOBAL gene index, so the Monte-Carlo draw is the same whatever the world size
+        for mod in model.modality_names:
+            if model.n_latent_gps[mod] is not None:  # LMC: latent space replicated (same noise on every rank)
+                names += [f"Omega_sqt_F_dict.{mod}", f"delta_F_dict.{mod}"]
+                model._kl_F_scale[mod] = 1.0 / self.world
+                model._gene_off[mod] = 0
+                continue
+            local = int(model.n_latent_outputs[mod])
+            counts = [local]
+            if self.world > 1 and dist.is_available() and dist.is_initialized():
+                counts = [None] * self.world
+                dist.all_gather_object(counts, local, group=group)
+            model._gene_off[mod] = int(sum(counts[:self.rank])) if len(counts) > 1 else 0
+        self._build_flat(model, names)
         model._kl_G_scale = 1.0 / self.world
 
     def nbytes(self):
@@ -104,3 +136,25 @@ class GeneSharding:
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         return self.flat[-1].clone() if loss is not None else None
+
+
+class SampleSharding(_FlatAllReduce):
+    """Monte-Carlo-sample sharding, the alternative when there are fewer genes than GPUs: every rank
+    holds ALL parameters and data and evaluates its contiguous share of the S samples (forward(..., S=S_total) keeps
+    its own S_loc of them; the noise is keyed by the global sample index, so the draw is world-size invariant).
+    loss_r = (S_loc / S) (-LL_r) + KL / world sums over ranks to the negative ELBO; ALL gradients are all-reduced
+    (that includes Omega_sqt_F: 4 L M^2 bytes, the price of this partition)."""
+
+    def __init__(self, model, world, rank, group=None):
+        self.model, self.world, self.rank, self.group = model, int(world), int(rank), group
+        self._build_flat(model, [n for n, _ in model.named_parameters()])
+        model._sample_shard = (self.rank, self.world)
+        model._kl_G_scale = 1.0 / self.world
+        for mod in model.modality_names:
+            model._kl_F_scale[mod] = 1.0 / self.world
+
+
+for _cls in (SampleSharding,):
+    _cls.nbytes = GeneSharding.nbytes
+    _cls.zero_grad = GeneSharding.zero_grad
+    _cls.allreduce = GeneSharding.allreduce

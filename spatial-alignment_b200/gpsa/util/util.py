@@ -55,6 +55,35 @@ def matern32_kernel(x1, x2, lengthscale_unconstrained, output_variance_unconstra
     )
 
 
+def kmeans_gpu(X, n_clusters, iters=30, seed=0):
+    """Lloyd's k-means on the GPU (csrc/aux.cu: gpsa_kmeans_lloyd): X [N,D] (D <= 3) -> (centres [K,D] float32 CUDA
+    tensor, inertia float).  Initial centres = a random subset of the points (numpy Generator(seed)).  Used by
+    VariationalGPSA(data_init=True) for inputs too large for the host KMeans of the reference
+    (gpsa/models/vgpsa.py:61-92), where the inducing-point initialisation dominates the time to the first iteration."""
+    import ctypes as C
+
+    from gpsa import _lib
+
+    if not torch.cuda.is_available():
+        raise _lib.GPSALibraryError("kmeans_gpu needs a CUDA device (no CPU fallback exists)")
+    Xd = torch.as_tensor(X, dtype=torch.float32)
+    Xd = (Xd if Xd.is_cuda else Xd.cuda()).contiguous()
+    N, D = Xd.shape
+    K = int(n_clusters)
+    if K > N:
+        raise ValueError(f"n_clusters={K} exceeds the number of points {N}")
+    rng = np.random.default_rng(seed)
+    sel = torch.as_tensor(rng.choice(N, K, replace=False), device=Xd.device)
+    centres = Xd[sel].clone()
+    assign = torch.empty(N, dtype=torch.int32, device=Xd.device)
+    sums = torch.empty(K * (D + 1), dtype=torch.float64, device=Xd.device)
+    inertia = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        _lib.check(_lib.lib().gpsa_kmeans_lloyd(N, D, K, Xd.data_ptr(), centres.data_ptr(), int(iters), assign.data_ptr(),
+                                                sums.data_ptr(), inertia.data_ptr(), _lib.stream()), "kmeans_lloyd")
+    return centres, float(inertia)
+
+
 def rbf_kernel_numpy(x, xp, kernel_params):
     """Host-side helper of the data simulators (reference gpsa/util/util.py:26-30)."""
     output_scale = np.exp(kernel_params[0])

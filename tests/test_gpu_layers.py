@@ -129,7 +129,9 @@ def test_warp_layer_against_float64(name):
 
 
 def test_graphed_iteration_matches_eager():
-    """One CUDA-graph replay of forward + loss + backward + Adam equals the eager iteration (same seed, same noise)."""
+    """CUDA-graph replays of forward + loss + backward + Adam EQUAL the eager iterations started from the same model,
+    optimizer state and generator seed (the graph-safe CUDA generator reads seed and offset at replay time): losses
+    to 1e-5, parameter updates to 1e-3 (what run-to-run atomics order leaves after Adam's normalisation)."""
     import copy
 
     from golden_io import Golden
@@ -138,27 +140,30 @@ def test_graphed_iteration_matches_eager():
 
     g = Golden("c2_matern")
     model, data_dict = build(g)
-    ref = copy.deepcopy(model)
-    view_idx, Ns, _, _ = ref.create_view_idx_dict(data_dict)
+    view_idx, Ns, _, _ = model.create_view_idx_dict(data_dict)
     X = {m: data_dict[m]["spatial_coords"] for m in g.mods}
-    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, capturable=True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True)
     with pytest.raises(ValueError):
         GraphedIteration(model, data_dict, torch.optim.Adam(model.parameters(), lr=1e-2), S=g.S)
     it = GraphedIteration(model, data_dict, opt, S=g.S, warmup=2)   # 2 warm-up iterations already stepped the model
-    for _ in range(2):
+    ref = copy.deepcopy(model)                                       # eager twin: same parameters, same Adam state
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, capturable=True)
+    opt_ref.load_state_dict(copy.deepcopy(opt.state_dict()))
+    p0 = [p.detach().clone() for p in model.parameters()]
+    for k in range(3):
+        torch.manual_seed(500 + k)
+        lg = float(it.step())
+        torch.manual_seed(500 + k)
         out = ref.forward(X, view_idx=view_idx, Ns=Ns, S=g.S)
-        l = ref.loss_fn(data_dict, out[3])
+        le = ref.loss_fn(data_dict, out[3])
         opt_ref.zero_grad(set_to_none=True)
-        l.backward()
+        le.backward()
         opt_ref.step()
-    # noise differs between the two runs (different generator offsets); compare a deterministic quantity instead:
-    # parameters stay finite and the graphed loss is a sane ELBO of the same magnitude as the eager one
-    losses = [float(it.step()) for _ in range(3)]
-    assert all(np.isfinite(losses))
-    assert abs(losses[-1] - float(l)) < 0.2 * abs(float(l))
-    for p in model.parameters():
-        assert torch.isfinite(p).all()
+        assert np.isfinite(lg) and abs(lg - float(le)) <= 1e-5 * abs(float(le)), (k, lg, float(le))
+    for a, b, c in zip(model.parameters(), ref.parameters(), p0):
+        da, db = (a - c).detach(), (b - c).detach()
+        assert torch.isfinite(a).all()
+        assert float((da - db).abs().max()) <= 1e-3 * max(float(db.abs().max()), 1e-12)
 
 
 def test_iteration_survives_poisoned_allocator_blocks():

@@ -38,10 +38,14 @@ def run(g, model, data_dict):
     return ret, loss
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_ll", "materialised"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_forward_loss_gradients_match_reference(name):
+def test_forward_loss_gradients_match_reference(name, fused):
+    """`fused`: loss_fn consumes the lazy handle forward() returned (fused sampling + likelihood kernel; the samples
+    compared below are then recovered from its gradient buffer) vs plain tensors end to end."""
     g = Golden(name)
     model, data_dict = build(g)
+    model.fused_ll = fused
     ret, loss = run(g, model, data_dict)
     t_out, t_cache, t_loss, t_grads = orc.elbo_and_grads(g.params, g.cfg, g.X, g.Y, g.S, g.eps, dtype=torch.float64,
                                                          G_test=g.G_test)
@@ -105,6 +109,7 @@ def test_rng_order_matches_reference_stream():
     (SURVEY.md 0, item 9): seeding the CUDA generator and replaying those calls reproduces forward()."""
     g = Golden("v3_d3_free")
     model, data_dict = build(g)
+    model.rng_mode = "torch"  # the reference's torch.randn stream (the default draws eps_F in-kernel from Philox)
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dict)
     X = {m: data_dict[m]["spatial_coords"] for m in g.mods}
     torch.manual_seed(123)

@@ -51,10 +51,17 @@ def test_shard_state_and_data():
     lo, hi = gene_range(P, 4, 3)
     assert torch.equal(dd["expression"]["outputs"], data_dict["expression"]["outputs"][:, lo:hi])
     assert dd["expression"]["spatial_coords"] is data_dict["expression"]["spatial_coords"]
+    # LMC: the latent GPs are replicated, the loadings are sharded by output column (needs to be told which modalities)
     g2 = Golden("lmc")
-    m2, _ = _model_from_golden(g2)
-    with pytest.raises(NotImplementedError):
-        shard_state_dict(m2.state_dict(), 2, 0)
+    m2, dd2 = _model_from_golden(g2)
+    sd2 = m2.state_dict()
+    with pytest.raises(ValueError):
+        shard_state_dict(sd2, 2, 0)
+    mod = g2.mods[0]
+    parts2 = [shard_state_dict(sd2, 2, r, n_latent_gps=g2.n_latent) for r in range(2)]
+    assert torch.equal(torch.cat([p[f"W_dict.{mod}"] for p in parts2], 1), sd2[f"W_dict.{mod}"])
+    assert all(torch.equal(p[f"Omega_sqt_F_dict.{mod}"], sd2[f"Omega_sqt_F_dict.{mod}"]) for p in parts2)
+    assert all(torch.equal(p[f"delta_F_dict.{mod}"], sd2[f"delta_F_dict.{mod}"]) for p in parts2)
 
 
 def _cpu_worker(rank, world, port, ret):
@@ -108,18 +115,18 @@ def test_shared_gradient_allreduce_gloo_world2():
 
 
 # --------------------------------------------------------------------------------------------------
-def _gpu_worker(rank, world, port, name, out):
+def _gpu_worker(rank, world, port, name, out, inject=True, mode="gene"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import gpsa
-        from gpsa.parallel import GeneSharding, gene_range, shard_data_dict, shard_state_dict
+        from gpsa.parallel import GeneSharding, SampleSharding, gene_range, shard_data_dict, shard_state_dict
 
         g = Golden(name)
         full, data_dict = _model_from_golden(g)
         sd = {k: torch.from_numpy(np.asarray(v)) for k, v in g.params.items() if k not in g.fixed_params}
         full.load_state_dict(sd, strict=True)
-        local_dd = shard_data_dict(data_dict, world, rank)
+        local_dd = shard_data_dict(data_dict, world, rank) if mode == "gene" else data_dict
         kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel, "matern32": gpsa.matern32_kernel}
         np.random.seed(0)
         torch.manual_seed(0)
@@ -127,17 +134,29 @@ def _gpu_worker(rank, world, port, name, out):
                                      m_G=g.cfg.m_G, data_init=True, n_latent_gps=g.n_latent,
                                      kernel_func_warp=kern[g.cfg.kernel_warp], kernel_func_data=kern[g.cfg.kernel_data],
                                      fixed_view_idx=g.fixed)
-        model.load_state_dict(shard_state_dict(full.state_dict(), world, rank))
+        if mode == "gene":
+            model.load_state_dict(shard_state_dict(full.state_dict(), world, rank, n_latent_gps=g.n_latent))
+        else:
+            model.load_state_dict(full.state_dict())
         model = model.to("cuda")
         local_dd = {m: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for m, d in local_dd.items()}
-        sh = GeneSharding(model, world, rank)
+        sh = GeneSharding(model, world, rank) if mode == "gene" else SampleSharding(model, world, rank)
         view_idx, Ns, _, _ = model.create_view_idx_dict(local_dd)
         P = g.Y[g.mods[0]].shape[1]
         lo, hi = gene_range(P, world, rank)
+        lmc = any(v is not None for v in g.n_latent.values())
+        if mode == "sample" or lmc:   # every rank holds every latent output: full noise (the model keeps its samples)
+            lo_e, hi_e = 0, None
+        else:
+            lo_e, hi_e = lo, hi
         eps = {"G": {v: torch.from_numpy(e) for v, e in g.eps["G"].items()},  # identical warp noise on every rank
-               "F": {m: torch.from_numpy(e[:, :, lo:hi].copy()) for m, e in g.eps["F"].items()}, "F_test": {}}
+               "F": {m: torch.from_numpy(e[:, :, lo_e:hi_e].copy()) for m, e in g.eps["F"].items()}, "F_test": {}}
         X = {m: local_dd[m]["spatial_coords"] for m in g.mods}
-        ret = model.forward(X, view_idx=view_idx, Ns=Ns, S=g.S, _eps=eps)
+        if inject:
+            ret = model.forward(X, view_idx=view_idx, Ns=Ns, S=g.S, _eps=eps)
+        else:  # default noise: every rank seeds alike; eps_F comes from the in-kernel generator keyed by GLOBAL gene
+            torch.manual_seed(4242)
+            ret = model.forward(X, view_idx=view_idx, Ns=Ns, S=g.S)
         loss = model.loss_fn(local_dd, ret[3])
         sh.zero_grad()
         loss.backward()
@@ -176,3 +195,89 @@ def test_sharded_iteration_equals_unsharded(name):
             got = out[0][n]
             assert np.array_equal(out[0][n], out[1][n]), n  # all-reduced: bitwise identical on every rank
         assert relerr(got, gref) < 5e-5, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_shipped"])
+def test_sharded_iteration_equals_unsharded_without_injected_noise(name):
+    """World-size-invariant Monte-Carlo draw: with the default in-kernel noise (no injected eps) the gene-sharded
+    iteration at world 2 reproduces the unsharded loss and gradients for the same torch seed."""
+    from test_gpu_parity import build
+
+    g = Golden(name)
+    model, data_dict = build(g)
+    view_idx, Ns, _, _ = model.create_view_idx_dict(data_dict)
+    X = {m: data_dict[m]["spatial_coords"] for m in g.mods}
+    torch.manual_seed(4242)
+    ret = model.forward(X, view_idx=view_idx, Ns=Ns, S=g.S)
+    loss = model.loss_fn(data_dict, ret[3])
+    model.zero_grad()
+    loss.backward()
+    ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, False), nprocs=world, join=True)
+    out = dict(out)
+    assert abs(out[0]["loss"] - float(loss)) <= 2e-5 * abs(float(loss))
+    mod = g.mods[0]
+    for n, gref in ref.items():
+        if n == f"Omega_sqt_F_dict.{mod}":
+            got = np.concatenate([out[r][n] for r in range(world)], 0)
+        elif n == f"delta_F_dict.{mod}":
+            got = np.concatenate([out[r][n] for r in range(world)], 1)
+        else:
+            got = out[0][n]
+        assert relerr(got, gref) <= 5e-5, n
+
+
+def _gather(out, world, n, mod, how):
+    if how == "rows":
+        return np.concatenate([out[r][n] for r in range(world)], 0)
+    if how == "cols":
+        return np.concatenate([out[r][n] for r in range(world)], 1)
+    assert np.array_equal(out[0][n], out[1][n]), n  # all-reduced: bitwise identical on every rank
+    return out[0][n]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_shipped", "v3_d3_free"])
+def test_sample_sharded_iteration_equals_unsharded(name):
+    """Monte-Carlo-sample sharding (fewer genes than GPUs): each of 2 ranks evaluates its share of the S = 5 samples,
+    every gradient is all-reduced; loss and gradients equal the unsharded iteration on the same noise."""
+    from test_gpu_parity import build, run
+
+    g = Golden(name)
+    model, data_dict = build(g)
+    _, loss = run(g, model, data_dict)
+    ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, True, "sample"), nprocs=world, join=True)
+    out = dict(out)
+    assert abs(out[0]["loss"] - float(loss)) <= 2e-5 * abs(float(loss))
+    for n, gref in ref.items():
+        assert relerr(_gather(out, world, n, None, "same"), gref) < 1e-4, n
+
+
+@pytest.mark.gpu
+def test_lmc_gene_sharded_iteration_equals_unsharded():
+    """Gene sharding with LMC loadings: the observed outputs (columns of W and of the data) are split over 2 ranks,
+    the latent GPs are replicated and their gradients all-reduced."""
+    from test_gpu_parity import build, run
+
+    g = Golden("lmc")
+    model, data_dict = build(g)
+    _, loss = run(g, model, data_dict)
+    ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), "lmc", out, True, "gene"), nprocs=world, join=True)
+    out = dict(out)
+    assert abs(out[0]["loss"] - float(loss)) <= 2e-5 * abs(float(loss))
+    mod = g.mods[0]
+    for n, gref in ref.items():
+        how = "cols" if n == f"W_dict.{mod}" else "same"
+        assert relerr(_gather(out, world, n, mod, how), gref) < 1e-4, n
