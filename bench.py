@@ -425,8 +425,8 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
     names = ["fwd", "bwd_alpha", "bwd_omega"]
     engine = _ops.pick_engine(cfg["M"], S * N, local_genes)
     tc = engine in _ops.TC_ENGINES
-    kern = {"fwd": "tc_gemm_kernel<4> (implicit-feature forward)" if engine == 2 else "tc_qf_fwd_kernel",
-            "bwd_alpha": "tc_gemm_kernel<1>", "bwd_omega": "tc_gemm_kernel<2>"}
+    kern = {"fwd": "tc_gemm_kernel<3> (implicit-feature forward)", "bwd_alpha": "tc_gemm_kernel<1>",
+            "bwd_omega": "tc_gemm_kernel<2>"}
     per = {n: tot_ms[i] / max(counts[i], 1) for i, n in enumerate(names)}
     f_one = f_q2 / 3.0  # algorithmic (symmetric-minimum) flops of ONE of the three products, per launch
     passes = 3 if tc else 1
@@ -480,7 +480,7 @@ def main():
                     help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
                          "the JSON line is then NOT the named configuration and says so")
     ap.add_argument("--engine", type=int, default=None,
-                    help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 / Cholesky-form forward, 2 tcgen05 / feature-form forward (default: auto)")
+                    help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 (default: auto)")
     args = ap.parse_args()
     config_name = args.config or "c3"
     cfg = dict(CONFIGS[config_name])

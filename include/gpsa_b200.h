@@ -10,7 +10,9 @@
  * Shapes use the symbols of SURVEY.md:  M inducing points, D spatial dims (1..3), R = S*N rows
  * (Monte-Carlo sample s, spot n; r = s*N + n), L latent outputs (genes), V views.
  * Kernel kinds: 0 = rbf (gpsa/util/util.py:8-23), 1 = matern12 (gpsa/util/util.py:33-47),
- * 2 = matern32 (gpsa/util/util.py:50-66).
+ * 2 = matern32 (gpsa/util/util.py:50-66), 3 = external: K_uu / K_uf are evaluated (and differentiated) by the caller --
+ * the path for user-supplied covariance callables (kernel_func_warp / kernel_func_data, gpsa/models/vgpsa.py:25-26);
+ * the layer entry points then take the matrices and hand back dLoss/dK_uu, dLoss/dK_uf.
  */
 #ifndef GPSA_B200_H
 #define GPSA_B200_H
@@ -64,6 +66,9 @@ int gpsa_potrf_batched_f32(int M, int batch, float* A, float* half_logdet, int* 
 int gpsa_potrf_batched_f64(int M, int batch, double* A, double* half_logdet, int* info, cudaStream_t stream);
 /* X = L^-1 (lower).  X must not alias L.  Stands in for the triangular solves of
  * torch.cholesky_solve (gpsa/models/vgpsa.py:177) and of the MultivariateNormal KL (:506-530). */
+/* fp32 factorisation out of place (A: lower triangle read; L may alias A) with the log-determinant in fp64. */
+int gpsa_potrf_batched_f32_ld64(int M, int batch, const float* A, float* L, double* half_logdet, int* info,
+                                cudaStream_t stream);
 int gpsa_trtri_batched_f32(int M, int batch, const float* L, float* X, cudaStream_t stream);
 int gpsa_trtri_batched_f64(int M, int batch, const double* L, double* X, cudaStream_t stream);
 
@@ -82,16 +87,25 @@ int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_
                        float* Kinv, double* Kinv64, double* half_logdet, int* info, double* ws64,
                        cudaStream_t stream);
 
+/* Same for kind 3: Kuu [M,M] fp32 (without the 1e-5 jitter) evaluated by the caller. */
+int gpsa_prior_prepare_ext(int M, const float* Kuu, float* Lk, float* Kinv, double* Kinv64, double* half_logdet, int* info,
+                           double* ws64, cudaStream_t stream);
+
 /* ---- variational covariances Omega = Omega_sqt Omega_sqt^T + 1e-5 I, batched ------------------
  * Replaces get_Omega_from_Omega_sqt + torch.cholesky (gpsa/models/vgpsa.py:206-210, :255-257, :410-412).
  * Omega, Ltril: [B,M,M]; half_logdet [B]; info [B]. */
 int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, double* L64, double* half_logdet,
                        int* info, cudaStream_t stream);
+/* L64 == NULL selects the fp32 factorisation (large gene batches): Omega is still accumulated in fp64 and rounded once,
+ * the Cholesky runs in fp32 (what the reference does, :410-412), the log-determinants are summed in fp64. */
 /* Backward: Osq_bar = 2 (Obar + coef[b] * Omega^-1) Osq.  Obar [B,M,M] symmetric; coef: device [B]
  * (the -1/2 dKL factor of the log-det term, 0 for slices without a KL term; NULL = no such term);
  * L64: the fp64 factor from gpsa_omega_prepare; Linv64, Y64: [B,M,M] fp64 scratch. */
 int gpsa_omega_grad(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
                     double* Linv64, double* Y64, float* Osq_bar, cudaStream_t stream);
+/* fp32 form for factors from the fp32 branch of gpsa_omega_prepare (Ltril fp32; Linv32, Y32: [B,M,M] fp32 scratch). */
+int gpsa_omega_grad_f32(int M, int B, const float* Osq, const float* Ltril, const float* Obar, const float* coef,
+                        float* Linv32, float* Y32, float* Osq_bar, void* tc_ws, size_t tc_ws_bytes, cudaStream_t stream);
 /* Same, with the 2 Obar Osq product on the tcgen05 engine; tc_ws: gpsa_gemm_tc_ws_bytes(M, M, M, B) bytes. */
 int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* L64, const float* Obar, const float* coef,
                        double* Linv64, double* Y64, float* Osq_bar, void* tc_ws, size_t tc_ws_bytes, cudaStream_t stream);
@@ -111,18 +125,14 @@ int gpsa_quadform_bwd_alpha_f32(int M, long R, int L, const float* A, const floa
                                 cudaStream_t stream);
 
 /* ---- tensor-core (tcgen05) engine for the same three products ------------------------------------
- * bf16 hi/lo split operands, three MMA passes, fp32 accumulation in TMEM (error ~2^-16 per product).
- * The forward uses the reference's own formulation q2 = ||a^T L_p||^2 with Ltril = chol(Omega)
- * (gpsa/models/vgpsa.py:193-196); the backward products use Omega / the packed features as above.
- * `ws` is caller-provided device scratch of at least gpsa_quadform_tc_ws_bytes(M, R, L) bytes (bf16
- * copies of the operands); gpsa_tc_supported(M) says whether the forward kernel covers this M
- * (16 <= M <= 512; above 256 the forward streams both operands through the generic GEMM core).  G [R,L] = dLoss/dq2, Abar [M,R] is ADDED to, H as for the fp32 engine. */
+ * bf16 hi/lo split operands, three MMA passes, fp32 accumulation in TMEM in chains of bounded length (error ~2^-16 per
+ * product).  All three products are implicit-feature GEMMs over the packed symmetric features of Omega: the forward is
+ * q2 = Phi(A) W(Omega) with Phi[r,(i,j)] = a_r[i] a_r[j] generated on the fly (gpsa/models/vgpsa.py:193-196; the
+ * Cholesky factor is not needed for it).  `ws` is caller-provided device scratch of at least
+ * gpsa_quadform_tc_ws_bytes(M, R, L) bytes (bf16 copies of the operands); gpsa_tc_supported(M) says whether the engine
+ * covers this M (16 <= M <= 512).  G [R,L] = dLoss/dq2, Abar [M,R] is ADDED to, H as for the fp32 engine. */
 int gpsa_tc_supported(int M);
 size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L);
-int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws, size_t ws_bytes,
-                         cudaStream_t stream);
-/* The same forward in the implicit-feature form the backward products use: q2 = Phi(A) W(Omega), Phi generated on the
- * fly, no Cholesky factor needed.  This is the form the data layer uses (engine 2). */
 int gpsa_quadform_fwd_feat_tc(int M, long R, int L, const float* A, const float* Omega, float* q2, void* ws,
                               size_t ws_bytes, cudaStream_t stream);
 int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, const float* G, const float* Omega, float* Abar,
@@ -173,6 +183,8 @@ typedef struct {
   long gs_stride;
   double* kl_acc;         /* fp64 scalar, ADDED to (may be NULL) */
   double* ws64;           /* 2*M*M doubles */
+  const float* Kuu_ext;   /* kind 3 only: k(Z,Z) [M,M] and k(Z,X) [M,n] evaluated by the caller; else NULL */
+  const float* Kuf_ext;
 } gpsa_warp_fwd_args;
 int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t stream);
 
@@ -193,6 +205,8 @@ typedef struct {
   float *mubar, *varbar, *q1bar; /* [n,D], [n,D], [n] */
   double *Abar, *C, *AS;         /* fp64 [M,n], [M,n], [D,M,n] */
   double* ws64;                  /* 3*M*M doubles */
+  float* Kuu_bar;                /* kind 3 only: out [M,M] dLoss/dK_uu, out [M,n] dLoss/dK_uf; else NULL */
+  float* Kuf_bar;
 } gpsa_warp_bwd_args;
 int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t stream);
 
@@ -223,11 +237,10 @@ typedef struct {
   float* q2;              /* out [R,L] quadratic form */
   double* kl_acc;         /* fp64 scalar, ADDED to; may be NULL (prediction) */
   double* ws64;           /* 2*M*M doubles */
-  int engine;             /* 0 = fp32 SIMT quadratic form, 1 = tcgen05 split-bf16 with the ||a^T L||^2 forward,
-                             2 = tcgen05 split-bf16 with the implicit-feature forward (default for large shapes) */
-  const float* Ltril;     /* [L,M,M] chol(Omega) from gpsa_omega_prepare (engine 1 only) */
-  void* tc_ws;            /* engines 1, 2: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  int engine;             /* 0 = fp32 SIMT quadratic form (launch-bound toy shapes), 1 = tcgen05 split-bf16 */
+  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;
+  const float* Kuu_ext;   /* kind 3 only: k(Gt,Gt) [M,M] evaluated by the caller, and B is an INPUT holding k(Gt,G) [M,R] */
 } gpsa_data_fwd_args;
 int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
 
@@ -254,8 +267,9 @@ typedef struct {
   float* H;               /* [gpsa_feat_count(M), L] */
   double* ws64;           /* 3*M*M doubles */
   int engine;
-  void* tc_ws;            /* engines 1, 2: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
+  void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;
+  float* Kuu_bar;         /* kind 3 only: out [M,M] dLoss/dK_uu; dLoss/dK_uf is C [M,R]; G_bar / acc_Gt are not written */
 } gpsa_data_bwd_args;
 int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t stream);
 
@@ -319,7 +333,7 @@ typedef struct {
   float* m[GPSA_ADAM_MAX_TENSORS];        /* exp_avg */
   float* v[GPSA_ADAM_MAX_TENSORS];        /* exp_avg_sq */
   long n[GPSA_ADAM_MAX_TENSORS];          /* elements */
-  float lr, beta1, beta2, eps;
+  double lr, beta1, beta2, eps;           /* doubles like torch's Python scalars: 1 - beta2 must not be formed in fp32 */
   float* step;
 } gpsa_adam_args;
 int gpsa_adam_step(const gpsa_adam_args* a, cudaStream_t stream);

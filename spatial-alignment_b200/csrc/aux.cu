@@ -23,9 +23,11 @@ __global__ void adam_tick_kernel(const gpsa_adam_args a) {
 __global__ void __launch_bounds__(256) adam_multi_kernel(const gpsa_adam_args a) {
   const float t = a.step[blockIdx.y];  // already incremented by adam_tick_kernel on the same stream
   // bias corrections in double like torch's host-side scalars (1 - 0.999^t loses 5 digits in float at small t)
-  const double bc1d = 1.0 - pow((double)a.beta1, (double)t);
-  const float bc2s = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
-  const float step_size = (float)((double)a.lr / bc1d);
+  const double bc1d = 1.0 - pow(a.beta1, (double)t);
+  const float bc2s = (float)sqrt(1.0 - pow(a.beta2, (double)t));
+  const float step_size = (float)(a.lr / bc1d);
+  const float b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+  const float eps = (float)a.eps;
   // blockIdx.y = tensor, blockIdx.x strides over its elements
   const int k = blockIdx.y;
   float* __restrict__ p = a.p[k];
@@ -42,9 +44,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const gpsa_adam_args a)
     float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
 #define ADAM1(c)                                                  \
-  mm.c = a.beta1 * mm.c + (1.0f - a.beta1) * gg.c;                \
-  vv.c = a.beta2 * vv.c + (1.0f - a.beta2) * gg.c * gg.c;         \
-  pp.c -= step_size * mm.c / (sqrtf(vv.c) / bc2s + a.eps);
+  mm.c = mm.c + omb1 * (gg.c - mm.c);       /* exp_avg.lerp_(grad, 1 - beta1) */ \
+  vv.c = b2 * vv.c + omb2 * gg.c * gg.c;    /* exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2) */ \
+  pp.c -= step_size * mm.c / (sqrtf(vv.c) / bc2s + eps);
     ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
 #undef ADAM1
     reinterpret_cast<float4*>(p)[i] = pp;
@@ -53,11 +55,11 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const gpsa_adam_args a)
   }
   for (long i = 4 * n4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = g[i];
-    const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
-    const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * gi * gi;
+    const float mi = m[i] + omb1 * (gi - m[i]);
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= step_size * mi / (sqrtf(vi) / bc2s + a.eps);
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
   }
 }
 

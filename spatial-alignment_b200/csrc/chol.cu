@@ -54,8 +54,8 @@ __device__ __forceinline__ bool warp_potrf32(T* Dg, int kn) {
   return bad;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) potrf_kernel(int M, T* A, long stride, T* half_logdet, int* info) {
+template <typename T, typename TL>
+__global__ void __launch_bounds__(256) potrf_kernel(int M, T* A, long stride, TL* half_logdet, int* info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Dg = reinterpret_cast<T*>(smem_raw);  // [NB][LDP]
   T* P = Dg + NB * LDP;                    // [M][LDP] panel rows below the diagonal block
@@ -134,14 +134,14 @@ __global__ void __launch_bounds__(256) potrf_kernel(int M, T* A, long stride, T*
     const int i = idx / M, j = idx % M;
     if (j > i) Ab[idx] = T(0);
   }
-  T ld = 0;
-  for (int i = tid; i < M; i += blockDim.x) ld += log(Ab[(long)i * M + i]);
-  __shared__ T red[32];
-  ld = block_sum<T>(ld, red);
+  TL ld = 0;
+  for (int i = tid; i < M; i += blockDim.x) ld += log((TL)Ab[(long)i * M + i]);
+  __shared__ TL red[32];
+  ld = block_sum<TL>(ld, red);
   if (tid == 0) {
     // a non-positive pivot poisons the log-determinant: the KL terms, hence the loss, become NaN on the device, so a
     // failed factorisation cannot pass silently even when nobody reads `info` (torch.cholesky raises on the host)
-    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (T)NAN : ld;
+    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (TL)NAN : ld;
     if (info) info[blockIdx.x] = s_bad;
   }
 }
@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(256) trtri_kernel(int M, const T* L, T* X, lon
 // single 200 x 200 fp64 matrix; these take 0.156 ms (potrf) / 0.149 ms (trtri), bound by the serial 16-wide
 // diagonal blocks and the barriers between panel phases.
 // ------------------------------------------------------------------------------------------------
-constexpr int PK_THREADS = 512;
+constexpr int PK_THREADS = 512;      // fp64: one CTA per SM (the packed triangle of M = 200 is 161 KB)
+constexpr int PK_THREADS_F32 = 256;  // fp32: half the shared memory and half the threads -> two CTAs per SM, so one
+                                     // matrix's serial diagonal-block phases overlap the other's trailing updates
 __host__ __device__ inline long pk(int i, int j) { return (long)i * (i + 1) / 2 + j; }
 
 constexpr int PB = 16;        // panel width of the packed kernels
@@ -260,19 +262,23 @@ __device__ __forceinline__ bool warp_potrf16(T (&r)[PB], int lane) {
 // block in registers, one thread per row solves the panel against it, and the trailing triangle is updated in
 // 8 x 4 register tiles (12 shared-memory loads per 32 FMAs).  The fp64 pipe of one SM (64 FMA/clk) bounds a
 // 200 x 200 matrix at ~25 us; the barriers and the serial diagonal blocks add about as much again.
-template <typename T>
-__global__ void __launch_bounds__(PK_THREADS, 1) potrf_packed_kernel(int M, T* A, long stride, T* half_logdet, int* info) {
+// Ain (lower triangle read) -> Aout (lower factor, zeros above); Aout may be Ain.  TL: type of the log-determinant.
+template <typename T, typename TL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+potrf_packed_kernel(int M, const T* Ain, T* Aout, long stride, TL* half_logdet, int* info) {
+  constexpr int PK_THREADS = THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Lp = reinterpret_cast<T*>(smem_raw);       // packed lower triangle
   T* Dg = Lp + (long)M * (M + 1) / 2;           // [PB][PLD] current diagonal block
   T* dinv = Dg + PB * PLD;                      // [PB]
-  T* Ab = A + (long)blockIdx.x * stride;
+  const T* Ai = Ain + (long)blockIdx.x * stride;
+  T* Ab = Aout + (long)blockIdx.x * stride;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
   for (long idx = tid; idx < (long)M * M; idx += PK_THREADS) {
     const int i = idx / M, j = idx % M;
-    if (j <= i) Lp[pk(i, j)] = Ab[idx];
+    if (j <= i) Lp[pk(i, j)] = Ai[idx];
   }
   __syncthreads();
   for (int k0 = 0; k0 < M; k0 += PB) {
@@ -370,14 +376,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) potrf_packed_kernel(int M, T* A
     const int i = idx / M, j = idx % M;
     Ab[idx] = (j <= i) ? Lp[pk(i, j)] : T(0);
   }
-  T ld = 0;
-  for (int i = tid; i < M; i += PK_THREADS) ld += log(Lp[pk(i, i)]);
-  __shared__ T red[32];
-  ld = block_sum<T>(ld, red);
+  TL ld = 0;
+  for (int i = tid; i < M; i += PK_THREADS) ld += log((TL)Lp[pk(i, i)]);
+  __shared__ TL red[32];
+  ld = block_sum<TL>(ld, red);
   if (tid == 0) {
     // a non-positive pivot poisons the log-determinant: the KL terms, hence the loss, become NaN on the device, so a
     // failed factorisation cannot pass silently even when nobody reads `info` (torch.cholesky raises on the host)
-    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (T)NAN : ld;
+    if (half_logdet) half_logdet[blockIdx.x] = s_bad ? (TL)NAN : ld;
     if (info) info[blockIdx.x] = s_bad;
   }
 }
@@ -387,8 +393,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) potrf_packed_kernel(int M, T* A
 // The block row of L is staged in a side buffer (it is overwritten by X[I, :]); the product W = L[I,:] X runs in
 // 4 x 4 register tiles with the contraction split over 4 adjacent lanes (the early block rows are short and would
 // otherwise leave most of the CTA idle), while one warp inverts the diagonal block.
-template <typename T>
-__global__ void __launch_bounds__(PK_THREADS, 1) trtri_packed_kernel(int M, const T* L, T* X, long stride) {
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) trtri_packed_kernel(int M, const T* L, T* X, long stride) {
+  constexpr int PK_THREADS = THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Xp = reinterpret_cast<T*>(smem_raw);   // packed: L on entry, X on exit
   T* stage = Xp + (long)M * (M + 1) / 2;    // [PB][M]  block row of L
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) trtri_packed_kernel(int M, cons
       Dg[i * PLD + j] = (i < in && j <= i) ? Xp[pk(I0 + i, I0 + j)] : ((i == j) ? T(1) : T(0));
     }
     __syncthreads();
-    if (warp == 15) {
+    if (warp == PK_THREADS / 32 - 1) {
       // X_II by forward substitution: lane c solves L_II x = e_c; written back as column c (zeros above the diagonal)
       T xcol[PB];
       const int c = lane & (PB - 1);
@@ -502,28 +509,38 @@ size_t packed_smem(int M, int extra_rows) {
   return ((size_t)M * (M + 1) / 2 + (size_t)extra_rows * M + PB * PLD + PB) * sizeof(T);
 }
 
-template <typename T>
-int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t st) {
+template <typename T> struct PkThreads { static constexpr int v = PK_THREADS; };
+template <> struct PkThreads<float> { static constexpr int v = PK_THREADS_F32; };
+
+// Ain -> Aout (may alias), log-determinant in TL
+template <typename T, typename TL>
+int potrf_launch(int M, int batch, const T* Ain, T* Aout, TL* half_logdet, int* info, cudaStream_t st) {
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+  constexpr int TH = PkThreads<T>::v;
   const size_t psm = packed_smem<T>(M, 0);
+  const size_t cap = sizeof(T) == 4 ? 113 * 1024 : 226 * 1024;  // fp32: two CTAs per SM
   if (!no_packed && psm <= 226 * 1024) {
     static size_t attr[GPSA_MAX_DEVICES] = {};
     const int dev = gpsa_dev();
     if (psm > 48 * 1024 && psm > attr[dev]) {
-      if (cudaFuncSetAttribute(potrf_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+      if (cudaFuncSetAttribute(potrf_packed_kernel<T, TL, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
         return GPSA_ERR_CUDA;
       attr[dev] = 226 * 1024;
     }
-    potrf_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, A, (long)M * M, half_logdet, info);
+    (void)cap;
+    potrf_packed_kernel<T, TL, TH><<<batch, TH, psm, st>>>(M, Ain, Aout, (long)M * M, half_logdet, info);
     GPSA_LAUNCH_CHECK();
     return GPSA_OK;
   }
   const size_t smem = (size_t)(NB * LDP + (size_t)M * LDP) * sizeof(T);
   if (smem > 220 * 1024) return GPSA_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(potrf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (Ain != Aout &&
+      cudaMemcpyAsync(Aout, Ain, sizeof(T) * (size_t)batch * M * M, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return GPSA_ERR_CUDA;
-  potrf_kernel<T><<<batch, 256, smem, st>>>(M, A, (long)M * M, half_logdet, info);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(potrf_kernel<T, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return GPSA_ERR_CUDA;
+  potrf_kernel<T, TL><<<batch, 256, smem, st>>>(M, Aout, (long)M * M, half_logdet, info);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }
@@ -531,16 +548,17 @@ int potrf_launch(int M, int batch, T* A, T* half_logdet, int* info, cudaStream_t
 template <typename T>
 int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+  constexpr int TH = PkThreads<T>::v;
   const size_t psm = packed_smem<T>(M, 2 * PB);
   if (!no_packed && psm <= 226 * 1024 && L != X) {
     static size_t attr[GPSA_MAX_DEVICES] = {};
     const int dev = gpsa_dev();
     if (psm > 48 * 1024 && psm > attr[dev]) {
-      if (cudaFuncSetAttribute(trtri_packed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+      if (cudaFuncSetAttribute(trtri_packed_kernel<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
         return GPSA_ERR_CUDA;
       attr[dev] = 226 * 1024;
     }
-    trtri_packed_kernel<T><<<batch, PK_THREADS, psm, st>>>(M, L, X, (long)M * M);
+    trtri_packed_kernel<T, TH><<<batch, TH, psm, st>>>(M, L, X, (long)M * M);
     GPSA_LAUNCH_CHECK();
     return GPSA_OK;
   }
@@ -558,11 +576,18 @@ int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
 
 extern "C" int gpsa_potrf_batched_f32(int M, int batch, float* A, float* half_logdet, int* info, cudaStream_t st) {
   if (M <= 0 || batch <= 0) return GPSA_OK;
-  return potrf_launch<float>(M, batch, A, half_logdet, info, st);
+  return potrf_launch<float, float>(M, batch, A, A, half_logdet, info, st);
 }
 extern "C" int gpsa_potrf_batched_f64(int M, int batch, double* A, double* half_logdet, int* info, cudaStream_t st) {
   if (M <= 0 || batch <= 0) return GPSA_OK;
-  return potrf_launch<double>(M, batch, A, half_logdet, info, st);
+  return potrf_launch<double, double>(M, batch, A, A, half_logdet, info, st);
+}
+// fp32 factorisation A (lower triangle read) -> L (may alias A) with the log-determinant accumulated in fp64: the form
+// the gene-batched variational covariances use (gpsa_omega_prepare with L64 == NULL)
+extern "C" int gpsa_potrf_batched_f32_ld64(int M, int batch, const float* A, float* L, double* half_logdet, int* info,
+                                           cudaStream_t st) {
+  if (M <= 0 || batch <= 0) return GPSA_OK;
+  return potrf_launch<float, double>(M, batch, A, L, half_logdet, info, st);
 }
 extern "C" int gpsa_trtri_batched_f32(int M, int batch, const float* L, float* X, cudaStream_t st) {
   if (M <= 0 || batch <= 0) return GPSA_OK;

@@ -11,6 +11,7 @@
 #define GPSA_KIND_RBF 0
 #define GPSA_KIND_MATERN12 1
 #define GPSA_KIND_MATERN32 2
+#define GPSA_KIND_EXTERNAL 3  // K_uu / K_uf evaluated by the caller (user-supplied covariance function)
 
 #define GPSA_OFF 1e-5f  // diagonal_offset, reference gpsa/models/gpsa.py:153
 

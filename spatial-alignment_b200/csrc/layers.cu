@@ -806,6 +806,32 @@ extern "C" int gpsa_gemm_f32(int M, int N, long K, float alpha, const float* A, 
                                                   sC, batch);
 }
 
+namespace {
+// Kd (fp64, M x M, jitter already on its diagonal) -> factor, inverse, fp32 copies.  Xd: M*M doubles of scratch.
+int prior_factorise(int M, double* Kd, double* Xd, float* Lk, float* Kinv, double* Kinv64, double* half_logdet, int* info,
+                    cudaStream_t st) {
+  const long MM = (long)M * M;
+  TRY(gpsa_potrf_batched_f64(M, 1, Kd, half_logdet, info, st));
+  TRY(gpsa_trtri_batched_f64(M, 1, Kd, Xd, st));
+  // K^-1 = X^T X
+  TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv64, M, 0, 1)));
+  cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
+  GPSA_LAUNCH_CHECK();
+  if (Kinv) {
+    cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kinv64, Kinv);
+    GPSA_LAUNCH_CHECK();
+  }
+  return GPSA_OK;
+}
+
+// Kd = (double) K + 1e-5 I
+__global__ void ext_kuu_kernel(int M, const float* __restrict__ K, double* __restrict__ Kd) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * M) return;
+  Kd[idx] = (double)K[idx] + ((idx / M == idx % M) ? 1e-5 : 0.0);
+}
+}  // namespace
+
 extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const float* log_ls, const float* log_var,
                                   float* Lk, float* Kinv, double* Kinv64, double* half_logdet, int* info, double* ws64,
                                   cudaStream_t st) {
@@ -826,23 +852,47 @@ extern "C" int gpsa_prior_prepare(int kind, int D, int M, const float* Z, const 
   }
 #undef PK
   GPSA_LAUNCH_CHECK();
-  TRY(gpsa_potrf_batched_f64(M, 1, Kd, half_logdet, info, st));
-  TRY(gpsa_trtri_batched_f64(M, 1, Kd, Xd, st));
-  // K^-1 = X^T X
-  TRY((gemm_strided<double, double, double, double>(st, M, M, M, 1.0, Xd, 1, M, 0, Xd, M, 1, 0, 0.0, Kinv64, M, 0, 1)));
-  cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kd, Lk);
-  GPSA_LAUNCH_CHECK();
-  if (Kinv) {
-    cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kinv64, Kinv);
-    GPSA_LAUNCH_CHECK();
-  }
-  return GPSA_OK;
+  return prior_factorise(M, Kd, Xd, Lk, Kinv, Kinv64, half_logdet, info, st);
 }
+
+// Same with K_uu [M,M] (fp32, WITHOUT the jitter) evaluated by the caller: user-supplied covariance functions.
+extern "C" int gpsa_prior_prepare_ext(int M, const float* Kuu, float* Lk, float* Kinv, double* Kinv64, double* half_logdet,
+                                      int* info, double* ws64, cudaStream_t st) {
+  if (M <= 0 || !Kuu) return GPSA_ERR_ARG;
+  const long MM = (long)M * M;
+  ext_kuu_kernel<<<gpsa_cdiv(MM, 256), 256, 0, st>>>(M, Kuu, ws64);
+  GPSA_LAUNCH_CHECK();
+  return prior_factorise(M, ws64, ws64 + MM, Lk, Kinv, Kinv64, half_logdet, info, st);
+}
+
+namespace {
+// in place: upper triangle <- lower triangle, per matrix
+__global__ void mirror_lower_kernel(long n, int M, float* __restrict__ A) {
+  const long MM = (long)M * M;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const long b = idx / MM;
+    const int e = (int)(idx - b * MM);
+    const int i = e / M, j = e - i * M;
+    if (j > i) A[idx] = A[b * MM + (long)j * M + i];
+  }
+}
+}  // namespace
 
 extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, float* Ltril, double* L64,
                                   double* half_logdet, int* info, cudaStream_t st) {
   if (M <= 0 || B <= 0) return GPSA_OK;
   const long MM = (long)M * M;
+  if (!L64) {
+    // fp32 factorisation (the gene-batched Omega_F): the product Osq Osq^T is still ACCUMULATED in fp64 and rounded
+    // once -- forming Omega in fp32 is what dominates the reference's own error here (cond(Omega) ~ 1e6 at its
+    // initialisation: 3-8x further from float64 than this path, tools/ measurements in DESIGN.md) -- then one fp32
+    // Cholesky per matrix, two CTAs per SM, log-determinant summed in fp64.
+    TRY((gemm_strided<double, float, float, float>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, Omega, M, MM, B, 1,
+                                                   (double)GPSA_OFF, 1)));
+    mirror_lower_kernel<<<grid_for(MM * B), 256, 0, st>>>(MM * B, M, Omega);
+    GPSA_LAUNCH_CHECK();
+    return gpsa_potrf_batched_f32_ld64(M, B, Omega, Ltril, half_logdet, info, st);
+  }
   // Omega = Osq Osq^T + 1e-5 I with fp64 accumulation, kept in fp64 for the factorisation
   // (symmetric: only the tiles that touch the lower triangle are computed; the fp32 copy mirrors them)
   TRY((gemm_strided<double, float, float, double>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, L64, M, MM, B, 1,
@@ -884,6 +934,30 @@ extern "C" int gpsa_omega_grad_tc(int M, int B, const float* Osq, const double* 
   return GPSA_OK;
 }
 
+// fp32 form of the same backward for factors that came from the fp32 branch of gpsa_omega_prepare:
+// Linv32, Y32: [B,M,M] fp32 scratch.
+extern "C" int gpsa_omega_grad_f32(int M, int B, const float* Osq, const float* Ltril, const float* Obar, const float* coef,
+                                   float* Linv32, float* Y32, float* Osq_bar, void* tc_ws, size_t tc_ws_bytes,
+                                   cudaStream_t st) {
+  if (M <= 0 || B <= 0) return GPSA_OK;
+  const long MM = (long)M * M;
+  if (tc_ws && M >= 32) {
+    TRY(gpsa_gemm_tc(M, M, M, B, Obar, M, MM, 1, Osq, M, MM, 0, Osq_bar, M, MM, 2.f, 0, 1, tc_ws, tc_ws_bytes, st));
+  } else {
+    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Obar, M, 1, MM, Osq, M, 1, MM, 0.0, Osq_bar, M, MM,
+                                                  B)));
+  }
+  if (coef) {
+    // ... + 2 coef[b] Omega^-1 Osq, Omega^-1 = Linv^T Linv (triangular K ranges trimmed in both products)
+    TRY(gpsa_trtri_batched_f32(M, B, Ltril, Linv32, st));
+    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 1.0, Linv32, M, 1, MM, Osq, M, 1, MM, 0.0, Y32, M, MM, B, 1,
+                                                  0.0, 0, nullptr, 0, 1)));
+    TRY((gemm_strided<float, float, float, float>(st, M, M, M, 2.0, Linv32, 1, M, MM, Y32, M, 1, MM, 1.0, Osq_bar, M, MM, B,
+                                                  1, 0.0, 0, coef, 1, 2)));
+  }
+  return GPSA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 #define DISPATCH_WARP(D, kind, CALL)                                                                        \
   do {                                                                                                      \
@@ -905,9 +979,14 @@ extern "C" int gpsa_warp_view_fwd(const gpsa_warp_fwd_args* a, cudaStream_t st) 
   const long n = a->n, MM = (long)M * M;
   if (n <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  TRY(gpsa_prior_prepare(a->kind, D, M, a->Z, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
-                         a->ws64, st));
-  {
+  if (a->kind == GPSA_KIND_EXTERNAL) {
+    if (!a->Kuu_ext || !a->Kuf_ext) return GPSA_ERR_ARG;
+    TRY(gpsa_prior_prepare_ext(M, a->Kuu_ext, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info, a->ws64, st));
+    cvt_kernel<float, double><<<grid_for((long)M * n), 256, 0, st>>>((long)M * n, a->Kuf_ext, a->B);
+    GPSA_LAUNCH_CHECK();
+  } else {
+    TRY(gpsa_prior_prepare(a->kind, D, M, a->Z, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
+                           a->ws64, st));
     dim3 grid(gpsa_cdiv(n, 256), M < 32 ? M : 32);
 #define KF(DD, KK) kuf64_kernel<DD, KK><<<grid, 256, 0, st>>>(M, n, a->Z, a->X, a->log_ls, a->log_var, a->B)
     DISPATCH_WARP(D, a->kind, KF);
@@ -986,6 +1065,15 @@ extern "C" int gpsa_warp_view_bwd(const gpsa_warp_bwd_args* a, cudaStream_t st) 
     kl_e_bwd_kernel<<<gpsa_cdiv(M * D, 256), 256, 0, st>>>(M, D, a->Ke, a->kl_bar, a->acc_Z, a->acc_dlt);
     GPSA_LAUNCH_CHECK();
   }
+  if (a->kind == GPSA_KIND_EXTERNAL) {
+    // the caller differentiates its own covariance function: hand back dLoss/dK_uf and dLoss/dK_uu
+    if (!a->Kuu_bar || !a->Kuf_bar) return GPSA_ERR_ARG;
+    cvt_kernel<double, float><<<grid_for((long)M * n), 256, 0, st>>>((long)M * n, a->C, a->Kuf_bar);
+    GPSA_LAUNCH_CHECK();
+    cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kbar, a->Kuu_bar);
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
+  }
 #define KB(DD, KK)                                                                                            \
   kuf64_bwd_kernel<DD, KK><<<rgrid, 256, 0, st>>>(M, n, chunk, a->Z, a->X, a->log_ls, a->log_var, a->C, a->acc_Z, \
                                                   a->acc_hyp)
@@ -1001,11 +1089,17 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   const long R = a->R;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine < 0 || a->engine > 2) return GPSA_ERR_UNSUPPORTED;
-  if (a->engine != 0 && (!gpsa_tc_supported(M) || !a->tc_ws || (a->engine == 1 && !a->Ltril))) return GPSA_ERR_UNSUPPORTED;
-  TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
-                         a->ws64, st));
-  TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
+  if (a->engine < 0 || a->engine > 1) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine == 1 && (!gpsa_tc_supported(M) || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
+  if (a->kind == GPSA_KIND_EXTERNAL) {
+    // user-supplied covariance function: K_uu comes in, and B already holds K_uf [M,R]
+    if (!a->Kuu_ext) return GPSA_ERR_ARG;
+    TRY(gpsa_prior_prepare_ext(M, a->Kuu_ext, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info, a->ws64, st));
+  } else {
+    TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
+                           a->ws64, st));
+    TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
+  }
   TRY((gemm_nn<double, double, float, float>(st, M, (int)R, M, 1.0, a->Kinv64, M, a->B, R, 0.0, a->A, R)));
   kq_kernel<<<gpsa_cdiv(R, 256), 256, 0, st>>>(M, R, a->A, a->B, a->log_var, a->kq);
   GPSA_LAUNCH_CHECK();
@@ -1020,10 +1114,6 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
     TRY(gpsa_feat_pack(M, L, a->Omega, a->W, st));
     gpsa_prof_begin(0, st);
     TRY(gpsa_quadform_fwd_f32(M, R, L, a->A, a->W, a->q2, st));
-    gpsa_prof_end(0, st);
-  } else if (a->engine == 1) {
-    gpsa_prof_begin(0, st);
-    TRY(gpsa_quadform_fwd_tc(M, R, L, a->A, a->Ltril, a->q2, a->tc_ws, a->tc_ws_bytes, st));
     gpsa_prof_end(0, st);
   } else {
     gpsa_prof_begin(0, st);
@@ -1044,7 +1134,7 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
   const long R = a->R, MM = (long)M * M;
   if (R <= 0 || L <= 0) return GPSA_OK;
   if (D < 1 || D > 3) return GPSA_ERR_ARG;
-  if (a->engine < 0 || a->engine > 2 || (a->engine != 0 && !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
+  if (a->engine < 0 || a->engine > 1 || (a->engine == 1 && !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
   double* Kbar = a->ws64;
   double* P = a->ws64 + MM;
   double* T1 = a->ws64 + 2 * MM;
@@ -1092,6 +1182,13 @@ extern "C" int gpsa_data_layer_bwd(const gpsa_data_bwd_args* a, cudaStream_t st)
     TRY((gemm_nn<double, double, double, double>(st, M, M, M, -0.5, T1, M, a->Kinv64, M, 1.0, Kbar, M, a->kl_bar)));
     TRY((gemm_nt<double, double, double, double>(st, M, M, L, -0.5, a->KD, L, a->KD, L, 1.0, Kbar, M, a->kl_bar)));
     TRY((axpy_dev<double, double>(st, MM, 0.5 * L, a->kl_bar, a->Kinv64, Kbar)));
+  }
+  if (a->kind == GPSA_KIND_EXTERNAL) {
+    // dLoss/dK_uf is C [M,R] as it stands; dLoss/dK_uu goes out in fp32
+    if (!a->Kuu_bar) return GPSA_ERR_ARG;
+    cvt_kernel<double, float><<<grid_for(MM), 256, 0, st>>>(MM, Kbar, a->Kuu_bar);
+    GPSA_LAUNCH_CHECK();
+    return GPSA_OK;
   }
   TRY(gpsa_kernel_matrix_bwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->C, a->acc_Gt, a->G_bar, nullptr,
                              a->acc_hyp, st));

@@ -45,7 +45,17 @@ constexpr int NSTAGE = 2;
 constexpr int OPER_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi/lo of both operands: 96 KB
 constexpr int RAW_BYTES = 8192;  // Omega-bar only: 4 row groups x 2 halves of [8 rows x 32 r] fp32, 128B-swizzled
 
-enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_SUMSQ = 3, MODE_FWD = 4 };
+enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_FWD = 3 };
+// tcgen05.mma adds into its fp32 TMEM accumulator with TRUNCATION: a chain of n dependent MMAs shrinks the magnitude of
+// the sum by ~0.3 ulp per instruction (measured: 24 000 chained MMAs -> -5e-4 relative in the C3 Omega-bar product,
+// 25 000 -> -3e-4 in the M = 512 forward; it would be ~2 % over the 1.2 M MMAs of a C5 Omega-bar tile).  A K loop longer
+// than KB_CHAIN K blocks (12 MMAs each: <= 1536 instructions, bias <= ~3e-5 of the chain's partial sum) is therefore
+// accumulated on TWO LEVELS: the MMAs of one chain run into TMEM columns [0, 256); when a chain completes, the epilogue
+// warps add it, in fp32 registers with round-to-nearest, into a second accumulator in TMEM columns [256, 512)
+// (tcgen05.ld / add / tcgen05.st), and only the last chain of an item goes out to memory.  The MMA warp waits for the
+// chain accumulator to be drained (~2 % of a chain's time).  Items with a single chain keep the two alternating
+// accumulator stages, i.e. the epilogue of one item runs under the MMAs of the next.
+constexpr int KB_CHAIN = 128;
 constexpr int N_GEN_WARPS = 8;
 // modes whose A operand is generated on the fly from TMA-staged raw rows of A (never stored)
 __host__ __device__ constexpr bool mode_gen(int mode) { return mode == MODE_OMEGA || mode == MODE_FWD; }
@@ -56,18 +66,17 @@ __host__ __device__ constexpr int gemm_threads(int mode) { return mode_gen(mode)
 struct GemmParams {
   int n_mt, n_nt, group_m, n_split, kblocks, kb_per;
   long Mrows, Ncols;  // logical output extent
-  float* C;           // TEST: C [Mrows, Ncols];  OMEGA: H [NF, L]
+  float* C;           // TEST: C [Mrows, Ncols];  OMEGA: H [NF, L];  FWD: q2 [R, L]
   long ldc;
-  int accumulate;     // OMEGA/TEST: 1 = atomicAdd (split-K), 0 = plain store
+  int accumulate;     // OMEGA/TEST/FWD: 1 = reductions into C (split-K), 0 = plain store
   int batch;          // TEST: > 0 -> operands are 3-D maps [batch, rows, K], item = (b, tile); C advances by sC per batch
   long sC;
   int trans_add;      // TEST: 1 -> C[col*ldc + row] += alpha*acc (transposed, read-modify-write), 0 -> C[row*ldc + col]
   float alpha;
-  const float* Amat;  // ALPHA/OMEGA: A [Mind, R]
+  const float* Amat;  // ALPHA/OMEGA/FWD: A [Mind, R]
   long R;
   int Mind, nb, nblk;
   float* Abar;        // ALPHA: [Mind, R], added to
-  int halves, L;      // SUMSQ: column tiles per gene, genes; C = q2 [Mrows, L], accumulated atomically
 };
 
 __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& ks) {
@@ -84,8 +93,28 @@ __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& 
   mt = m0 + w % gm;
 }
 
+// four consecutive floats, 16-byte aligned: one fire-and-forget L2 reduction (REDG.ADD.F32x4, round to nearest)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ int item_batch(const GemmParams& p, int item) {
   return p.batch > 0 ? item / (p.n_mt * p.n_nt * p.n_split) : 0;
+}
+
+// 32 accumulator columns of this thread's TMEM lane: the chain accumulator, plus the second-level accumulator when
+// `prev` (see KB_CHAIN)
+__device__ __forceinline__ void ld_acc32(uint32_t t_chain, uint32_t t_acc2, bool prev, uint32_t* v) {
+  tmem_ld32(t_chain, v);
+  if (prev) {
+    uint32_t w[32];
+    tmem_ld32(t_acc2, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+  } else {
+    tmem_ld_wait();
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -100,9 +129,9 @@ __device__ __forceinline__ int item_batch(const GemmParams& p, int item) {
 // Output tile = 128 rows r x 256 genes, K runs over the nblk 8x8 feature blocks (I, J) in feat.cu order.  Per K block
 // the producer stages the two 8-row groups a[I*8.., r0..r0+127] and a[J*8.., ...] (8 KB, fp32) and the 256 x 64 block of
 // the packed W^T (hi, lo); the generator warps (thread = row r, two threads per row) multiply, split to bf16 (hi, lo)
-// and write the swizzled K-major A operand.  Measured against fp64 the three-pass feature form is as accurate as the
-// ||a^T L||^2 form (2-3e-6 scale-relative at C3-like operands, tests/test_gpu_tc.py) and runs at the issue rate of the
-// plain GEMM core instead of the shrinking-N triangular stream.
+// and write the swizzled K-major A operand.  Measured against fp64 the three-pass feature form is at least as accurate
+// as the reference's own ||a^T L||^2 form evaluated the same way and runs at the issue rate of the plain
+// GEMM core.
 template <int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -142,6 +171,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = p.n_mt * p.n_nt * p.n_split * (p.batch > 0 ? p.batch : 1);
+  // two-level accumulation (see KB_CHAIN): every item of this launch has the same chain structure
+  const bool two_level = p.kb_per > KB_CHAIN;
 
   // Producer and MMA warps run converged (all lanes wait on the barriers, loop state is warp-uniform); only the
   // TMA / MMA issue is predicated on elect.sync, which keeps the single issuing thread's instruction stream short.
@@ -152,8 +183,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
-      // SUMSQ: column tile h of gene nt / halves; K rows below h * TN only meet structural zeros of the factor
-      const int kb0 = MODE == MODE_SUMSQ ? (nt % p.halves) * (TN / BK) : ks * p.kb_per;
+      const int kb0 = ks * p.kb_per;
       const int kb1 = min(p.kblocks, kb0 + p.kb_per);
       int grow[4] = {0, 0, 0, 0};  // MODE_OMEGA: first A row of the (I, J) index groups of the tile's two feature blocks
       if (MODE == MODE_OMEGA) {
@@ -166,6 +196,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
       int fI = 0, fJ = 0;  // MODE_FWD: feature block (I, J) of K block kb (feat.cu order: J runs from I to nb - 1)
+      if (MODE == MODE_FWD && kb0 > 0) decode_block(kb0, p.nb, fI, fJ);
       for (int kb = kb0; kb < kb1; ++kb) {
         uint8_t* st = smem + stage * STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
@@ -179,29 +210,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tma_load_2d(st + OPER_BYTES + c * 1024, &tmA_hi, &rawfull[stage], mt * TM + c * 32, fI * FB);
               tma_load_2d(st + OPER_BYTES + (4 + c) * 1024, &tmA_hi, &rawfull[stage], mt * TM + c * 32, fJ * FB);
             }
-          } else if (MODE == MODE_TEST && p.batch > 0) {
-            const int bz = item_batch(p, item);
-            tma_load_3d(st, &tmA_hi, &full[stage], kb * BK, mt * TM, bz);
-            tma_load_3d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM, bz);
-            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN, bz);
-            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN, bz);
-          } else if (MODE == MODE_SUMSQ) {
-            tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
-            tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
-            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, (nt % p.halves) * TN, nt / p.halves);
-            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, (nt % p.halves) * TN, nt / p.halves);
-          } else if (MODE != MODE_OMEGA) {
-            tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
-            tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
-          } else {
+          } else if (MODE == MODE_OMEGA) {
             mbar_arrive_expect_tx(&rawfull[stage], RAW_BYTES);
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq)
 #pragma unroll
               for (int h = 0; h < 2; ++h)
                 tma_load_2d(st + OPER_BYTES + (gq * 2 + h) * 1024, &tmA_hi, &rawfull[stage], kb * BK + h * 32, grow[gq]);
+          } else if (p.batch > 0) {
+            const int bz = item_batch(p, item);
+            tma_load_3d(st, &tmA_hi, &full[stage], kb * BK, mt * TM, bz);
+            tma_load_3d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM, bz);
+            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN, bz);
+            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN, bz);
+          } else {
+            tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
+            tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
           }
-          if (!(MODE == MODE_TEST && p.batch > 0) && MODE != MODE_SUMSQ) {
+          if (!(MODE == MODE_TEST && p.batch > 0)) {
             tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
             tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
           }
@@ -216,81 +242,93 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t idesc = make_idesc_bf16(TM, TN);
     const uint64_t desc0 = make_desc_sw128(smem_u32(smem));
     int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    uint32_t phase = 0;
+    uint32_t acc_ph[2] = {0, 0};  // completed uses of each accumulator stage, mod 2
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
-      const int kb0 = MODE == MODE_SUMSQ ? (nt % p.halves) * (TN / BK) : ks * p.kb_per;
+      const int kb0 = ks * p.kb_per;
       const int kb1 = min(p.kblocks, kb0 + p.kb_per);
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d = tmem_base + (uint32_t)acc * TN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+      // chains of at most KB_CHAIN K blocks; one-level items are a single chain on the alternating stage `acc`
+      for (int c0 = kb0; c0 < kb1; c0 += (two_level ? KB_CHAIN : p.kb_per)) {
+        const int c1 = two_level ? min(kb1, c0 + KB_CHAIN) : kb1;
+        mbar_wait(&tempty[acc], acc_ph[acc] ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
-          const uint64_t a_lo = a_hi + (A_TILE_BYTES >> 4);
-          const uint64_t b_hi = a_hi + (2 * A_TILE_BYTES >> 4);
-          const uint64_t b_lo = b_hi + (B_TILE_BYTES >> 4);
+        const uint32_t d = tmem_base + (uint32_t)acc * TN;
+        for (int kb = c0; kb < c1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
+            const uint64_t a_lo = a_hi + (A_TILE_BYTES >> 4);
+            const uint64_t b_hi = a_hi + (2 * A_TILE_BYTES >> 4);
+            const uint64_t b_lo = b_hi + (B_TILE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t off = (k * UMMA_K * 2) >> 4;
-            umma_bf16(d, a_hi + off, b_hi + off, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_bf16(d, a_lo + off, b_hi + off, idesc, 1u);
-            umma_bf16(d, a_hi + off, b_lo + off, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t off = (k * UMMA_K * 2) >> 4;
+              umma_bf16(d, a_hi + off, b_hi + off, idesc, (kb > c0 || k > 0) ? 1u : 0u);
+              umma_bf16(d, a_lo + off, b_hi + off, idesc, 1u);
+              umma_bf16(d, a_hi + off, b_lo + off, idesc, 1u);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
+        if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        acc_ph[acc] ^= 1;
+        if (!two_level) acc ^= 1;  // two-level: the chain accumulator is always stage 0, stage 1 is the second level
       }
-      if (elect_one()) umma_commit(&tfull[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue =====
     const int q = warp & 3;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_ph[2] = {0, 0};
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
-      const long row = (long)mt * TM + q * 32 + lane;
-      if (MODE == MODE_SUMSQ) {
-        // q2[row, gene] += sum over this tile's columns of T^2 (columns beyond Mp are zero rows of the packed factor)
-        float s0 = 0.f, s1 = 0.f;
+      const int kb0 = ks * p.kb_per;
+      const int kb1 = min(p.kblocks, kb0 + p.kb_per);
+      bool prev = false;  // the second-level accumulator holds the sum of this item's earlier chains
+      if (two_level) {
+        // every chain but the last: second level += chain (fp32 registers, round to nearest), release the chain stage
+        for (int c0 = kb0; c0 + KB_CHAIN < kb1; c0 += KB_CHAIN) {
+          mbar_wait(&tfull[0], acc_ph[0]);
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < TN / 32; ++c) {
-          if ((long)(nt % p.halves) * TN + c * 32 >= p.Ncols) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
-            s0 = fmaf(x, x, s0);
-            s1 = fmaf(y, y, s1);
+          for (int c = 0; c < TN / 32; ++c) {
+            uint32_t v[32];
+            ld_acc32(lane_base + c * 32, lane_base + TN + c * 32, prev, v);
+            tmem_st32(lane_base + TN + c * 32, v);
           }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[0]);
+          acc_ph[0] ^= 1;
+          prev = true;
         }
-        if (row < p.Mrows) atomicAdd(&p.C[row * p.ldc + nt / p.halves], s0 + s1);
-      } else if (MODE == MODE_TEST || MODE == MODE_OMEGA || MODE == MODE_FWD) {
+      }
+      mbar_wait(&tfull[acc], acc_ph[acc]);
+      tc_fence_after();
+      const uint32_t taddr = lane_base + (uint32_t)acc * TN;  // two-level: acc == 0
+      const uint32_t taddr2 = lane_base + TN;
+      const long row = (long)mt * TM + q * 32 + lane;
+      if (MODE == MODE_TEST || MODE == MODE_OMEGA || MODE == MODE_FWD) {
         float* Cb = p.C + (MODE == MODE_TEST ? (long)item_batch(p, item) * p.sC : 0);
         const float alpha = MODE == MODE_TEST ? p.alpha : 1.f;
-        const bool vec4 = (MODE == MODE_TEST || MODE == MODE_FWD) && !p.accumulate && !p.trans_add && (p.ldc & 3) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+        const bool al4 = !p.trans_add && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+        const bool vec4 = al4 && !p.accumulate;
+        const bool red4 = al4 && p.accumulate;
 #pragma unroll 1
         for (int c = 0; c < TN / 32; ++c) {
           const long col0 = (long)nt * TN + c * 32;
           if (col0 >= p.Ncols) break;  // warp-uniform
           uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
+          ld_acc32(taddr + c * 32, taddr2 + c * 32, prev, v);
           if (row < p.Mrows) {
             if (MODE == MODE_TEST && p.trans_add) {
 #pragma unroll
@@ -308,6 +346,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               for (int j = 0; j < 8; ++j)
                 dst[j] = make_float4(alpha * __uint_as_float(v[4 * j]), alpha * __uint_as_float(v[4 * j + 1]),
                                      alpha * __uint_as_float(v[4 * j + 2]), alpha * __uint_as_float(v[4 * j + 3]));
+            } else if (red4 && col0 + 32 <= p.Ncols) {
+              float* dst = Cb + row * p.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                red_add_v4(dst + 4 * j, alpha * __uint_as_float(v[4 * j]), alpha * __uint_as_float(v[4 * j + 1]),
+                           alpha * __uint_as_float(v[4 * j + 2]), alpha * __uint_as_float(v[4 * j + 3]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -330,9 +374,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           int I, J;
           decode_block(b, p.nb, I, J);
           uint32_t v[64];
-          tmem_ld32(taddr + bb * FBK, v);
-          tmem_ld32(taddr + bb * FBK + 32, v + 32);
-          tmem_ld_wait();
+          ld_acc32(taddr + bb * FBK, taddr2 + bb * FBK, prev, v);
+          ld_acc32(taddr + bb * FBK + 32, taddr2 + bb * FBK + 32, prev, v + 32);
           float aI[FB], aJ[FB], sJ[FB];
 #pragma unroll
           for (int t = 0; t < FB; ++t) {
@@ -366,8 +409,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      acc_ph[acc] ^= 1;
+      if (!two_level) acc ^= 1;
     }
   } else if (MODE == MODE_OMEGA && warp >= 8) {
     // ===== feature-operand generators =====
@@ -463,592 +506,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 // -------------------------------------------------------------------------------------------------
-// forward: q2[r,p] = || A_tile[r,:] L_p ||^2, A tile resident, L_p^T streamed in reverse K order
-// -------------------------------------------------------------------------------------------------
-// This kernel uses the 64-byte swizzle (K blocks of 32): the triangular factor is trimmed at 32-column
-// granularity (25 % less L2 -> shared traffic than 64-column blocks) and the ring has 6-8 slots, enough bytes in
-// flight to cover the TMA latency with the 112-128 KB resident A tile next to it.
-constexpr int FK = 32;                 // K elements per block
-constexpr int FROW = 64;               // bytes per operand row
-constexpr int FA_BYTES = TM * FROW;    // one A slab: 8 KB
-constexpr int FWD_MAXSLOT = 8;
-constexpr int FWD_MAXKB = 8;            // Mp <= 256
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
-struct FwdParams {
-  int Mp, nkb, L, n_rt, gsplit, genes_per, nslot, slot_bytes, ring_bytes;
-  long R;
-  float* q2;
-  int dbg;  // timing experiments only (GPSA_TC_DBG): 2 = no epilogue TMEM reads, 4 = no B loads
-};
-struct FwdMaps {
-  CUtensorMap a_hi, a_lo;    // At [R, Kp], box 32 x 128
-  CUtensorMap b_hi[5], b_lo[5];  // Lt [L, Mp, Kp], boxes 32 x {128, 64, 32, 16, 8} x 1 (8: pair kernel only)
-};
-
-// CL = CTAs per cluster.  CL = 2: the two CTAs of a cluster work on two different 128-row tiles against the SAME gene
-// stream; each K block of the factor is fetched from L2 once per cluster -- CTA 0 issues the hi half, CTA 1 the lo
-// half, both as TMA multicasts into the same ring slot of both CTAs -- which halves the L2 -> shared-memory traffic
-// that bounds the single-CTA kernel (6.8 TB/s at C3).  A slot is released by both MMA warps (multicast commit).
-//
-// GR ("gene ring"): the factor ring holds exactly ONE gene, K block kb at the fixed offset 2048 kb (kb + 1) with its own
-// full/empty barrier pair, sized to its triangular extent (32 (kb+1) rows instead of Mp).  Block (g, kb) overwrites
-// block (g-1, kb) as soon as that one is consumed, so a whole gene of loads (112 KB at M = 200) is in flight ahead of
-// the MMA warp -- the uniform 4-slot ring kept ~50 KB in flight and the kernel waited on TMA latency.  Used whenever
-// the A tile and one gene fit in shared memory together (M <= 208); otherwise the uniform ring of p.nslot slots.
-//
-// NTS ("TMEM A"): the hi half of the first NTS K steps of the resident A tile is also copied into the TMEM columns the
-// accumulators leave free ([Mp, Mp + 8 NTS)) by the epilogue warps at the start of a work item, and the hi*hi and
-// hi*lo passes of those K steps use the TS form of tcgen05.mma.  An SS-form MMA fetches its 4 KB A operand from
-// shared memory every time -- that fetch is the 58-cycle floor of the small-N steps -- while the TS form costs
-// N/2 + 10..19 cycles (tools/mma_probe.cu).  Measured at C3: NTS = 4 (the steps with N <= 64, where TS is cheaper per
-// MMA) 31.4 ms, NTS = 12 (everything the free TMEM columns hold; 96 KB less shared-memory traffic per (tile, gene))
-// 29.2 ms, NTS = 0 31.6 ms.  NTS is a template parameter: with a run-time count both forms of every MMA were emitted
-// and the issue loop spilled uniform registers (32.6 - 38 ms).
-template <int CL, bool GR, int NTS>
-__global__ void __launch_bounds__(256, 1) tc_qf_fwd_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA_hi = smem;                           // [nkb][128 x 32]
-  uint8_t* sA_lo = smem + p.nkb * FA_BYTES;        // [nkb][128 x 32]
-  uint8_t* ring = smem + 2 * p.nkb * FA_BYTES;     // [nslot][hi: Mp x 32 | lo: Mp x 32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ring_bytes);
-  uint64_t* full = bars;                    // [FWD_MAXSLOT]
-  uint64_t* empty = bars + FWD_MAXSLOT;     // [FWD_MAXSLOT]
-  uint64_t* tfull = bars + 2 * FWD_MAXSLOT; // [2]
-  uint64_t* tempty = tfull + 2;             // [2]
-  uint64_t* a_full = tempty + 2;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* ta_full = a_empty + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_full + 1);
-
-  // warp index through a shuffle: provably warp-uniform, so the role branches below are convergent for the compiler
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm.a_hi);
-    prefetch_tmap(&tm.a_lo);
-    for (int i = 0; i < 4; ++i) { prefetch_tmap(&tm.b_hi[i]); prefetch_tmap(&tm.b_lo[i]); }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    mbar_init(ta_full, 4);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
-  const int n_rp = (p.n_rt + CL - 1) / CL;  // row-tile groups: CTA `crank` of a cluster takes tile rp * CL + crank
-  const int n_items = n_rp * p.gsplit;
-  const int Mp = p.Mp, nkb = p.nkb;
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
-
-  // Producer and MMA warps run their loops CONVERGED and every barrier wait ends in a full-mask vote
-  // (mbar_wait_u), so the compiler keeps the loop state -- ring position, descriptors, barrier addresses -- in
-  // UNIFORM registers; the K loop of the MMA warp is fully unrolled, so the A-tile descriptors and the
-  // instruction descriptors (N shrinks with K) are immediates.  What is left per K block in the issuing
-  // thread is ~45 uniform-datapath instructions for 6 UTCHMMA; before this the same block cost ~90 instructions
-  // with a dozen R2UR round trips and the tensor pipe idled 40 % of the time waiting for the issue.
-  if (warp == 0) {
-    int slot = 0;
-    uint32_t sphase = 0, aphase = 0;
-    const bool leader = elect_one();
-    for (int item = cid; item < n_items; item += ncl) {
-      const int rt = (item % n_rp) * CL + crank, gs = item / n_rp;  // rt may be >= n_rt in the last group: zero tile
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait_u(a_empty, aphase ^ 1);
-      if (leader) {
-        mbar_arrive_expect_tx(a_full, 2 * nkb * FA_BYTES);
-        for (int kb = 0; kb < nkb; ++kb) {
-          tma_load_2d(sA_hi + kb * FA_BYTES, &tm.a_hi, a_full, kb * FK, rt * TM);
-          tma_load_2d(sA_lo + kb * FA_BYTES, &tm.a_lo, a_full, kb * FK, rt * TM);
-        }
-      }
-      aphase ^= 1;
-      for (int g = g0; g < g1; ++g) {
-        for (int kb = nkb - 1; kb >= 0; --kb) {
-          const int nrows = min(FK * (kb + 1), Mp);  // T columns k that meet a non-zero L[i,k], i in this K block
-          if (GR) slot = kb;
-          mbar_wait_u(&empty[slot], sphase ^ 1);
-          if (leader) {
-            uint8_t* dst = GR ? ring + 2048 * kb * (kb + 1) : ring + slot * p.slot_bytes;
-            const int half_bytes = GR ? nrows * FROW : (p.slot_bytes >> 1);
-            if (p.dbg & 4) {
-              mbar_arrive(&full[slot]);
-            } else {
-              mbar_arrive_expect_tx(&full[slot], 2 * nrows * FROW);  // both halves, whoever issues them
-              int row = 0;
-#pragma unroll
-              for (int hsel = 0; hsel < 4; ++hsel) {
-                const int hgt = 128 >> hsel;
-                for (; row + hgt <= nrows; row += hgt) {
-                  if (CL == 1) {
-                    tma_load_3d(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g);
-                    tma_load_3d(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g);
-                  } else if (crank == 0) {
-                    tma_load_3d_mc(dst + row * FROW, &tm.b_hi[hsel], &full[slot], kb * FK, row, g, MC_MASK);
-                  } else {
-                    tma_load_3d_mc(dst + half_bytes + row * FROW, &tm.b_lo[hsel], &full[slot], kb * FK, row, g, MC_MASK);
-                  }
-                }
-              }
-            }
-          }
-          if (!GR && ++slot == p.nslot) { slot = 0; sphase ^= 1; }
-        }
-        if (GR) sphase ^= 1;  // every barrier of the gene ring completes one phase per gene
-      }
-    }
-    if (CL > 1) {
-      // drain: the last use of every slot has been released by BOTH MMA warps, i.e. no multicast commit of the peer
-      // is still on its way to this CTA's barriers when it exits
-      const int ns = GR ? nkb : p.nslot;
-      if (GR) slot = 0;
-      for (int i = 0; i < ns; ++i) {
-        mbar_wait_u(&empty[slot], sphase ^ 1);
-        if (GR) ++slot;
-        else if (++slot == p.nslot) { slot = 0; sphase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    int slot = 0, acc = 0;
-    uint32_t sphase = 0, acc_phase = 0, aphase = 0;
-    // descriptors as (low word, constant high word): the low word carries the start address, so stepping through
-    // the tile is 32-bit arithmetic
-    const uint32_t DHI = (uint32_t)(make_desc_sw64(0) >> 32);
-    const uint32_t a_hi0 = (uint32_t)make_desc_sw64(smem_u32(sA_hi));
-    const uint32_t a_lo0 = (uint32_t)make_desc_sw64(smem_u32(sA_lo));
-    const uint32_t ring0 = (uint32_t)make_desc_sw64(smem_u32(ring));
-    const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, half16 = slot16 >> 1;  // slot / hi -> lo stride, descriptor units
-    constexpr uint32_t idesc0 = make_idesc_bf16(TM, 0);
-    const bool leader = elect_one();
-    for (int item = cid; item < n_items; item += ncl) {
-      const int gs = item / n_rp;
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait_u(a_full, aphase);
-      if (NTS > 0) mbar_wait_u(ta_full, aphase);  // the epilogue warps have copied A_hi into TMEM for this item
-      aphase ^= 1;
-      tc_fence_after();
-      for (int g = g0; g < g1; ++g) {
-        mbar_wait_u(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)acc * TN;
-#pragma unroll
-        for (int kb = FWD_MAXKB - 1; kb >= 0; --kb) {
-          if (kb >= nkb) continue;  // uniform
-          if (GR) slot = kb;
-          mbar_wait_u(&full[slot], sphase);
-          tc_fence_after();
-          const uint32_t b_hi = GR ? ring0 + (uint32_t)((2048 * kb * (kb + 1)) >> 4) : ring0 + (uint32_t)slot * slot16;
-          const uint32_t b_lo = b_hi + (GR ? (uint32_t)((kb + 1 < nkb ? FK * (kb + 1) : Mp) * FROW) >> 4 : half16);
-          if (leader) {
-#pragma unroll
-            for (int k = FK / UMMA_K - 1; k >= 0; --k) {
-              const int k0 = kb * FK + k * UMMA_K;
-              if (k0 >= Mp) continue;
-              // N = k0 + 16: columns beyond it only meet structural zeros of the factor.  The first MMA of a gene
-              // (k0 = Mp - 16) therefore has N = Mp and initialises every accumulator column.
-              const uint32_t idesc = idesc0 | ((uint32_t)((k0 + UMMA_K) >> 3) << 17);
-              const uint32_t accum = (k0 != Mp - UMMA_K) ? 1u : 0u;
-              const uint32_t aoff = (uint32_t)((kb * FA_BYTES) >> 4) + (uint32_t)(k * UMMA_K * 2 >> 4);
-              const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
-              const int ks = kb * (FK / UMMA_K) + k;
-              if (ks < NTS) {
-                const uint32_t a_t = tmem_base + (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));  // NTS > 6: Mp <= 208
-                umma_bf16_ts(d, a_t, desc64(b_hi + boff, DHI), idesc, accum);
-                umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-                umma_bf16_ts(d, a_t, desc64(b_lo + boff, DHI), idesc, 1u);
-              } else {
-                umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
-                umma_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-                umma_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
-              }
-            }
-            if (CL == 1) umma_commit(&empty[slot]);
-            else umma_commit_mc(&empty[slot], MC_MASK);
-          }
-          if (!GR && ++slot == p.nslot) { slot = 0; sphase ^= 1; }
-        }
-        if (GR) sphase ^= 1;
-        if (leader) umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-      if (leader) umma_commit(a_empty);  // the resident A tile may be overwritten once every MMA of this item is done
-    }
-  } else if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0, ta_phase = 0;
-    const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
-    for (int item = cid; item < n_items; item += ncl) {
-      const int rt = (item % n_rp) * CL + crank, gs = item / n_rp;
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      const long row = (long)rt * TM + q * 32 + lane;
-      if (NTS > 0) {
-        // every MMA of the previous item has completed (its last tfull was consumed above), so the TMEM copy of
-        // A_hi can be replaced: thread = row, 32 bytes (one K step) per tcgen05.st out of the swizzled smem tile
-        mbar_wait(a_full, ta_phase);
-        ta_phase ^= 1;
-        const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
-#pragma unroll
-        for (int ks = 0; ks < NTS; ++ks) {
-          const uint8_t* src = sA_hi + (ks >> 1) * FA_BYTES + rl * FROW;
-          const int c = (ks & 1) * 2;
-          const uint4 v0 = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
-          const uint4 v1 = *reinterpret_cast<const uint4*>(src + (((c + 1) ^ sw) << 4));
-          const uint32_t col = (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
-          tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + col, v0, v1);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ta_full);
-      }
-      for (int g = g0; g < g1; ++g) {
-        mbar_wait(&tfull[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < ((p.dbg & 2) ? 0 : n32); ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
-            s0 = fmaf(x, x, s0);
-            s1 = fmaf(y, y, s1);
-          }
-        }
-        if (rem16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + n32 * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
-            s0 = fmaf(x, x, s0);
-            s1 = fmaf(y, y, s1);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (row < p.R) p.q2[row * p.L + g] = s0 + s1;
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CL > 1) cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
-// forward, cta_group::2 ("pair") variant -- EXPERIMENTAL, selected with GPSA_FWD_PAIR=1 (Mp = 208 only)
-// -------------------------------------------------------------------------------------------------
-// A 2-CTA cluster owns 256 rows: each CTA keeps its own 128-row A tile (shared memory hi + lo, TMEM copy of A_hi for
-// NTS K steps) and its own half of the accumulator rows in its own TMEM, but only HALF of every factor block: with
-// N = 32 (kb + 1) for both K steps of block kb, CTA 0 stores rows [0, N/2) and CTA 1 rows [N/2, N) of the block at the
-// same ring offset (1024 kb (kb+1)) -- so the ring holds TWO genes in the space one took.  The leader's single thread issues tcgen05.mma.cta_group::2 (M = 256); the peer's
-// TMA completes on the LEADER's `full` barrier; `empty`, `tfull`, `a_empty` are multicast commits to both CTAs;
-// `tempty` and `ta_full` of the leader collect the arrivals of both CTAs' epilogue warps (remote mbarrier.arrive).
-// Per SM the TMA write stream into shared memory is halved (56 KB per gene instead of 112 KB), which is what bounds
-// the single-CTA kernel.
-template <int NTS>
-__global__ void __launch_bounds__(256, 1) tc_qf_fwd_pair_kernel(const __grid_constant__ FwdMaps tm, const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA_hi = smem;
-  uint8_t* sA_lo = smem + p.nkb * FA_BYTES;
-  uint8_t* ring = smem + 2 * p.nkb * FA_BYTES;  // block kb: [hi: N/2 x 32 | lo: N/2 x 32] at 1024 kb (kb+1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ring_bytes);
-  // the ring holds TWO genes (parity gp of the running gene count): barrier index gp * 8 + kb
-  uint64_t* full = bars;                     // [16] leader only: both CTAs' TMA bytes
-  uint64_t* empty = bars + 2 * FWD_MAXSLOT;  // [16] per CTA, multicast commit of the leader
-  uint64_t* tfull = bars + 4 * FWD_MAXSLOT;  // [2]  per CTA, multicast commit
-  uint64_t* tempty = tfull + 2;              // [2]  leader only: 4 warps x 2 CTAs
-  uint64_t* a_full = tempty + 2;             // per CTA (own A tile)
-  uint64_t* a_empty = a_full + 1;            // per CTA, multicast commit
-  uint64_t* ta_full = a_empty + 1;           // leader only: 4 warps x 2 CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_full + 1);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm.a_hi);
-    prefetch_tmap(&tm.a_lo);
-    for (int i = 0; i < 5; ++i) { prefetch_tmap(&tm.b_hi[i]); prefetch_tmap(&tm.b_lo[i]); }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2 * FWD_MAXSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    mbar_init(ta_full, 8);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc2(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int crank = (int)cluster_ctarank();
-  const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
-  const int n_rp = (p.n_rt + 1) / 2;
-  const int n_items = n_rp * p.gsplit;
-  const int Mp = p.Mp, nkb = p.nkb;
-  const int gene_bytes = p.ring_bytes >> 1;  // one gene of this CTA's half blocks (a multiple of 1024)
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs): own A tile, own half of every factor block =====
-    uint32_t aphase = 0;
-    int gc = 0;  // genes produced so far: ring half gc & 1, barrier phase (gc >> 1) & 1
-    const bool leader = elect_one();
-    for (int item = cid; item < n_items; item += ncl) {
-      const int rt = (item % n_rp) * 2 + crank, gs = item / n_rp;
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait_u(a_empty, aphase ^ 1);
-      if (leader) {
-        mbar_arrive_expect_tx(a_full, 2 * nkb * FA_BYTES);
-        for (int kb = 0; kb < nkb; ++kb) {
-          tma_load_2d(sA_hi + kb * FA_BYTES, &tm.a_hi, a_full, kb * FK, rt * TM);
-          tma_load_2d(sA_lo + kb * FA_BYTES, &tm.a_lo, a_full, kb * FK, rt * TM);
-        }
-      }
-      aphase ^= 1;
-      for (int g = g0; g < g1; ++g, ++gc) {
-        const int gp = gc & 1;
-        const uint32_t sphase = (uint32_t)(gc >> 1) & 1u;
-        for (int kb = nkb - 1; kb >= 0; --kb) {
-          const int nrows = min(FK * (kb + 1), Mp), hrows = nrows >> 1;
-          const int bi = gp * FWD_MAXSLOT + kb;
-          mbar_wait_u(&empty[bi], sphase ^ 1);
-          if (leader) {
-            if (crank == 0) mbar_arrive_expect_tx(&full[bi], 2 * nrows * FROW);  // hi + lo, both CTAs' halves
-            const uint32_t fbar = cluster_addr_of(&full[bi], 0);
-            uint8_t* dst = ring + gp * gene_bytes + 1024 * kb * (kb + 1);
-            const int r0 = crank * hrows;
-            int row = 0;
-#pragma unroll
-            for (int hsel = 0; hsel < 5; ++hsel) {
-              const int hgt = 128 >> hsel;
-              for (; row + hgt <= hrows; row += hgt) {
-                tma_load_3d_2sm(dst + row * FROW, &tm.b_hi[hsel], fbar, kb * FK, r0 + row, g);
-                tma_load_3d_2sm(dst + (hrows + row) * FROW, &tm.b_lo[hsel], fbar, kb * FK, r0 + row, g);
-              }
-            }
-          }
-        }
-      }
-    }
-    // drain (as if two more genes were produced): the last multicast commits of the leader have arrived here
-    // before this CTA exits
-    for (int i = 0; i < 2; ++i, ++gc)
-      for (int kb = 0; kb < nkb; ++kb) mbar_wait_u(&empty[(gc & 1) * FWD_MAXSLOT + kb], ((uint32_t)(gc >> 1) & 1u) ^ 1u);
-  } else if (warp == 1 && crank == 0) {
-    // ===== MMA issuer (pair leader only) =====
-    int acc = 0, gc = 0;
-    uint32_t acc_phase = 0, aphase = 0;
-    const uint32_t DHI = (uint32_t)(make_desc_sw64(0) >> 32);
-    const uint32_t a_hi0 = (uint32_t)make_desc_sw64(smem_u32(sA_hi));
-    const uint32_t a_lo0 = (uint32_t)make_desc_sw64(smem_u32(sA_lo));
-    const uint32_t ring0 = (uint32_t)make_desc_sw64(smem_u32(ring));
-    constexpr uint32_t idesc0 = make_idesc_bf16(2 * TM, 0);
-    const bool leader = elect_one();
-    for (int item = cid; item < n_items; item += ncl) {
-      const int gs = item / n_rp;
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      mbar_wait_u(a_full, aphase);
-      mbar_wait_u(ta_full, aphase);  // both CTAs: A tile landed and A_hi copied into TMEM
-      aphase ^= 1;
-      tc_fence_after();
-      for (int g = g0; g < g1; ++g, ++gc) {
-        const int gp = gc & 1;
-        const uint32_t sphase = (uint32_t)(gc >> 1) & 1u;
-        const uint32_t ringg = ring0 + (uint32_t)((gp * gene_bytes) >> 4);
-        mbar_wait_u(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)acc * TN;
-#pragma unroll
-        for (int kb = FWD_MAXKB - 1; kb >= 0; --kb) {
-          if (kb >= nkb) continue;
-          const int bi = gp * FWD_MAXSLOT + kb;
-          mbar_wait_u(&full[bi], sphase);
-          tc_fence_after();
-          const int nrows = (kb + 1 < nkb) ? FK * (kb + 1) : Mp;
-          const uint32_t b_hi = ringg + (uint32_t)((1024 * kb * (kb + 1)) >> 4);
-          const uint32_t b_lo = b_hi + ((uint32_t)((nrows >> 1) * FROW) >> 4);
-          const uint32_t idesc = idesc0 | ((uint32_t)(nrows >> 3) << 17);  // same N for both K steps of the block
-          if (leader) {
-#pragma unroll
-            for (int k = FK / UMMA_K - 1; k >= 0; --k) {
-              const int k0 = kb * FK + k * UMMA_K;
-              if (k0 >= Mp) continue;
-              const uint32_t accum = (k0 != Mp - UMMA_K) ? 1u : 0u;
-              const uint32_t aoff = (uint32_t)((kb * FA_BYTES) >> 4) + (uint32_t)(k * UMMA_K * 2 >> 4);
-              const uint32_t boff = (uint32_t)(k * UMMA_K * 2 >> 4);
-              const int ks = kb * (FK / UMMA_K) + k;
-              if (ks < NTS) {
-                const uint32_t a_t = tmem_base + (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
-                umma2_bf16_ts(d, a_t, desc64(b_hi + boff, DHI), idesc, accum);
-                umma2_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-                umma2_bf16_ts(d, a_t, desc64(b_lo + boff, DHI), idesc, 1u);
-              } else {
-                umma2_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, accum);
-                umma2_bf16(d, desc64(a_lo0 + aoff, DHI), desc64(b_hi + boff, DHI), idesc, 1u);
-                umma2_bf16(d, desc64(a_hi0 + aoff, DHI), desc64(b_lo + boff, DHI), idesc, 1u);
-              }
-            }
-            umma2_commit_mc(&empty[bi]);
-          }
-        }
-        if (leader) umma2_commit_mc(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-      if (leader) umma2_commit_mc(a_empty);
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue (both CTAs): own TMEM rows -> q2; arrivals go to the LEADER's barriers =====
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0, ta_phase = 0;
-    const int n32 = Mp / 32, rem16 = (Mp % 32) / 16;
-    const uint32_t ta_leader = cluster_addr_of(ta_full, 0);
-    const uint32_t te_leader[2] = {cluster_addr_of(&tempty[0], 0), cluster_addr_of(&tempty[1], 0)};
-    for (int item = cid; item < n_items; item += ncl) {
-      const int rt = (item % n_rp) * 2 + crank, gs = item / n_rp;
-      const int g0 = gs * p.genes_per, g1 = min(p.L, g0 + p.genes_per);
-      const long row = (long)rt * TM + q * 32 + lane;
-      if (NTS > 0) {
-        mbar_wait(a_full, ta_phase);
-        ta_phase ^= 1;
-        const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
-#pragma unroll
-        for (int ks = 0; ks < NTS; ++ks) {
-          const uint8_t* src = sA_hi + (ks >> 1) * FA_BYTES + rl * FROW;
-          const int c = (ks & 1) * 2;
-          const uint4 v0 = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
-          const uint4 v1 = *reinterpret_cast<const uint4*>(src + (((c + 1) ^ sw) << 4));
-          const uint32_t col = (uint32_t)(ks < 6 ? Mp + 8 * ks : TN + Mp + 8 * (ks - 6));
-          tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + col, v0, v1);
-        }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ta_leader);
-      for (int g = g0; g < g1; ++g) {
-        mbar_wait(&tfull[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < n32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
-            s0 = fmaf(x, x, s0);
-            s1 = fmaf(y, y, s1);
-          }
-        }
-        if (rem16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + n32 * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float x = __uint_as_float(v[j]), y = __uint_as_float(v[j + 1]);
-            s0 = fmaf(x, x, s0);
-            s1 = fmaf(y, y, s1);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(te_leader[acc]);
-        if (row < p.R) p.q2[row * p.L + g] = s0 + s1;
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc2(tmem_base, 512);
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
 // operand packing (HBM-bound pre-passes): fp32 -> bf16 (hi, lo), K-major, zero padded
 // -------------------------------------------------------------------------------------------------
-// out[r, i] = A[i, r]     A [M, R] -> [R, Kp]
-__global__ void pack_At_kernel(int M, long R, int Kp, const float* __restrict__ A, __nv_bfloat16* __restrict__ hi,
-                               __nv_bfloat16* __restrict__ lo) {
-  __shared__ float t[32][33];
-  const long r0 = (long)blockIdx.x * 32;
-  const int i0 = blockIdx.y * 32;
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
-    const int i = i0 + yy;
-    const long r = r0 + threadIdx.x;
-    t[yy][threadIdx.x] = (i < M && r < R) ? A[(long)i * R + r] : 0.f;
-  }
-  __syncthreads();
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
-    const long r = r0 + yy;
-    const int i = i0 + threadIdx.x;
-    if (r < R && i < Kp) {
-      __nv_bfloat16 h, l;
-      split_one(t[threadIdx.x][yy], h, l);
-      hi[r * Kp + i] = h;
-      lo[r * Kp + i] = l;
-    }
-  }
-}
-
-// out[p, k, i] = Ltril[p, i, k]   [L, M, M] -> [L, Mp, Kp]
-__global__ void pack_Lt_kernel(int M, int Mp, int Kp, const float* __restrict__ Ltril, __nv_bfloat16* __restrict__ hi,
-                               __nv_bfloat16* __restrict__ lo) {
-  __shared__ float t[32][33];
-  const int p = blockIdx.z;
-  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-  const float* src = Ltril + (long)p * M * M;
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
-    const int i = i0 + yy, k = k0 + threadIdx.x;
-    t[yy][threadIdx.x] = (i < M && k < M) ? src[(long)i * M + k] : 0.f;
-  }
-  __syncthreads();
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
-    const int k = k0 + yy, i = i0 + threadIdx.x;
-    if (k < Mp && i < Kp) {
-      __nv_bfloat16 h, l;
-      split_one(t[threadIdx.x][yy], h, l);
-      const long o = ((long)p * Mp + k) * Kp + i;
-      hi[o] = h;
-      lo[o] = l;
-    }
-  }
-}
-
 // Wt[(b, il, jl), p] = c_b Omega[p, i, j]   (c = 1 on diagonal blocks, 2 above; same ordering as feat.cu)
 __global__ void __launch_bounds__(256) pack_Wt_kernel(int M, int L, int Lp, const float* __restrict__ Omega,
                                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -1270,17 +729,6 @@ int sm_count() {
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline long rup(long x, long m) { return (x + m - 1) / m * m; }
 
-struct FwdLayout { int Mp, Kp, nkb; size_t at, lt, total; };
-FwdLayout fwd_layout(int M, long R, int L) {
-  FwdLayout f;
-  f.Mp = (int)rup(M, 16);
-  f.nkb = (f.Mp + FK - 1) / FK;
-  f.Kp = (int)rup(f.Mp, 64);  // 128-byte row pitch
-  f.at = al256((size_t)R * f.Kp * 2);
-  f.lt = al256((size_t)L * f.Mp * f.Kp * 2);
-  f.total = 2 * f.at + 2 * f.lt;
-  return f;
-}
 struct FeatFwdLayout { long NF; size_t wg, apad, total; };
 FeatFwdLayout featfwd_layout(int M, long R, int L) {
   FeatFwdLayout f;
@@ -1348,8 +796,8 @@ extern "C" size_t gpsa_gemm_tc_ws_bytes(long Mr, long Nc, int K, int batch);
 // products and the four plain GEMMs (predictive mean, delta-bar, A-bar += delta Fbar^T, Omega-bar Omega_sqt)
 extern "C" size_t gpsa_quadform_tc_ws_bytes(int M, long R, int L) {
   if (M <= 0 || R <= 0 || L <= 0) return 0;
-  size_t m = fwd_layout(M, R, L).total;
-  const size_t c[] = {featfwd_layout(M, R, L).total, alpha_layout(M, R, L).total, omega_layout(M, R, L).total,
+  size_t m = featfwd_layout(M, R, L).total;
+  const size_t c[] = {alpha_layout(M, R, L).total, omega_layout(M, R, L).total,
                       gpsa_gemm_tc_ws_bytes(R, L, M, 1),
                       gpsa_gemm_tc_ws_bytes(M, L, (int)(R > 2000000000L ? 2000000000L : R), 1), gpsa_gemm_tc_ws_bytes(R, M, L, 1),
                       gpsa_gemm_tc_ws_bytes(M, M, M, L)};
@@ -1469,210 +917,6 @@ extern "C" int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, 
   return launch_gemm<MODE_TEST>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
 }
 
-extern "C" int gpsa_quadform_fwd_tc(int M, long R, int L, const float* A, const float* Ltril, float* q2, void* ws,
-                                    size_t ws_bytes, cudaStream_t st) {
-  if (M <= 0 || R <= 0 || L <= 0) return GPSA_OK;
-  if (!gpsa_tc_supported(M)) return GPSA_ERR_UNSUPPORTED;
-  const FwdLayout f = fwd_layout(M, R, L);
-  if (ws_bytes < f.total) return GPSA_ERR_ARG;
-  uint8_t* w = static_cast<uint8_t*>(ws);
-  __nv_bfloat16 *at_hi = (__nv_bfloat16*)w, *at_lo = (__nv_bfloat16*)(w + f.at), *lt_hi = (__nv_bfloat16*)(w + 2 * f.at),
-                *lt_lo = (__nv_bfloat16*)(w + 2 * f.at + f.lt);
-  {
-    dim3 grid(gpsa_cdiv(R, 32), f.Kp / 32), block(32, 8);
-    pack_At_kernel<<<grid, block, 0, st>>>(M, R, f.Kp, A, at_hi, at_lo);
-    GPSA_LAUNCH_CHECK();
-    dim3 grid2(f.Kp / 32, gpsa_cdiv(f.Mp, 32), L);
-    pack_Lt_kernel<<<grid2, block, 0, st>>>(M, f.Mp, f.Kp, Ltril, lt_hi, lt_lo);
-    GPSA_LAUNCH_CHECK();
-  }
-  if (f.Mp > TN) {
-    // M > 256 (C5: M = 512): the A tile (128 x Mp, hi + lo) no longer fits in shared memory next to a factor ring, so
-    // both operands are streamed through the generic 128 x 256 GEMM core: one item = (row tile, gene, 256-column
-    // slice of T), K blocks below the slice skipped (structural zeros), sum of squares out of TMEM added to q2.
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (make_tmap_2d(&ta_hi, at_hi, f.Mp, R, f.Kp, TM) || make_tmap_2d(&ta_lo, at_lo, f.Mp, R, f.Kp, TM)) return GPSA_ERR_CUDA;
-    const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
-    const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
-    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)TN, 1};
-    if (make_tmap(&tb_hi, lt_hi, 3, dims, str, box) || make_tmap(&tb_lo, lt_lo, 3, dims, str, box)) return GPSA_ERR_CUDA;
-    GemmParams g = {};
-    g.halves = gpsa_cdiv(f.Mp, TN);
-    g.L = L;
-    g.n_mt = gpsa_cdiv(R, TM);
-    g.n_nt = L * g.halves;
-    g.group_m = g.n_mt < 32 ? g.n_mt : 32;
-    g.kblocks = gpsa_cdiv(f.Mp, BK);
-    set_split(g, 1);
-    g.Mrows = R; g.Ncols = f.Mp; g.C = q2; g.ldc = L;
-    if (cudaMemsetAsync(q2, 0, sizeof(float) * (size_t)R * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
-    return launch_gemm<MODE_SUMSQ>(ta_hi, ta_lo, tb_hi, tb_lo, g, st);
-  }
-  FwdMaps maps;
-  {
-    const uint64_t dims[2] = {(uint64_t)f.Mp, (uint64_t)R}, str[1] = {(uint64_t)f.Kp * 2};
-    const uint32_t box[2] = {(uint32_t)FK, (uint32_t)TM};
-    if (make_tmap(&maps.a_hi, at_hi, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) ||
-        make_tmap(&maps.a_lo, at_lo, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
-      return GPSA_ERR_CUDA;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)f.Mp, (uint64_t)f.Mp, (uint64_t)L};
-    const uint64_t str[2] = {(uint64_t)f.Kp * 2, (uint64_t)f.Mp * f.Kp * 2};
-    for (int hsel = 0; hsel < 5; ++hsel) {
-      const uint32_t box[3] = {(uint32_t)FK, (uint32_t)(128 >> hsel), 1};
-      if (make_tmap(&maps.b_hi[hsel], lt_hi, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) ||
-          make_tmap(&maps.b_lo[hsel], lt_lo, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
-        return GPSA_ERR_CUDA;
-    }
-  }
-  FwdParams p = {};
-  p.Mp = f.Mp; p.nkb = f.nkb; p.L = L; p.R = R; p.q2 = q2;
-#ifdef GPSA_DEBUG  // timing experiments only (skip the epilogue / the factor loads): never in the shipped library
-  {
-    static const int dbg = [] { const char* e = getenv("GPSA_TC_DBG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
-  }
-#endif
-  p.n_rt = gpsa_cdiv(R, TM);
-  // split the gene range when there are too few row tiles to fill the machine
-  p.gsplit = 1;
-  if (p.n_rt < sm_count()) {
-    p.gsplit = (sm_count() + p.n_rt - 1) / p.n_rt;
-    if (p.gsplit > L) p.gsplit = L;
-  }
-  p.genes_per = (L + p.gsplit - 1) / p.gsplit;
-  p.gsplit = (L + p.genes_per - 1) / p.genes_per;
-  p.slot_bytes = 2 * f.Mp * FROW;  // one K block: hi rows, then lo rows
-  const int fixed = 2 * f.nkb * FA_BYTES + 1024 + 256;
-  // gene ring: block kb at 2048 kb (kb+1), the top block (Mp rows) last
-  static const int want_gr = [] { const char* e = getenv("GPSA_FWD_GENE_RING"); return e ? atoi(e) : 1; }();
-  const int gr_bytes = 2048 * (f.nkb - 1) * f.nkb + 2 * f.Mp * FROW;
-  const bool gr = want_gr && fixed + gr_bytes <= 232448;
-  if (gr) {
-    p.nslot = f.nkb;
-    p.ring_bytes = gr_bytes;
-  } else {
-    p.nslot = (232448 - fixed) / p.slot_bytes;
-    if (p.nslot > FWD_MAXSLOT) p.nslot = FWD_MAXSLOT;
-    if (p.nslot < 2) return GPSA_ERR_UNSUPPORTED;
-    p.ring_bytes = p.nslot * p.slot_bytes;
-  }
-  const int smem_bytes = fixed + p.ring_bytes;
-  static int attr_bytes_dev[GPSA_MAX_DEVICES] = {};
-  int& attr_bytes = attr_bytes_dev[gpsa_dev()];
-  if (smem_bytes > attr_bytes) {
-    if (cudaFuncSetAttribute(tc_qf_fwd_kernel<1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<2, true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_qf_fwd_kernel<1, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-      return GPSA_ERR_CUDA;
-    attr_bytes = smem_bytes;
-  }
-  // A_hi in TMEM (gene-ring variants): 12 of the 13 K steps when Mp = 208 (both column gaps, 96 columns), else the
-  // first 4 K steps if 32 columns are free next to the accumulator.  GPSA_FWD_TMEM_A=0/4 overrides (experiments).
-  static const int want_ta = [] { const char* e = getenv("GPSA_FWD_TMEM_A"); return e ? atoi(e) : 12; }();
-  const bool ta = want_ta > 0 && gr && (TN - f.Mp) >= 32 && f.Mp >= 5 * UMMA_K;
-  // EXPERIMENTAL cta_group::2 kernel (GPSA_FWD_PAIR=1): Mp = 208, at least two row tiles
-  static const int want_pair = [] { const char* e = getenv("GPSA_FWD_PAIR"); return e ? atoi(e) : 0; }();
-  if (want_pair && f.Mp == 208 && p.n_rt >= 2) {
-    FwdParams q = p;
-    q.ring_bytes = 2 * (1024 * (f.nkb - 1) * f.nkb + f.Mp * FROW);  // two genes of this CTA's half blocks
-    const int smem_pair = fixed + 256 + q.ring_bytes;                 // + room for the 32 ring barriers
-    static bool pair_attr_dev[GPSA_MAX_DEVICES] = {};
-    bool& pair_attr = pair_attr_dev[gpsa_dev()];
-    if (!pair_attr) {
-      if (cudaFuncSetAttribute(tc_qf_fwd_pair_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair) != cudaSuccess)
-        return GPSA_ERR_CUDA;
-      pair_attr = true;
-    }
-    const int n_rp = (q.n_rt + 1) / 2, ncl_max = sm_count() / 2;
-    q.gsplit = 1;
-    if (n_rp < ncl_max) {
-      q.gsplit = (ncl_max + n_rp - 1) / n_rp;
-      if (q.gsplit > L) q.gsplit = L;
-    }
-    q.genes_per = (L + q.gsplit - 1) / q.gsplit;
-    q.gsplit = (L + q.genes_per - 1) / q.genes_per;
-    const int n_items = n_rp * q.gsplit;
-    const int ncl = n_items < ncl_max ? n_items : ncl_max;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * ncl);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = smem_pair;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc_qf_fwd_pair_kernel<12>, maps, q) != cudaSuccess) return GPSA_ERR_CUDA;
-    GPSA_LAUNCH_CHECK();
-    return GPSA_OK;
-  }
-  // clusters of 2 CTAs (multicast factor stream) whenever there are at least two row tiles per gene range
-  static const int want_cl = [] { const char* e = getenv("GPSA_FWD_CLUSTER"); return e ? atoi(e) : 2; }();
-  const int cl = (want_cl >= 2 && p.n_rt >= 2) ? 2 : 1;
-  if (cl == 2) {
-    // re-derive the gene split for row-tile PAIRS
-    const int n_rp = (p.n_rt + 1) / 2, ncl_max = sm_count() / 2;
-    p.gsplit = 1;
-    if (n_rp < ncl_max) {
-      p.gsplit = (ncl_max + n_rp - 1) / n_rp;
-      if (p.gsplit > L) p.gsplit = L;
-    }
-    // (Chunking the genes so that a chunk of packed factors stays L2-resident across all row tiles was tried: with
-    // 80 MB chunks the kernel's DRAM reads went UP, 2.28 -> 2.89 GB -- the q2 write stream and the A tiles evict the
-    // chunk -- at the same kernel time, so items stay (row-tile pair, all genes).)
-    p.genes_per = (L + p.gsplit - 1) / p.gsplit;
-    p.gsplit = (L + p.genes_per - 1) / p.genes_per;
-    const int n_items = n_rp * p.gsplit;
-    const int ncl = n_items < ncl_max ? n_items : ncl_max;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * ncl);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    const cudaError_t rc = (ta && want_ta == 12 && f.Mp == 208) ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 12>, maps, p)
-                           : ta ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 4>, maps, p)
-                           : gr ? cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, true, 0>, maps, p)
-                                : cudaLaunchKernelEx(&cfg, tc_qf_fwd_kernel<2, false, 0>, maps, p);
-    if (rc == cudaSuccess) {
-      GPSA_LAUNCH_CHECK();
-      return GPSA_OK;
-    }
-    // a device that cannot co-schedule the 2-CTA cluster at this shared-memory size: clear the launch error and
-    // run the single-CTA kernel (same results, the factor stream is then fetched per CTA)
-    (void)cudaGetLastError();
-    p.gsplit = 1;
-    if (p.n_rt < sm_count()) {
-      p.gsplit = (sm_count() + p.n_rt - 1) / p.n_rt;
-      if (p.gsplit > L) p.gsplit = L;
-    }
-    p.genes_per = (L + p.gsplit - 1) / p.gsplit;
-    p.gsplit = (L + p.genes_per - 1) / p.genes_per;
-  }
-  const int n_items = p.n_rt * p.gsplit;
-  const int grid = n_items < sm_count() ? n_items : sm_count();
-  if (ta) tc_qf_fwd_kernel<1, true, 4><<<grid, 256, smem_bytes, st>>>(maps, p);
-  else if (gr) tc_qf_fwd_kernel<1, true, 0><<<grid, 256, smem_bytes, st>>>(maps, p);
-  else tc_qf_fwd_kernel<1, false, 0><<<grid, 256, smem_bytes, st>>>(maps, p);
-  GPSA_LAUNCH_CHECK();
-  return GPSA_OK;
-}
-
 // fp32 TMA map of A [M, R] (box 32 r x 8 rows, 128-byte swizzle) for the generator modes; a 16-byte row pitch is
 // required, so an R that is not a multiple of 4 goes through a padded copy in `pad` (apad bytes)
 static int make_raw_map(CUtensorMap* tm, int M, long R, const float* A, void* pad, cudaStream_t st) {
@@ -1708,7 +952,7 @@ extern "C" int gpsa_quadform_fwd_feat_tc(int M, long R, int L, const float* A, c
   p.n_nt = gpsa_cdiv(L, TN);
   p.group_m = p.n_mt;  // all row tiles of one 256-gene panel run together: the packed W panel (NF x 256 x 4 B) is shared through L2
   p.kblocks = (int)feat_nblk(M);
-  set_split(p, 1);     // the K loop walks the feature blocks from (0, 0): no split
+  set_split(p, 1);  // one item walks all feature blocks (in chains of KB_CHAIN, combined in TMEM)
   p.Mrows = R; p.Ncols = L; p.C = q2; p.ldc = L; p.alpha = 1.f;
   p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
   return launch_gemm<MODE_FWD>(ta_raw, ta_raw, tb_hi, tb_lo, p, st);

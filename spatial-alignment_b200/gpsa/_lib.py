@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpsa_b200.so")
 
-KIND_RBF, KIND_MATERN12, KIND_MATERN32 = 0, 1, 2
+KIND_RBF, KIND_MATERN12, KIND_MATERN32, KIND_EXTERNAL = 0, 1, 2, 3
 OFF = 1e-5
 
 _lib = None
@@ -49,7 +49,7 @@ class WarpFwdArgs(C.Structure):
         ("Z", P), ("dlt", P), ("log_ls", P), ("log_var", P), ("Omega_G", P), ("hld_Omega", P), ("X", P), ("eps", P),
         ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
         ("A", P), ("B", P), ("T", P), ("Ke", P), ("var", P), ("Gmean", P), ("Gs", P), ("gs_stride", LNG),
-        ("kl_acc", P), ("ws64", P),
+        ("kl_acc", P), ("ws64", P), ("Kuu_ext", P), ("Kuf_ext", P),
     ]
 
 
@@ -61,7 +61,7 @@ class WarpBwdArgs(C.Structure):
         ("Gs_bar", P), ("gs_stride", LNG), ("Gm_bar", P), ("kl_bar", P),
         ("acc_Z", P), ("acc_dlt", P), ("acc_hyp", P), ("Obar_G", P),
         ("mubar", P), ("varbar", P), ("q1bar", P), ("Abar", P), ("C", P), ("AS", P),
-        ("ws64", P),
+        ("ws64", P), ("Kuu_bar", P), ("Kuf_bar", P),
     ]
 
 
@@ -71,7 +71,8 @@ class DataFwdArgs(C.Structure):
         ("Gt", P), ("log_ls", P), ("log_var", P), ("dlt", P), ("Omega", P), ("hld_Omega", P), ("G", P),
         ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
         ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("mean", P), ("q2", P),
-        ("kl_acc", P), ("ws64", P), ("engine", I), ("Ltril", P), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
+        ("kl_acc", P), ("ws64", P), ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
+        ("Kuu_ext", P),
     ]
 
 
@@ -83,7 +84,7 @@ class DataBwdArgs(C.Structure):
         ("mean_bar", P), ("q2_bar", P), ("kq_bar", P), ("kl_bar", P),
         ("G_bar", P), ("acc_Gt", P), ("acc_hyp", P), ("dlt_bar", P), ("Obar", P),
         ("q1bar", P), ("Abar", P), ("C", P), ("H", P), ("ws64", P),
-        ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
+        ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t), ("Kuu_bar", P),
     ]
 
 
@@ -93,7 +94,8 @@ ADAM_MAX_TENSORS = 24
 class AdamArgs(C.Structure):
     _fields_ = [
         ("count", I), ("p", P * ADAM_MAX_TENSORS), ("g", P * ADAM_MAX_TENSORS), ("m", P * ADAM_MAX_TENSORS),
-        ("v", P * ADAM_MAX_TENSORS), ("n", LNG * ADAM_MAX_TENSORS), ("lr", F), ("beta1", F), ("beta2", F), ("eps", F),
+        ("v", P * ADAM_MAX_TENSORS), ("n", LNG * ADAM_MAX_TENSORS), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+        ("eps", C.c_double),
         ("step", P),
     ]
 
@@ -110,13 +112,16 @@ SIGNATURES = {
     "gpsa_kernel_matrix_bwd": [I, I, I, LNG, P, P, P, P, P, P, P, P, P, P],
     "gpsa_potrf_batched_f32": [I, I, P, P, P, P],
     "gpsa_potrf_batched_f64": [I, I, P, P, P, P],
+    "gpsa_potrf_batched_f32_ld64": [I, I, P, P, P, P, P],
     "gpsa_trtri_batched_f32": [I, I, P, P, P],
     "gpsa_trtri_batched_f64": [I, I, P, P, P],
     "gpsa_gemm_f32": [I, I, LNG, F, P, LNG, LNG, LNG, P, LNG, LNG, LNG, F, P, LNG, LNG, I, P],
     "gpsa_prior_prepare": [I, I, I, P, P, P, P, P, P, P, P, P, P],
+    "gpsa_prior_prepare_ext": [I, P, P, P, P, P, P, P, P],
     "gpsa_omega_prepare": [I, I, P, P, P, P, P, P, P],
     "gpsa_omega_grad": [I, I, P, P, P, P, P, P, P, P],
     "gpsa_omega_grad_tc": [I, I, P, P, P, P, P, P, P, P, C.c_size_t, P],
+    "gpsa_omega_grad_f32": [I, I, P, P, P, P, P, P, P, P, C.c_size_t, P],
     "gpsa_gemm_tc_ws_bytes": [LNG, LNG, I, I],
     "gpsa_gemm_tc": [LNG, LNG, I, I, P, LNG, LNG, I, P, LNG, LNG, I, P, LNG, LNG, F, I, I, P, C.c_size_t, P],
     "gpsa_feat_count": [I],
@@ -127,7 +132,6 @@ SIGNATURES = {
     "gpsa_quadform_bwd_alpha_f32": [I, LNG, I, P, P, P, P, P],
     "gpsa_tc_supported": [I],
     "gpsa_quadform_tc_ws_bytes": [I, LNG, I],
-    "gpsa_quadform_fwd_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
     "gpsa_quadform_fwd_feat_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],
     "gpsa_quadform_bwd_alpha_tc": [I, LNG, I, P, P, P, P, P, C.c_size_t, P],
     "gpsa_quadform_bwd_omega_tc": [I, LNG, I, P, P, P, P, C.c_size_t, P],

@@ -12,19 +12,19 @@ f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
 KINDS = {"rbf": _lib.KIND_RBF, "matern12": _lib.KIND_MATERN12, "matern32": _lib.KIND_MATERN32}
 
-# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 split-bf16 with the ||a^T L||^2 forward, 2 = tcgen05 split-bf16
-# with the implicit-feature forward (all three products on the same generator GEMM core); "auto" = engine 2 whenever
-# the shape can fill 128-row MMA tiles (the SIMT engine stays for the launch-bound toy configurations)
+# quadratic-form engine: 0 = fp32 SIMT, 1 = tcgen05 (bf16 hi/lo split, three passes, all three products as implicit-
+# feature GEMMs); "auto" = tcgen05 whenever the shape can fill 128-row MMA tiles (the SIMT engine stays for the
+# launch-bound toy configurations)
 ENGINE = {"value": "auto"}
-TC_ENGINES = (1, 2)
+TC_ENGINES = (1,)
 
 
 def pick_engine(M, R, L):
     e = ENGINE["value"]
     if e == "auto":
-        return 2 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
+        return 1 if (lib().gpsa_tc_supported(int(M)) and R >= 2048 and L >= 16 and M >= 32) else 0
     if e in TC_ENGINES and not lib().gpsa_tc_supported(int(M)):
-        raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} yet (16 <= M <= 512)")
+        raise _lib.GPSALibraryError(f"the tcgen05 quadratic-form engine does not cover M={M} (16 <= M <= 512)")
     return int(e)
 
 
@@ -129,15 +129,26 @@ def omega_prepare(Osq):
         return _omega_prepare(Osq)
 
 
+# Batches of at least this many M x M variational covariances (M >= 32) are factorised in fp32 (two CTAs per SM, half
+# the bytes); smaller batches -- the warp layer's V*D matrices, toy gene counts -- stay in fp64.  Omega itself is
+# accumulated in fp64 either way.
+OMEGA_F32_MIN_BATCH = 16
+
+
+def omega_uses_f32(B, M):
+    return B >= OMEGA_F32_MIN_BATCH and M >= 32
+
+
 def _omega_prepare(Osq):
     B, M, _ = Osq.shape
     Omega, Ltril = _new(Osq, B, M, M), _new(Osq, B, M, M)
-    L64 = _new(Osq, B, M, M, dtype=f64)
+    L64 = None if omega_uses_f32(B, M) else _new(Osq, B, M, M, dtype=f64)
     hld = _new(Osq, B, dtype=f64)
     info = _new(Osq, B, dtype=i32)
     check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(L64, f64), ptr(hld, f64),
                                    ptr(info, i32), stream()), "omega_prepare")
-    return Omega, Ltril, L64, hld, info
+    # fp32 branch: the fp32 factor itself is what the backward inverts
+    return Omega, Ltril, (L64 if L64 is not None else Ltril), hld, info
 
 
 class OmegaFromSqt(torch.autograd.Function):
@@ -158,18 +169,25 @@ class OmegaFromSqt(torch.autograd.Function):
         return omega_grad(Osq, None, sym, None)
 
 
-def omega_grad(Osq, L64, Obar, coef, tc=False):
-    """Osq_bar = 2 (Obar + coef Omega^-1) Osq; tc=True runs the 2 Obar Osq product on the tcgen05 engine."""
+def omega_grad(Osq, Lfac, Obar, coef, tc=False):
+    """Osq_bar = 2 (Obar + coef Omega^-1) Osq; tc=True runs the 2 Obar Osq product on the tcgen05 engine.
+    Lfac: the factor omega_prepare returned for the backward (fp64, or fp32 for large batches); None if coef is None."""
     B, M, _ = Osq.shape
-    Linv = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
-    Y = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
     out = _new(Osq, B, M, M)
     ws = None
     if tc and M >= 32:
         ws = torch.empty(int(lib().gpsa_gemm_tc_ws_bytes(M, M, M, B)), dtype=torch.uint8, device=Osq.device)
-    check(lib().gpsa_omega_grad_tc(M, B, ptr(Osq), ptr(L64, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
-                                   ptr(out), ptr(ws, torch.uint8), ws.numel() if ws is not None else 0, stream()),
-          "omega_grad")
+    nws = ws.numel() if ws is not None else 0
+    if Lfac is not None and Lfac.dtype == f32:
+        Linv = _new(Osq, B, M, M) if coef is not None else None
+        Y = _new(Osq, B, M, M) if coef is not None else None
+        check(lib().gpsa_omega_grad_f32(M, B, ptr(Osq), ptr(Lfac), ptr(Obar), ptr(coef), ptr(Linv), ptr(Y), ptr(out),
+                                        ptr(ws, torch.uint8), nws, stream()), "omega_grad_f32")
+        return out
+    Linv = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
+    Y = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
+    check(lib().gpsa_omega_grad_tc(M, B, ptr(Osq), ptr(Lfac, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
+                                   ptr(out), ptr(ws, torch.uint8), nws, stream()), "omega_grad")
     return out
 
 
@@ -180,6 +198,8 @@ class WarpLayer(torch.autograd.Function):
     forward(meta, Xtilde, delta_G, Omega_sqt_G, log_ls, log_var, *[X_v, eps_v for each free view])
       -> (KL_G, Kuu_chol_list, Omega_tril_G, info, *[Gmean_v, Gsamples_v ...])
     meta = dict(kind=int, V=int, S=int, free=[view indices], with_kl=bool)
+    kind = KIND_EXTERNAL (user-supplied covariance callable): the per-view inputs are [X_v, eps_v, Kuu_v [M,M],
+    Kuf_v [M,n_v]] -- k(Z,Z) and k(Z,X) evaluated by the caller with torch -- and the backward returns dLoss/dK for both.
     """
 
     @staticmethod
@@ -202,8 +222,12 @@ class WarpLayer(torch.autograd.Function):
         overlap = meta.get("overlap")
         side = _side_streams(Xtilde.device, min(len(free), 4)) if (len(free) > 1 or (overlap and free)) else []
         keep = []
+        ext = kind == _lib.KIND_EXTERNAL
+        nper = 4 if ext else 2
         for k, v in enumerate(free):
-            X, eps = _c(xe[2 * k].detach()), _c(xe[2 * k + 1].detach())
+            X, eps = _c(xe[nper * k].detach()), _c(xe[nper * k + 1].detach())
+            Kuu_e = _c(xe[nper * k + 2].detach().to(f32)) if ext else None
+            Kuf_e = _c(xe[nper * k + 3].detach().to(f32)) if ext else None
             n = X.shape[0]
             ws64 = _new(Xtilde, 2 * M * M, dtype=f64)
             keep.append(ws64)
@@ -220,7 +244,9 @@ class WarpLayer(torch.autograd.Function):
                                 hld_K=ptr(hldK, f64) + 8 * v, info=ptr(info, i32) + 4 * v, A=ptr(A, f64),
                                 B=ptr(B, f64), T=ptr(T, f64), Ke=ptr(Ke, f64), var=ptr(var),
                                 Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
-                                kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64))
+                                kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
+                                Kuu_ext=ptr(Kuu_e), Kuf_ext=ptr(Kuf_e))
+                keep += [Kuu_e, Kuf_e]
                 st = stream()
                 if side:
                     # fork HERE: everything this view reads (copies, zero fills) has been enqueued on `cur` by now
@@ -261,12 +287,17 @@ class WarpLayer(torch.autograd.Function):
         side = _side_streams(dev.device, min(len(live), 4)) if len(live) > 1 else []
         # views add into overlapping Omega-bar slices (v*D+j and j*V+v): one buffer per concurrent view, summed at the join
         Obars, keep = [], []
+        ext = kind == _lib.KIND_EXTERNAL
         for k, v in enumerate(free):
             X, eps, Kinv, A, B, T, Ke = saved[7 * k: 7 * k + 7]
             n = X.shape[0]
             gm, gs = gouts[2 * k], gouts[2 * k + 1]
-            xgrads += [None, None]
+            Kuu_b = _new(dev, M, M) if ext else None
+            Kuf_b = _new(dev, M, n) if ext else None
+            xgrads += [None, None, Kuu_b, Kuf_b] if ext else [None, None]
             if n == 0:
+                if ext:
+                    Kuu_b.zero_()
                 continue
             lane = len(Obars) % len(side) if side else 0
             if side or not Obars:
@@ -287,7 +318,8 @@ class WarpLayer(torch.autograd.Function):
                             acc_Z=ptr(acc_Z, f64) + 8 * v * M * D, acc_dlt=ptr(acc_dlt, f64) + 8 * v * M * D,
                             acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
                             mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar, f64),
-                            C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64))
+                            C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64),
+                            Kuu_bar=ptr(Kuu_b), Kuf_bar=ptr(Kuf_b))
             st = stream()
             if side:
                 # fork HERE, after this view's zero fills / contiguous copies were enqueued on `cur`
@@ -318,8 +350,10 @@ class WarpLayer(torch.autograd.Function):
 class DataLayerPre(torch.autograd.Function):
     """One modality of the data GP up to its predictive moments (reference gpsa/models/vgpsa.py:390-421, KL :520-530).
 
-    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D])
+    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D][, Kuu [M,M], Kuf [M,S*N]])
       -> (mean [S,N,L], q2 [S,N,L], kq [S,N], KL_F, Kuu_chol_F, Omega_tril_F, info)
+    The last two inputs only with kind = KIND_EXTERNAL (user-supplied covariance callable): k(Gt,Gt) and k(Gt,G) are
+    evaluated by the caller with torch and the backward returns dLoss/dK for both (and nothing for Gtilde / G).
     with q2[s,n,p] = a^T Omega_p a (the hot contraction) and kq = sigma^2 - a^T K a; the marginal variance is
     kq + q2 + 2e-5 and the sample F = mean + sqrt(var) eps is the sampling stage (SampleF / SampleNLL below).
     meta = dict(kind=int, with_kl=bool[, omega=omega_prepare(Omega_sqt_F)])
@@ -327,7 +361,7 @@ class DataLayerPre(torch.autograd.Function):
 
     @staticmethod
     @on_device_of(1)
-    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G):
+    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, Kuu=None, Kuf=None):
         Gtilde, delta_F, Osq_F = _c(Gtilde.detach()), _c(delta_F.detach()), _c(Osq_F.detach())
         log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
         G = _c(G.detach())
@@ -336,12 +370,17 @@ class DataLayerPre(torch.autograd.Function):
         S, N = G.shape[0], G.shape[1]
         R = S * N
         kind = meta["kind"]
+        ext = kind == _lib.KIND_EXTERNAL
+        if ext and (Kuu is None or Kuf is None or tuple(Kuu.shape) != (M, M) or tuple(Kuf.shape) != (M, R)):
+            raise ValueError("external covariance: expected Kuu [M,M] and Kuf [M,S*N]")
         pre = meta.get("omega")
         Omega, Ltril, L64, hld, info_O = pre if pre is not None else _omega_prepare(Osq_F)
         Lk, Kinv, Kinv64 = _new(G, M, M), _new(G, M, M), _new(G, M, M, dtype=f64)
         hldK = _zeros(G, 1, dtype=f64)
         info = _zeros(G, 1, dtype=i32)
-        A, B, kq = _new(G, M, R), _new(G, M, R), _new(G, S, N)
+        A, kq = _new(G, M, R), _new(G, S, N)
+        B = _c(Kuf.detach().to(f32)) if ext else _new(G, M, R)  # external: B comes in filled
+        Kuu_e = _c(Kuu.detach().to(f32)) if ext else None
         engine = pick_engine(M, R, L)
         W = _new(G, _lib.feat_count(M), L) if engine == 0 else _new(G, 1)
         tc_ws = _lib.tc_workspace(M, R, L, G) if engine in TC_ENGINES else None
@@ -355,12 +394,13 @@ class DataLayerPre(torch.autograd.Function):
                         info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), mean=ptr(mean),
                         q2=ptr(q2),
                         kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
-                        engine=engine, Ltril=ptr(Ltril), tc_ws=ptr(tc_ws, torch.uint8),
-                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
+                        engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
+                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0, Kuu_ext=ptr(Kuu_e))
         check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
         ctx.meta = meta
         ctx.engine = engine
         ctx.dims = (S, N)
+        ctx.n_in = 9 if Kuu is not None or Kuf is not None else 7
         ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64, Kinv, Kinv64, A, B, W, KD)
         info_all = torch.cat([info_O, info])
         ctx.mark_non_differentiable(Lk, Ltril, info_all)
@@ -381,7 +421,9 @@ class DataLayerPre(torch.autograd.Function):
         mean_bar = _c(mean_bar) if mean_bar is not None else _zeros(dev, S, N, L)
         q2_bar = _c(q2_bar) if q2_bar is not None else _zeros(dev, S, N, L)
         kq_bar = _c(kq_bar) if kq_bar is not None else _zeros(dev, S, N)
-        G_bar = _new(dev, S, N, D)
+        ext = meta["kind"] == _lib.KIND_EXTERNAL
+        G_bar = _new(dev, S, N, D) if not ext else None
+        Kuu_b = _new(dev, M, M) if ext else None
         acc_Gt, acc_hyp = _zeros(dev, M, D, dtype=f64), _zeros(dev, 2, dtype=f64)
         dlt_bar, Obar = _new(dev, M, L), _new(dev, L, M, M)
         q1bar = _new(dev, R)
@@ -398,13 +440,15 @@ class DataLayerPre(torch.autograd.Function):
                         acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar),
                         q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), ws64=ptr(ws64, f64),
                         engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
-                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0)
+                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0, Kuu_bar=ptr(Kuu_b))
         check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
         del tc_ws
         Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
         hyp = acc_hyp.to(f32)
-        return None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar
+        if ext:  # C = dLoss/dK_uf; the covariance function's own arguments get their gradients through the caller's autograd
+            return None, None, None, hyp[1:2], dlt_bar, Osq_bar, None, Kuu_b, Cm
+        return (None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar) + ((None, None) if ctx.n_in == 9 else ())
 
 
 class SampleF(torch.autograd.Function):
@@ -569,8 +613,8 @@ class DataLayer:
     """
 
     @staticmethod
-    def apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps):
-        mean, q2, kq, kl, Lk, Ltril, info = DataLayerPre.apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G)
+    def apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, eps, *kext):
+        mean, q2, kq, kl, Lk, Ltril, info = DataLayerPre.apply(meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, *kext)
         return SampleF.apply(mean, q2, kq, eps), kl, Lk, Ltril, info
 
 

@@ -13,7 +13,7 @@ import torch.nn as nn
 from sklearn.cluster import KMeans
 
 from .gpsa import GPSA
-from .. import _ops
+from .. import _lib, _ops
 from ..lazy import LazySamples
 from ..util.util import kmeans_gpu, matern12_kernel, matern32_kernel, rbf_kernel
 
@@ -25,18 +25,22 @@ _DEBUG_CHECKS = os.environ.get("GPSA_B200_CHECK", "0") == "1"
 
 
 def _kernel_kind(fn):
-    """The model receives kernel CALLABLES (reference :25-26); the fused path recognises the two it
-    implements by identity.  Anything else is an explicit error -- there is no slow fallback."""
+    """The model receives kernel CALLABLES (reference :25-26).  The three the reference exports are recognised by
+    identity and run fused (distances in registers, analytic gradients).  Any other callable with the reference's
+    signature k(x1, x2, lengthscale_unconstrained=..., output_variance_unconstrained=...) takes the documented SLOW
+    PATH (returns None here): K_uu and K_uf are evaluated by the callable itself with torch, differentiated by
+    torch autograd, and enter the layers as matrices (kernel kind 3 of include/gpsa_b200.h); everything downstream of
+    the two matrices -- factorisations, solves, the quadratic forms, sampling, likelihood, KL -- stays on the fused
+    path."""
     if fn is rbf_kernel:
         return "rbf"
     if fn is matern12_kernel:
         return "matern12"
     if fn is matern32_kernel:
         return "matern32"
-    raise NotImplementedError(
-        f"kernel function {getattr(fn, '__name__', fn)!r} is not supported by the fused B200 path; "
-        "use gpsa.rbf_kernel, gpsa.matern12_kernel or gpsa.matern32_kernel"
-    )
+    if not callable(fn):
+        raise TypeError(f"kernel function must be callable, got {type(fn).__name__}")
+    return None
 
 
 class VariationalGPSA(GPSA):
@@ -295,11 +299,18 @@ class VariationalGPSA(GPSA):
             for mod in mods:
                 pre_F[mod] = _ops.omega_prepare(self.Omega_sqt_F_dict[mod].detach().contiguous())
 
-        meta = {"kind": _ops.KINDS[self._kind_warp], "V": V, "S": S, "free": free, "with_kl": True,
-                "kl_mask": self._kl_mask, "overlap": _prepare_omega_F}
+        ext_w = self._kind_warp is None
+        meta = {"kind": _lib.KIND_EXTERNAL if ext_w else _ops.KINDS[self._kind_warp], "V": V, "S": S, "free": free,
+                "with_kl": True, "kl_mask": self._kl_mask, "overlap": _prepare_omega_F}
         flat = []
         for vv in free:
             flat += [X_views[vv], eps_G[vv]]
+            if ext_w:  # slow path: the user's covariance callable, evaluated and differentiated by torch (:314-318)
+                ls_v, var_v = self.warp_kernel_lengthscales[vv], self.warp_kernel_variances[vv]
+                flat += [self.kernel_func_warp(self.Xtilde[vv], self.Xtilde[vv], lengthscale_unconstrained=ls_v,
+                                               output_variance_unconstrained=var_v),
+                         self.kernel_func_warp(self.Xtilde[vv], X_views[vv], lengthscale_unconstrained=ls_v,
+                                               output_variance_unconstrained=var_v)]
         outs = _ops.WarpLayer.apply(
             meta, self.Xtilde, self.delta_G_list, self.Omega_sqt_G_list, self.warp_kernel_lengthscales,
             self.warp_kernel_variances, *flat,
@@ -344,7 +355,19 @@ class VariationalGPSA(GPSA):
             self.F_latent_samples_test, self.F_observed_samples_test = {}, {}
         kl = kl_G if self._kl_G_scale == 1.0 else kl_G * self._kl_G_scale
         infos = [info_G]
-        kind_d = _ops.KINDS[self._kind_data]
+        ext_d = self._kind_data is None
+        kind_d = _lib.KIND_EXTERNAL if ext_d else _ops.KINDS[self._kind_data]
+
+        def _k_ext(Gs):
+            """Slow path of the data layer (:390, :409): (k(Gt,Gt) [M,M], k(Gt,G) as [M, S*N]) from the user's callable."""
+            if not ext_d:
+                return ()
+            ls, var = self.data_kernel_lengthscale, self.data_kernel_variance
+            Kuu = self.kernel_func_data(self.Gtilde, self.Gtilde, lengthscale_unconstrained=ls,
+                                        output_variance_unconstrained=var)
+            Kuf = self.kernel_func_data(self.Gtilde, Gs, lengthscale_unconstrained=ls, output_variance_unconstrained=var)
+            return Kuu, Kuf.permute(1, 0, 2).reshape(Kuf.shape[1], -1)   # [S,M,N] -> [M, S*N], r = s*N + n
+
         for mod in mods:
             L = self.n_latent_outputs[mod]
             N = int(Ns[mod])
@@ -363,7 +386,7 @@ class VariationalGPSA(GPSA):
             mean, q2, kq, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayerPre.apply(
                 {"kind": kind_d, "with_kl": True, "omega": pre},
                 self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod], Osq,
-                G_samples[mod],
+                G_samples[mod], *_k_ext(G_samples[mod]),
             )
             kl = kl + (kl_F if self._kl_F_scale[mod] == 1.0 else kl_F * self._kl_F_scale[mod])
             infos.append(info_F)
@@ -401,7 +424,7 @@ class VariationalGPSA(GPSA):
                 F_t = _ops.DataLayer.apply(
                     {"kind": kind_d, "with_kl": False, "omega": pre},
                     self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod],
-                    Osq, Gt, eps_t,
+                    Osq, Gt, eps_t, *_k_ext(Gt),
                 )[0]
                 self.F_latent_samples_test[mod] = F_t
                 self.F_observed_samples_test[mod] = _ops.LMCObserve.apply(F_t, W) if W is not None else F_t

@@ -55,13 +55,28 @@ def matern32_kernel(x1, x2, lengthscale_unconstrained, output_variance_unconstra
     )
 
 
-def kmeans_gpu(X, n_clusters, iters=30, seed=0):
-    """Lloyd's k-means on the GPU (csrc/aux.cu: gpsa_kmeans_lloyd): X [N,D] (D <= 3) -> (centres [K,D] float32 CUDA
-    tensor, inertia float).  Initial centres = a random subset of the points (numpy Generator(seed)).  Used by
-    VariationalGPSA(data_init=True) for inputs too large for the host KMeans of the reference
-    (gpsa/models/vgpsa.py:61-92), where the inducing-point initialisation dominates the time to the first iteration."""
-    import ctypes as C
+def _kmeanspp_seeds(Xd, K, rng):
+    """k-means++ seeding (Arthur & Vassilvitskii 2007) on the device: every next centre is drawn with probability
+    proportional to the squared distance to the nearest centre chosen so far.  The uniforms come from `rng` (numpy) and
+    are uploaded once, so there is no host synchronisation inside the loop."""
+    N = Xd.shape[0]
+    u = torch.as_tensor(rng.random(K), dtype=torch.float64, device=Xd.device)
+    idx = torch.empty(K, dtype=torch.long, device=Xd.device)
+    idx[0] = int(rng.integers(N))
+    d2 = torch.sum((Xd - Xd[idx[0]]) ** 2, dim=1).double()
+    for k in range(1, K):
+        cs = torch.cumsum(d2, 0)
+        j = torch.searchsorted(cs, u[k] * cs[-1]).clamp_(max=N - 1)
+        idx[k] = j
+        d2 = torch.minimum(d2, torch.sum((Xd - Xd[j]) ** 2, dim=1).double())
+    return Xd[idx].clone()
 
+
+def kmeans_gpu(X, n_clusters, iters=30, seed=0, n_init=3):
+    """Lloyd's k-means on the GPU (csrc/aux.cu: gpsa_kmeans_lloyd): X [N,D] (D <= 3) -> (centres [K,D] float32 CUDA
+    tensor, inertia float).  k-means++ seeding, `n_init` restarts (the lowest inertia wins), numpy Generator(seed).
+    Used by VariationalGPSA(data_init=True) for inputs too large for the host KMeans of the reference
+    (gpsa/models/vgpsa.py:61-92), where the inducing-point initialisation dominates the time to the first iteration."""
     from gpsa import _lib
 
     if not torch.cuda.is_available():
@@ -73,15 +88,20 @@ def kmeans_gpu(X, n_clusters, iters=30, seed=0):
     if K > N:
         raise ValueError(f"n_clusters={K} exceeds the number of points {N}")
     rng = np.random.default_rng(seed)
-    sel = torch.as_tensor(rng.choice(N, K, replace=False), device=Xd.device)
-    centres = Xd[sel].clone()
     assign = torch.empty(N, dtype=torch.int32, device=Xd.device)
     sums = torch.empty(K * (D + 1), dtype=torch.float64, device=Xd.device)
-    inertia = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+    best = None
     with torch.cuda.device(Xd.device):
-        _lib.check(_lib.lib().gpsa_kmeans_lloyd(N, D, K, Xd.data_ptr(), centres.data_ptr(), int(iters), assign.data_ptr(),
-                                                sums.data_ptr(), inertia.data_ptr(), _lib.stream()), "kmeans_lloyd")
-    return centres, float(inertia)
+        for _ in range(max(1, int(n_init))):
+            centres = _kmeanspp_seeds(Xd, K, rng)
+            inertia = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+            _lib.check(_lib.lib().gpsa_kmeans_lloyd(N, D, K, Xd.data_ptr(), centres.data_ptr(), int(iters),
+                                                    assign.data_ptr(), sums.data_ptr(), inertia.data_ptr(), _lib.stream()),
+                       "kmeans_lloyd")
+            val = float(inertia)
+            if best is None or val < best[1]:
+                best = (centres, val)
+    return best
 
 
 def rbf_kernel_numpy(x, xp, kernel_params):

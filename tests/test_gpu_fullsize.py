@@ -53,7 +53,7 @@ def _setup(name, engine):
     return cfg, model, data_dict, X, Y, ocfg, params, eps
 
 
-@pytest.mark.parametrize("name,engine", [("c3", 2), ("c3", 1), ("c4", 2), ("c5", 2)])
+@pytest.mark.parametrize("name,engine", [("c3", 1), ("c4", 1), ("c5", 1)])
 def test_benchmark_shape_matches_oracle(name, engine):
     from gpsa import _ops
 

@@ -186,6 +186,43 @@ def test_omega_prepare_and_grad(L, M, B):
     assert relerr(out.cpu(), od.grad) < 1e-5
 
 
+@pytest.mark.parametrize("M,B", [(64, 16), (200, 40), (256, 17), (512, 16)])
+def test_omega_prepare_and_grad_fp32_batches(L, M, B):
+    """Gene-sized batches take the fp32 factorisation (Omega accumulated in fp64, fp32 Cholesky / inverse, log-det in
+    fp64).  Acceptance = SURVEY.md 7.5's rule against the reference's own fp32 arithmetic (torch fp32 on the same data):
+    no further from float64 than the reference is -- in fact several times closer, because forming Omega in fp32 is
+    what dominates the reference's error."""
+    from gpsa import _ops
+
+    g = torch.Generator().manual_seed(M + B)
+    Osq = (torch.randn(B, M, M, generator=g) * 0.1)
+    Obar_in = torch.randn(B, M, M, generator=g) * 1e-3
+    Obar_in = Obar_in + Obar_in.transpose(1, 2)
+    coef = torch.full((B,), -0.5)
+
+    def ref(dtype):
+        od = Osq.to(dtype).requires_grad_()
+        Om = orc.omega_from_sqt(od)
+        Lr = torch.linalg.cholesky(Om)
+        hld = torch.log(torch.diagonal(Lr, dim1=1, dim2=2)).sum(1)
+        ((Obar_in.to(dtype) * Om).sum() + (2 * coef.to(dtype) * hld).sum()).backward()
+        return Om.detach(), Lr.detach(), hld.detach(), od.grad
+
+    Om64, L64r, hld64, g64 = ref(f64)
+    Om32, L32r, hld32, g32 = ref(torch.float32)
+    assert _ops.omega_uses_f32(B, M)
+    Omega, Ltril, Lfac, hld, info = _ops.omega_prepare(Osq.cuda())
+    assert Lfac.dtype == torch.float32 and int(info.abs().sum()) == 0
+    out = _ops.omega_grad(Osq.cuda(), Lfac, Obar_in.cuda().contiguous(), coef.cuda(), tc=True)
+    assert relerr(Omega.cpu(), Om64) < 2e-7                                   # rounded once from the fp64 accumulation
+    assert relerr(Omega.cpu(), Omega.cpu().transpose(1, 2)) == 0.0            # exactly symmetric
+    for name, new, r32, r64 in (("Ltril", Ltril.cpu(), L32r, L64r), ("half_logdet", hld.cpu(), hld32, hld64),
+                                ("Osq_bar", out.cpu(), g32, g64)):
+        e_new, e_ref = relerr(new, r64), relerr(r32, r64)
+        assert e_new <= max(1e-6, 1.0 * e_ref), (name, e_new, e_ref)
+    assert bool((Ltril.cpu().triu(1) == 0).all())
+
+
 @pytest.mark.parametrize("kind", ["rbf", "matern12", "matern32"])
 @pytest.mark.parametrize("M,D", [(25, 2), (200, 2), (256, 3)])
 def test_prior_prepare(L, kind, M, D):

@@ -146,7 +146,8 @@ def test_graphed_iteration_matches_eager():
     with pytest.raises(ValueError):
         GraphedIteration(model, data_dict, torch.optim.Adam(model.parameters(), lr=1e-2), S=g.S)
     it = GraphedIteration(model, data_dict, opt, S=g.S, warmup=2)   # 2 warm-up iterations already stepped the model
-    ref = copy.deepcopy(model)                                       # eager twin: same parameters, same Adam state
+    ref, _ = build(g)                                                # eager twin: same parameters, same Adam state
+    ref.load_state_dict(model.state_dict())
     opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, capturable=True)
     opt_ref.load_state_dict(copy.deepcopy(opt.state_dict()))
     p0 = [p.detach().clone() for p in model.parameters()]

@@ -89,9 +89,13 @@ def test_create_view_idx_dict_and_errors():
         gpsa.VariationalGPSA(bad, m_X_per_view=4, m_G=4, n_latent_gps={"rna": None, "protein": None})
     with pytest.raises(TypeError):  # n_latent_gps must be a dict (reference :54)
         gpsa.VariationalGPSA(data_dict, m_X_per_view=4, m_G=4)
-    with pytest.raises(NotImplementedError):
-        gpsa.VariationalGPSA(data_dict, m_X_per_view=4, m_G=4, n_latent_gps={"rna": None, "protein": None},
+    # any callable is accepted (unknown ones take the documented slow path, see tests/test_gpu_callable.py) ...
+    m = gpsa.VariationalGPSA(data_dict, m_X_per_view=4, m_G=4, n_latent_gps={"rna": None, "protein": None},
                              kernel_func_warp=lambda *a, **k: None)
+    assert m._kind_warp is None and m._kind_data == "rbf"
+    with pytest.raises(TypeError):  # ... a non-callable is not
+        gpsa.VariationalGPSA(data_dict, m_X_per_view=4, m_G=4, n_latent_gps={"rna": None, "protein": None},
+                             kernel_func_warp="rbf")
 
 
 def test_forward_refuses_cpu():

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--L", type=int, default=2000)
     ap.add_argument("--engine", default="tc")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--which", default="fwd,fwdfeat,alpha,omega")
+    ap.add_argument("--which", default="fwd,alpha,omega")
     a = ap.parse_args()
     M, R, L = a.M, a.R, a.L
     lib = _lib.lib()
@@ -43,8 +43,6 @@ def main():
     def run(name):
         if a.engine == "tc":
             if name == "fwd":
-                return lib.gpsa_quadform_fwd_tc(M, R, L, A.data_ptr(), Ltril.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(), st)
-            if name == "fwdfeat":
                 return lib.gpsa_quadform_fwd_feat_tc(M, R, L, A.data_ptr(), Omega.data_ptr(), q2.data_ptr(), ws.data_ptr(), ws.numel(), st)
             if name == "alpha":
                 return lib.gpsa_quadform_bwd_alpha_tc(M, R, L, A.data_ptr(), G.data_ptr(), Omega.data_ptr(), Abar.data_ptr(), ws.data_ptr(), ws.numel(), st)
