@@ -56,6 +56,14 @@ enum { MODE_TEST = 0, MODE_ALPHA = 1, MODE_OMEGA = 2, MODE_FWD = 3 };
 // chain accumulator to be drained (~2 % of a chain's time).  Items with a single chain keep the two alternating
 // accumulator stages, i.e. the epilogue of one item runs under the MMAs of the next.
 constexpr int KB_CHAIN = 128;
+// Lockstep of the persistent CTAs.  In the forward and Omega-bar products every concurrently running item streams the
+// SAME B operand (the packed W panel / the G^T slab of its gene tile) K block by K block, and only the first CTA to
+// touch a block should pay for it in HBM.  Nothing keeps 148 free-running CTAs within an L2's worth of each other over
+// a long K loop: at the C5 rank shape (R = 6.4 M rows, 100 000 K blocks) the Omega-bar product ran at 224 TF/s, exactly
+// the HBM bound of every CTA fetching its own copy (72 KB per 0.9 us K block x 148 CTAs = 11.8 TB/s wanted), against
+// 400 TF/s at R = 128 000.  The TMA producers therefore meet at a grid-wide counter every SYNC_EVERY K blocks (all CTAs
+// are co-resident: one per SM); a producer that waits longer than ~2 s stops synchronising instead of hanging.
+constexpr int SYNC_EVERY = 128;
 constexpr int N_GEN_WARPS = 8;
 // modes whose A operand is generated on the fly from TMA-staged raw rows of A (never stored)
 __host__ __device__ constexpr bool mode_gen(int mode) { return mode == MODE_OMEGA || mode == MODE_FWD; }
@@ -77,7 +85,21 @@ struct GemmParams {
   long R;
   int Mind, nb, nblk;
   float* Abar;        // ALPHA: [Mind, R], added to
+  unsigned int* sync; // FWD/OMEGA: grid-wide arrival counter (zeroed by the launcher), NULL = no lockstep
 };
+
+// arrive at the grid-wide checkpoint whose cumulative arrival count is `expect`, wait for the others (bounded)
+__device__ __forceinline__ bool grid_checkpoint(unsigned int* counter, unsigned int expect) {
+  atomicAdd(counter, 1u);
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= expect) return true;
+    if (clock64() - t0 > 4000000000LL) return false;  // ~2 s: give up on lockstep, never hang
+    __nanosleep(200);
+  }
+}
 
 __device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& ks) {
   const int per_split = p.n_mt * p.n_nt;
@@ -180,6 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
+    bool lockstep = p.sync != nullptr && p.n_split == 1 && n_items > 1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
@@ -197,7 +220,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       int fI = 0, fJ = 0;  // MODE_FWD: feature block (I, J) of K block kb (feat.cu order: J runs from I to nb - 1)
       if (MODE == MODE_FWD && kb0 > 0) decode_block(kb0, p.nb, fI, fJ);
+      // lockstep checkpoints (n_split == 1: every item has the same K range): wave w of the persistent loop has
+      // part = min(grid, items left) participants and ncp checkpoints
+      const unsigned int wave = (unsigned int)((item - (int)blockIdx.x) / (int)gridDim.x);
+      const unsigned int part = (unsigned int)min((int)gridDim.x, n_items - (int)(wave * gridDim.x));
+      const unsigned int ncp = (unsigned int)((kb1 - kb0 + SYNC_EVERY - 1) / SYNC_EVERY);
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (mode_gen(MODE) && lockstep && (kb - kb0) % SYNC_EVERY == 0) {
+          const unsigned int cp = (unsigned int)((kb - kb0) / SYNC_EVERY);
+          unsigned int ok = 1;
+          if (elect_one()) ok = grid_checkpoint(p.sync, ncp * wave * gridDim.x + (cp + 1) * part) ? 1u : 0u;
+          if (!__all_sync(0xffffffffu, ok != 0)) lockstep = false;
+        }
         uint8_t* st = smem + stage * STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -735,7 +769,7 @@ FeatFwdLayout featfwd_layout(int M, long R, int L) {
   f.NF = feat_nblk(M) * FBK;
   f.wg = al256((size_t)L * f.NF * 2);
   f.apad = (R % 4 == 0) ? 0 : al256((size_t)M * rup(R, 4) * 4);  // TMA needs a 16-byte row pitch: padded copy of A
-  f.total = 2 * f.wg + f.apad;
+  f.total = 2 * f.wg + f.apad + 256;  // + the lockstep counter
   return f;
 }
 struct AlphaLayout { int Lp; long NF; size_t g, w, total; };
@@ -754,7 +788,7 @@ OmegaLayout omega_layout(int M, long R, int L) {
   o.Rp = rup(R, 8);
   o.gt = al256((size_t)L * o.Rp * 2);
   o.apad = (R % 4 == 0) ? 0 : al256((size_t)M * rup(R, 4) * 4);  // TMA needs a 16-byte row pitch: padded copy of A
-  o.total = 2 * o.gt + o.apad;
+  o.total = 2 * o.gt + o.apad + 256;  // + the lockstep counter
   return o;
 }
 
@@ -953,6 +987,8 @@ extern "C" int gpsa_quadform_fwd_feat_tc(int M, long R, int L, const float* A, c
   p.group_m = p.n_mt;  // all row tiles of one 256-gene panel run together: the packed W panel (NF x 256 x 4 B) is shared through L2
   p.kblocks = (int)feat_nblk(M);
   set_split(p, 1);  // one item walks all feature blocks (in chains of KB_CHAIN, combined in TMEM)
+  p.sync = reinterpret_cast<unsigned int*>(w + 2 * f.wg + f.apad);
+  if (cudaMemsetAsync(p.sync, 0, sizeof(unsigned int), st) != cudaSuccess) return GPSA_ERR_CUDA;
   p.Mrows = R; p.Ncols = L; p.C = q2; p.ldc = L; p.alpha = 1.f;
   p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
   return launch_gemm<MODE_FWD>(ta_raw, ta_raw, tb_hi, tb_lo, p, st);
@@ -1027,5 +1063,9 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
   p.accumulate = p.n_split > 1;
   if (p.accumulate && cudaMemsetAsync(H, 0, sizeof(float) * (size_t)NF * L, st) != cudaSuccess) return GPSA_ERR_CUDA;
   p.Amat = A; p.R = R; p.Mind = M; p.nb = feat_nb(M); p.nblk = (int)feat_nblk(M);
+  if (p.n_split == 1) {
+    p.sync = reinterpret_cast<unsigned int*>(w + 2 * o.gt + o.apad);
+    if (cudaMemsetAsync(p.sync, 0, sizeof(unsigned int), st) != cudaSuccess) return GPSA_ERR_CUDA;
+  }
   return launch_gemm<MODE_OMEGA>(ta_raw, ta_raw, tb_hi, tb_lo, p, st);
 }

@@ -32,9 +32,29 @@ def lib():
                 f"{LIB_PATH} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'). "
                 "gpsa_b200 has no CPU fallback."
             )
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         _declare(_lib)
     return _lib
+
+
+TORCH_LIB_PATH = os.path.join(_HERE, "libgpsa_b200_torch.so")
+_ops_ns = None
+
+
+def ops():
+    """torch.ops.gpsa_b200: the C ABI registered as torch custom ops (csrc/bindings.cpp, TORCH_LIBRARY(gpsa_b200)).
+    This is what gpsa/_ops.py calls; the ctypes table below stays for direct C-ABI use (tests, tools)."""
+    global _ops_ns
+    if _ops_ns is None:
+        lib()  # the kernels' library first: the op library links against it
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise GPSALibraryError(
+                f"{TORCH_LIB_PATH} not found: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "gpsa_b200 has no fallback path."
+            )
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _ops_ns = torch.ops.gpsa_b200
+    return _ops_ns
 
 
 P = C.c_void_p

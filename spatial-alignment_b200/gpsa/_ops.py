@@ -1,12 +1,13 @@
-"""torch.autograd.Function wrappers with EXPLICIT forward and backward around the C ABI
-(include/gpsa_b200.h).  Nothing below this file uses autograd; every gradient is the analytic
-backward implemented in CUDA."""
-import ctypes as C
+"""torch.autograd.Function wrappers with EXPLICIT forward and backward around the library's torch custom ops
+(torch.ops.gpsa_b200.*, csrc/bindings.cpp: one op per extern "C" launcher of include/gpsa_b200.h).  Nothing below this
+file uses autograd; every gradient is the analytic backward implemented in CUDA.  The ops check device / dtype /
+contiguity and launch on torch's current stream of the tensors' device."""
+import contextlib
 
 import torch
 
 from . import _lib
-from ._lib import DataBwdArgs, DataFwdArgs, WarpBwdArgs, WarpFwdArgs, check, lib, on_device_of, ptr, stream
+from ._lib import lib, on_device_of, ops
 
 f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
@@ -76,8 +77,7 @@ class KernelMatrix(torch.autograd.Function):
         if x2.shape[1] != D or not 1 <= D <= 3:
             raise ValueError("kernel inputs must share a trailing dimension of 1, 2 or 3")
         K = _new(x1, M, R)
-        check(lib().gpsa_kernel_matrix_fwd(kind, D, M, R, ptr(x1), ptr(x2), ptr(log_ls), ptr(log_var), ptr(K), stream()),
-              "kernel_matrix_fwd")
+        ops().kernel_matrix_fwd(kind, D, M, R, x1, x2, log_ls, log_var, K)
         ctx.kind = kind
         ctx.save_for_backward(x1, x2, log_ls, log_var)
         return K
@@ -92,9 +92,7 @@ class KernelMatrix(torch.autograd.Function):
         acc_x1 = _zeros(x1, M, D, dtype=f64)
         acc_h = _zeros(x1, 2, dtype=f64)
         x2bar = _new(x1, R, D)
-        check(lib().gpsa_kernel_matrix_bwd(ctx.kind, D, M, R, ptr(x1), ptr(x2), ptr(log_ls), ptr(log_var), ptr(Kbar),
-                                           ptr(acc_x1, f64), ptr(x2bar), None, ptr(acc_h, f64), stream()),
-              "kernel_matrix_bwd")
+        ops().kernel_matrix_bwd(ctx.kind, D, M, R, x1, x2, log_ls, log_var, Kbar, acc_x1, x2bar, None, acc_h)
         h = acc_h.to(f32)
         return None, acc_x1.to(f32), x2bar, h[0:1], h[1:2]
 
@@ -145,8 +143,7 @@ def _omega_prepare(Osq):
     L64 = None if omega_uses_f32(B, M) else _new(Osq, B, M, M, dtype=f64)
     hld = _new(Osq, B, dtype=f64)
     info = _new(Osq, B, dtype=i32)
-    check(lib().gpsa_omega_prepare(M, B, ptr(Osq), ptr(Omega), ptr(Ltril), ptr(L64, f64), ptr(hld, f64),
-                                   ptr(info, i32), stream()), "omega_prepare")
+    ops().omega_prepare(M, B, Osq, Omega, Ltril, L64, hld, info)
     # fp32 branch: the fp32 factor itself is what the backward inverts
     return Omega, Ltril, (L64 if L64 is not None else Ltril), hld, info
 
@@ -181,13 +178,11 @@ def omega_grad(Osq, Lfac, Obar, coef, tc=False):
     if Lfac is not None and Lfac.dtype == f32:
         Linv = _new(Osq, B, M, M) if coef is not None else None
         Y = _new(Osq, B, M, M) if coef is not None else None
-        check(lib().gpsa_omega_grad_f32(M, B, ptr(Osq), ptr(Lfac), ptr(Obar), ptr(coef), ptr(Linv), ptr(Y), ptr(out),
-                                        ptr(ws, torch.uint8), nws, stream()), "omega_grad_f32")
+        ops().omega_grad_f32(M, B, Osq, Lfac, Obar, coef, Linv, Y, out, ws, nws)
         return out
     Linv = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
     Y = _new(Osq, B, M, M, dtype=f64) if coef is not None else None
-    check(lib().gpsa_omega_grad_tc(M, B, ptr(Osq), ptr(Lfac, f64), ptr(Obar), ptr(coef), ptr(Linv, f64), ptr(Y, f64),
-                                   ptr(out), ptr(ws, torch.uint8), nws, stream()), "omega_grad")
+    ops().omega_grad_tc(M, B, Osq, Lfac, Obar, coef, Linv, Y, out, ws, nws)
     return out
 
 
@@ -236,23 +231,16 @@ class WarpLayer(torch.autograd.Function):
             Ke, var = _new(X, D, M, dtype=f64), _new(X, n, D)
             Gmean, Gs = _new(X, n, D), _new(X, S, n, D)
             if n > 0:
-                a = WarpFwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
-                                Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
-                                log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v,
-                                Omega_G=ptr(Omega_G), hld_Omega=ptr(hld_G, f64), X=ptr(X), eps=ptr(eps),
-                                Lk=ptr(Lk_all) + 4 * v * M * M, Kinv=None, Kinv64=ptr(Kinv, f64),
-                                hld_K=ptr(hldK, f64) + 8 * v, info=ptr(info, i32) + 4 * v, A=ptr(A, f64),
-                                B=ptr(B, f64), T=ptr(T, f64), Ke=ptr(Ke, f64), var=ptr(var),
-                                Gmean=ptr(Gmean), Gs=ptr(Gs), gs_stride=n * D,
-                                kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
-                                Kuu_ext=ptr(Kuu_e), Kuf_ext=ptr(Kuf_e))
                 keep += [Kuu_e, Kuf_e]
-                st = stream()
+                ctx_stream = contextlib.nullcontext()
                 if side:
                     # fork HERE: everything this view reads (copies, zero fills) has been enqueued on `cur` by now
                     side[k % len(side)].wait_stream(cur)
-                    st = C.c_void_p(side[k % len(side)].cuda_stream)
-                check(lib().gpsa_warp_view_fwd(C.byref(a), st), "warp_view_fwd")
+                    ctx_stream = torch.cuda.stream(side[k % len(side)])
+                with ctx_stream:  # the op launches on the current stream; it allocates nothing
+                    ops().warp_view_fwd(kind, D, M, V, v, S, n, Xtilde[v], delta_G[v], log_ls[v:v + 1], log_var[v:v + 1],
+                                        Omega_G, hld_G, X, eps, Lk_all[v], None, Kinv, hldK[v:v + 1], info[v:v + 1], A, B, T,
+                                        Ke, var, Gmean, Gs, n * D, kl if meta["with_kl"] else None, ws64, Kuu_e, Kuf_e)
             # `var` is written on the side stream and used nowhere else: it has to outlive the join below, or its block
             # returns to the current stream's allocator pool while this view's chain is still running
             keep.append(var)
@@ -309,23 +297,15 @@ class WarpLayer(torch.autograd.Function):
             mubar, varbar, q1bar = _new(dev, n, D), _new(dev, n, D), _new(dev, n)
             Abar, Cm, AS = (_new(dev, M, n, dtype=f64), _new(dev, M, n, dtype=f64),
                             _new(dev, D, M, n, dtype=f64))
-            a = WarpBwdArgs(kind=kind, D=D, M=M, V=V, v=v, S=S, n=n,
-                            Z=ptr(Xtilde) + 4 * v * M * D, dlt=ptr(delta_G) + 4 * v * M * D,
-                            log_ls=ptr(log_ls) + 4 * v, log_var=ptr(log_var) + 4 * v, Omega_G=ptr(Omega_G),
-                            X=ptr(X), eps=ptr(eps), Kinv64=ptr(Kinv, f64), A=ptr(A, f64), B=ptr(B, f64),
-                            T=ptr(T, f64), Ke=ptr(Ke, f64),
-                            Gs_bar=ptr(gs), gs_stride=n * D, Gm_bar=ptr(gm), kl_bar=ptr(klb),
-                            acc_Z=ptr(acc_Z, f64) + 8 * v * M * D, acc_dlt=ptr(acc_dlt, f64) + 8 * v * M * D,
-                            acc_hyp=ptr(acc_hyp, f64) + 16 * v, Obar_G=ptr(Obar),
-                            mubar=ptr(mubar), varbar=ptr(varbar), q1bar=ptr(q1bar), Abar=ptr(Abar, f64),
-                            C=ptr(Cm, f64), AS=ptr(AS, f64), ws64=ptr(ws64, f64),
-                            Kuu_bar=ptr(Kuu_b), Kuf_bar=ptr(Kuf_b))
-            st = stream()
+            ctx_stream = contextlib.nullcontext()
             if side:
                 # fork HERE, after this view's zero fills / contiguous copies were enqueued on `cur`
                 side[lane].wait_stream(cur)
-                st = C.c_void_p(side[lane].cuda_stream)
-            check(lib().gpsa_warp_view_bwd(C.byref(a), st), "warp_view_bwd")
+                ctx_stream = torch.cuda.stream(side[lane])
+            with ctx_stream:
+                ops().warp_view_bwd(kind, D, M, V, v, S, n, Xtilde[v], delta_G[v], log_ls[v:v + 1], log_var[v:v + 1], Omega_G,
+                                    X, eps, Kinv, A, B, T, Ke, gs, n * D, gm, klb, acc_Z[v], acc_dlt[v], acc_hyp[v], Obar,
+                                    mubar, varbar, q1bar, Abar, Cm, AS, ws64, Kuu_b, Kuf_b)
             keep += [gm, gs, mubar, varbar, q1bar, Abar, Cm, AS, ws64]
         for s_ in side:
             cur.wait_stream(s_)
@@ -388,15 +368,8 @@ class DataLayerPre(torch.autograd.Function):
         mean, q2 = _new(G, S, N, L), _new(G, S, N, L)
         kl = _zeros(G, 1, dtype=f64)
         ws64 = _new(G, 2 * M * M, dtype=f64)
-        a = DataFwdArgs(kind=kind, D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls), log_var=ptr(log_var),
-                        dlt=ptr(delta_F), Omega=ptr(Omega), hld_Omega=ptr(hld, f64), G=ptr(G),
-                        Lk=ptr(Lk), Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), hld_K=ptr(hldK, f64),
-                        info=ptr(info, i32), A=ptr(A), B=ptr(B), kq=ptr(kq), W=ptr(W), KD=ptr(KD, f64), mean=ptr(mean),
-                        q2=ptr(q2),
-                        kl_acc=ptr(kl, f64) if meta["with_kl"] else None, ws64=ptr(ws64, f64),
-                        engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
-                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0, Kuu_ext=ptr(Kuu_e))
-        check(lib().gpsa_data_layer_fwd(C.byref(a), stream()), "data_layer_fwd")
+        ops().data_layer_fwd(kind, D, M, L, R, Gtilde, log_ls, log_var, delta_F, Omega, hld, G, Lk, Kinv, Kinv64, hldK, info,
+                             A, B, kq, W, KD, mean, q2, kl if meta["with_kl"] else None, ws64, engine, tc_ws, Kuu_e)
         ctx.meta = meta
         ctx.engine = engine
         ctx.dims = (S, N)
@@ -432,16 +405,9 @@ class DataLayerPre(torch.autograd.Function):
         H = _new(dev, _lib.feat_count(M), L)
         tc_ws = _lib.tc_workspace(M, R, L, dev) if engine in TC_ENGINES else None
         ws64 = _new(dev, 3 * M * M, dtype=f64)
-        a = DataBwdArgs(kind=meta["kind"], D=D, M=M, L=L, R=R, Gt=ptr(Gtilde), log_ls=ptr(log_ls),
-                        log_var=ptr(log_var), dlt=ptr(delta_F), Omega=ptr(Omega), G=ptr(G),
-                        Kinv=ptr(Kinv), Kinv64=ptr(Kinv64, f64), A=ptr(A), B=ptr(B), W=ptr(W), KD=ptr(KD, f64),
-                        mean_bar=ptr(mean_bar), q2_bar=ptr(q2_bar), kq_bar=ptr(kq_bar), kl_bar=ptr(klb),
-                        G_bar=ptr(G_bar), acc_Gt=ptr(acc_Gt, f64),
-                        acc_hyp=ptr(acc_hyp, f64), dlt_bar=ptr(dlt_bar), Obar=ptr(Obar),
-                        q1bar=ptr(q1bar), Abar=ptr(Abar), C=ptr(Cm), H=ptr(H), ws64=ptr(ws64, f64),
-                        engine=engine, tc_ws=ptr(tc_ws, torch.uint8),
-                        tc_ws_bytes=tc_ws.numel() if tc_ws is not None else 0, Kuu_bar=ptr(Kuu_b))
-        check(lib().gpsa_data_layer_bwd(C.byref(a), stream()), "data_layer_bwd")
+        ops().data_layer_bwd(meta["kind"], D, M, L, R, Gtilde, log_ls, log_var, delta_F, Omega, G, Kinv, Kinv64, A, B, W, KD,
+                             mean_bar, q2_bar, kq_bar, klb, G_bar, acc_Gt, acc_hyp, dlt_bar, Obar, q1bar, Abar, Cm, H, ws64,
+                             engine, tc_ws, Kuu_b)
         coef = _c((-0.5 * klb).expand(L)) if use_kl else None
         del tc_ws
         Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
@@ -465,7 +431,7 @@ class SampleF(torch.autograd.Function):
         if not (F.is_contiguous() and var.is_contiguous()):
             raise _lib.GPSALibraryError("SampleF expects the contiguous outputs of DataLayerPre")
         kq, eps = _c(kq.detach()), _c(eps.detach())
-        check(lib().gpsa_sample_fwd(S * N, L, ptr(kq), ptr(eps), ptr(F), ptr(var), stream()), "sample_fwd")
+        ops().sample_fwd(S * N, L, kq, eps, F, var)
         ctx.save_for_backward(eps, var)
         return F
 
@@ -476,8 +442,7 @@ class SampleF(torch.autograd.Function):
         S, N, L = var.shape
         F_bar = _c(F_bar)
         q2_bar, kq_bar = _new(var, S, N, L), _new(var, S, N)
-        check(lib().gpsa_sample_bwd(S * N, L, ptr(F_bar), ptr(eps), ptr(var), ptr(q2_bar), ptr(kq_bar), stream()),
-              "sample_bwd")
+        ops().sample_bwd(S * N, L, F_bar, eps, var, q2_bar, kq_bar)
         return F_bar, q2_bar, kq_bar, None
 
 
@@ -485,8 +450,7 @@ def philox_normal(key, S, N, L, gene_off=0, samp_off=0):
     """eps [S,N,L] of the counter-based generator the fused sampling stage draws from in-kernel (same numbers)."""
     with torch.cuda.device(key.device):
         out = torch.empty(S, N, L, dtype=f32, device=key.device)
-        check(lib().gpsa_philox_normal(N, S, L, ptr(key, torch.int64), int(gene_off), int(samp_off), ptr(out), stream()),
-              "philox_normal")
+        ops().philox_normal(N, S, L, key, int(gene_off), int(samp_off), out)
     return out
 
 
@@ -514,10 +478,8 @@ class SampleNLL(torch.autograd.Function):
         eps = _c(eps.detach()) if eps is not None else None
         kqb = _new(U, S, N)
         acc = _zeros(U, 2, dtype=f64)  # [-LL, d(-LL)/dlog_noise]
-        check(lib().gpsa_sample_ll_fused(N, S, L, ptr(kq), ptr(Y), ptr(log_noise), ptr(eps),
-                                         ptr(key, torch.int64) if key is not None else None,
-                                         int(meta.get("gene_off", 0)), int(meta.get("samp_off", 0)), ptr(U), ptr(Gu),
-                                         ptr(kqb), acc.data_ptr(), acc.data_ptr() + 8, stream()), "sample_ll_fused")
+        ops().sample_ll_fused(N, S, L, kq, Y, log_noise, eps, key, int(meta.get("gene_off", 0)),
+                              int(meta.get("samp_off", 0)), U, Gu, kqb, acc[0:1], acc[1:2])
         ctx.save_for_backward(U, Gu, kqb, acc)
         ctx.used = False
         return acc[0].to(f32)
@@ -531,10 +493,9 @@ class SampleNLL(torch.autograd.Function):
         ctx.used = True
         U, Gu, kqb, acc = ctx.saved_tensors
         g = _c(g.to(f32).reshape(1))
-        st = stream()
         # loss.backward() hands down exactly 1: the kernels then return after one load
         for t in (U, Gu, kqb):
-            check(lib().gpsa_scale_if_not_one(t.numel(), ptr(g), ptr(t), st), "scale_if_not_one")
+            ops().scale_if_not_one(t.numel(), g, t)
         return None, U, Gu, kqb, None, (acc[1] * g).to(f32).reshape(1), None, None
 
 
@@ -551,7 +512,7 @@ class LMCObserve(torch.autograd.Function):
         if W.shape[0] != L:
             raise ValueError(f"W has shape {tuple(W.shape)}, latent samples have {L} outputs")
         out = _new(F_lat, S, N, P)
-        check(lib().gpsa_lmc_fwd(S * N, L, P, ptr(F_lat), ptr(W), ptr(out), stream()), "lmc_fwd")
+        ops().lmc_fwd(S * N, L, P, F_lat, W, out)
         ctx.save_for_backward(F_lat, W)
         return out
 
@@ -563,7 +524,7 @@ class LMCObserve(torch.autograd.Function):
         P = W.shape[1]
         Fb = _c(Fb)
         Flb, Wb = _new(F_lat, S, N, L), _new(W, L, P)
-        check(lib().gpsa_lmc_bwd(S * N, L, P, ptr(F_lat), ptr(W), ptr(Fb), ptr(Flb), ptr(Wb), stream()), "lmc_bwd")
+        ops().lmc_bwd(S * N, L, P, F_lat, W, Fb, Flb, Wb)
         return Flb, Wb
 
 
@@ -586,8 +547,7 @@ class LMCNLL(torch.autograd.Function):
             raise ValueError(f"outputs {tuple(Y.shape)} / loadings {tuple(W.shape)} do not match samples {(S, N, L)}")
         Flb, Wb = _new(F_lat, S, N, L), _new(W, L, P)
         acc = _zeros(F_lat, 2, dtype=f64)
-        check(lib().gpsa_lmc_ll_fused(N, S, L, P, ptr(F_lat), ptr(W), ptr(Y), ptr(log_noise), ptr(Flb), ptr(Wb),
-                                      acc.data_ptr(), acc.data_ptr() + 8, stream()), "lmc_ll_fused")
+        ops().lmc_ll_fused(N, S, L, P, F_lat, W, Y, log_noise, Flb, Wb, acc[0:1], acc[1:2])
         ctx.save_for_backward(Flb, Wb, acc)
         ctx.used = False
         return acc[0].to(f32)
@@ -601,7 +561,7 @@ class LMCNLL(torch.autograd.Function):
         Flb, Wb, acc = ctx.saved_tensors
         g = _c(g.to(f32).reshape(1))
         for t in (Flb, Wb):
-            check(lib().gpsa_scale_if_not_one(t.numel(), ptr(g), ptr(t), stream()), "scale_if_not_one")
+            ops().scale_if_not_one(t.numel(), g, t)
         return Flb, Wb, None, (acc[1] * g).to(f32).reshape(1)
 
 
@@ -631,7 +591,7 @@ class GaussianLL(torch.autograd.Function):
         if Y.shape != (N, P):
             raise ValueError(f"outputs have shape {tuple(Y.shape)}, F_samples imply {(N, P)}")
         acc = _zeros(F, 1, dtype=f64)
-        check(lib().gpsa_gaussian_ll_fwd(N, P, S, ptr(F), ptr(Y), ptr(log_noise), ptr(acc, f64), stream()), "ll_fwd")
+        ops().gaussian_ll_fwd(N, P, S, F, Y, log_noise, acc)
         ctx.save_for_backward(F, Y, log_noise)
         return acc.to(f32).reshape(())
 
@@ -643,6 +603,5 @@ class GaussianLL(torch.autograd.Function):
         llb = _c(ll_bar.to(f32).reshape(1))
         F_bar = _new(F, S, N, P)
         acc = _zeros(F, 1, dtype=f64)
-        check(lib().gpsa_gaussian_ll_bwd(N, P, S, ptr(F), ptr(Y), ptr(log_noise), ptr(llb), ptr(F_bar),
-                                         ptr(acc, f64), stream()), "ll_bwd")
+        ops().gaussian_ll_bwd(N, P, S, F, Y, log_noise, llb, F_bar, acc)
         return F_bar, None, acc.to(f32)

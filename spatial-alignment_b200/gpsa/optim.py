@@ -5,8 +5,6 @@ every training loop of the reference uses (examples/grid_example.py:59) -- so ru
 The step count lives on the device, so `step()` can be captured in a CUDA graph (gpsa.graph.GraphedIteration)
 without the `capturable=True` variant's extra kernels.
 """
-import ctypes as C
-
 import torch
 
 from . import _lib
@@ -37,23 +35,20 @@ class Adam(torch.optim.Optimizer):
                 chunk = params[i:i + _lib.ADAM_MAX_TENSORS]
                 if i not in steps:  # device-side step counts, one per tensor of this launch
                     steps[i] = torch.zeros(_lib.ADAM_MAX_TENSORS, dtype=torch.float32, device=dev)
-                a = _lib.AdamArgs(count=len(chunk), lr=group["lr"], beta1=group["betas"][0], beta2=group["betas"][1],
-                                  eps=group["eps"], step=steps[i].data_ptr())
-                for k, p in enumerate(chunk):
+                grads, ms, vs = [], [], []
+                for p in chunk:
                     st = self.state[p]
                     if not st:
                         st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                         st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    if not p.is_contiguous() or p.dtype != torch.float32:
-                        raise _lib.GPSALibraryError("gpsa.optim.Adam expects contiguous float32 parameters")
                     g = p.grad
                     if g is not None and (not g.is_contiguous() or g.dtype != torch.float32):
                         g = g.contiguous().float()
                         keep.append(g)
-                    a.p[k], a.m[k], a.v[k] = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                    a.g[k] = g.data_ptr() if g is not None else None
-                    a.n[k] = p.numel()
-                with torch.cuda.device(dev):
-                    _lib.check(_lib.lib().gpsa_adam_step(C.byref(a), _lib.stream()), "adam_step")
+                    grads.append(g)
+                    ms.append(st["exp_avg"])
+                    vs.append(st["exp_avg_sq"])
+                _lib.ops().adam_step([p.data for p in chunk], grads, ms, vs, float(group["lr"]), float(group["betas"][0]),
+                                     float(group["betas"][1]), float(group["eps"]), steps[i])
             del keep
         return loss

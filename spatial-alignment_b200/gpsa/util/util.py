@@ -95,9 +95,7 @@ def kmeans_gpu(X, n_clusters, iters=30, seed=0, n_init=3):
         for _ in range(max(1, int(n_init))):
             centres = _kmeanspp_seeds(Xd, K, rng)
             inertia = torch.zeros(1, dtype=torch.float64, device=Xd.device)
-            _lib.check(_lib.lib().gpsa_kmeans_lloyd(N, D, K, Xd.data_ptr(), centres.data_ptr(), int(iters),
-                                                    assign.data_ptr(), sums.data_ptr(), inertia.data_ptr(), _lib.stream()),
-                       "kmeans_lloyd")
+            _lib.ops().kmeans_lloyd(N, D, K, Xd, centres, int(iters), assign, sums, inertia)
             val = float(inertia)
             if best is None or val < best[1]:
                 best = (centres, val)

@@ -130,3 +130,24 @@ def test_library_exports_every_declared_symbol():
     assert so.gpsa_version() >= 100
     so.gpsa_feat_count.restype = ctypes.c_long
     assert so.gpsa_feat_count(25) == 10 * 64 and so.gpsa_feat_count(200) == 325 * 64
+
+
+def test_torch_custom_op_layer_registers_every_launcher():
+    """TORCH_LIBRARY(gpsa_b200): every stream-taking entry point of include/gpsa_b200.h is a torch custom op with a
+    schema (pointers -> Tensor? / Tensor(a!)?, sizes -> int), and CPU tensors are refused with a RuntimeError."""
+    import re
+
+    from gpsa import _lib
+
+    ops = _lib.ops()
+    header = open(os.path.join(ROOT, "include", "gpsa_b200.h")).read()
+    launchers = re.findall(r"\bint\s+gpsa_(\w+)\s*\(([^;]*?)cudaStream_t stream\)\s*;", header, flags=re.S)
+    assert len(launchers) >= 30
+    for name, _ in launchers:
+        assert hasattr(ops, name), f"torch.ops.gpsa_b200.{name} is not registered"
+        schema = str(getattr(ops, name).default._schema)
+        assert schema.startswith(f"gpsa_b200::{name}(") and schema.endswith("-> ()")
+    s = str(ops.sample_fwd.default._schema)
+    assert "Tensor(m4!)? a4" in s and "int a0" in s          # outputs are declared mutable
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.sample_fwd(4, 2, torch.zeros(4), torch.zeros(4, 2), torch.zeros(4, 2), torch.zeros(4, 2))
