@@ -261,7 +261,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_2d(st, &tmA_hi, &full[stage], kb * BK, mt * TM);
             tma_load_2d(st + A_TILE_BYTES, &tmA_lo, &full[stage], kb * BK, mt * TM);
           }
-          if (!(MODE == MODE_TEST && p.batch > 0)) {
+          if (MODE == MODE_OMEGA) {  // G^T is stored K-block-major (pack_Gt_kernel): the tile is one contiguous piece
+            tma_load_3d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], 0, nt * TN, kb);
+            tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], 0, nt * TN, kb);
+          } else if (!(MODE == MODE_TEST && p.batch > 0)) {
             tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], kb * BK, nt * TN);
             tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, &full[stage], kb * BK, nt * TN);
           }
@@ -612,8 +615,13 @@ __global__ void pack_G_kernel(long R, int L, int Lp, const float* __restrict__ G
   }
 }
 
-// transposed split: out[p, r] = G[r, p], pitch Rp
-__global__ void pack_Gt_kernel(long R, int L, long Rp, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
+// transposed split in K-BLOCK-MAJOR order: out[r / 64][p][r % 64] = G[r, p]  (rows r >= R of the last block are zero).
+// The B operand tile of the Omega-bar product -- 256 genes x 64 consecutive r -- is then ONE contiguous 32 KB piece of
+// memory.  With the plain [L, R] transpose the 256 rows of a tile were R * 2 bytes apart: at the C5 rank shape
+// (R = 6.4 M) every 128-byte row of every TMA box sat in its own 2 MB page and the product ran at 224 TF/s against
+// 403 TF/s at R = 128 000 (the rate fell monotonically with the row stride: 256 KB / 1.3 MB / 1.6 MB / 12.8 MB ->
+// 403 / 347 / 318 / 224 TF/s).
+__global__ void pack_Gt_kernel(long R, int L, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
                                __nv_bfloat16* __restrict__ lo) {
   __shared__ float t[32][33];
   const long r0 = (long)blockIdx.x * 32;
@@ -626,12 +634,13 @@ __global__ void pack_Gt_kernel(long R, int L, long Rp, const float* __restrict__
   __syncthreads();
   for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
     const int pp = p0 + yy;
-    const long r = r0 + threadIdx.x;
-    if (pp < L && r < R) {
+    const long r = r0 + threadIdx.x;  // r0 is a multiple of 32: the 32 lanes stay inside one 64-row K block
+    if (pp < L) {
       __nv_bfloat16 h, l;
-      split_one(t[threadIdx.x][yy], h, l);
-      hi[(long)pp * Rp + r] = h;
-      lo[(long)pp * Rp + r] = l;
+      split_one(t[threadIdx.x][yy], h, l);  // zero beyond R
+      const long o = ((r >> 6) * L + pp) * 64 + (r & 63);
+      hi[o] = h;
+      lo[o] = l;
     }
   }
 }
@@ -785,7 +794,7 @@ AlphaLayout alpha_layout(int M, long R, int L) {
 struct OmegaLayout { long Rp; size_t gt, apad, total; };
 OmegaLayout omega_layout(int M, long R, int L) {
   OmegaLayout o;
-  o.Rp = rup(R, 8);
+  o.Rp = rup(R, BK);  // whole K blocks (pack_Gt_kernel zero-fills the tail)
   o.gt = al256((size_t)L * o.Rp * 2);
   o.apad = (R % 4 == 0) ? 0 : al256((size_t)M * rup(R, 4) * 4);  // TMA needs a 16-byte row pitch: padded copy of A
   o.total = 2 * o.gt + o.apad + 256;  // + the lockstep counter
@@ -1039,12 +1048,18 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
   uint8_t* w = static_cast<uint8_t*>(ws);
   __nv_bfloat16 *gt_hi = (__nv_bfloat16*)w, *gt_lo = (__nv_bfloat16*)(w + o.gt);
   {
-    dim3 grid(gpsa_cdiv(R, 32), gpsa_cdiv(L, 32)), block(32, 8);
-    pack_Gt_kernel<<<grid, block, 0, st>>>(R, L, o.Rp, G, gt_hi, gt_lo);
+    dim3 grid((unsigned)(o.Rp / 32), gpsa_cdiv(L, 32)), block(32, 8);
+    pack_Gt_kernel<<<grid, block, 0, st>>>(R, L, G, gt_hi, gt_lo);
     GPSA_LAUNCH_CHECK();
   }
   CUtensorMap tb_hi, tb_lo, ta_raw;
-  if (make_tmap_2d(&tb_hi, gt_hi, R, L, o.Rp, TN) || make_tmap_2d(&tb_lo, gt_lo, R, L, o.Rp, TN)) return GPSA_ERR_CUDA;
+  {
+    // [K block][gene][64 r]: box = 64 r x 256 genes x 1 block = one contiguous tile
+    const uint64_t dims[3] = {(uint64_t)BK, (uint64_t)L, (uint64_t)(o.Rp / BK)};
+    const uint64_t str[2] = {(uint64_t)BK * 2, (uint64_t)L * BK * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)TN, 1};
+    if (make_tmap(&tb_hi, gt_hi, 3, dims, str, box) || make_tmap(&tb_lo, gt_lo, 3, dims, str, box)) return GPSA_ERR_CUDA;
+  }
   if (make_raw_map(&ta_raw, M, R, A, w + 2 * o.gt, st)) return GPSA_ERR_CUDA;
   const long NF = feat_nblk(M) * FBK;
   GemmParams p = {};
