@@ -75,6 +75,12 @@ class _FlatAllReduce:
     def _build_flat(self, model, names):
         named = dict(model.named_parameters())
         self.shared = [(n, named[n]) for n in names if n in named and named[n].requires_grad]
+        # replicas must START identical (an initialisation with run-to-run round-off, e.g. the GPU k-means, would leave
+        # the ranks a few ulps apart for good: identical gradients never pull them together): rank 0's values win
+        if self.world > 1 and dist.is_available() and dist.is_initialized():
+            with torch.no_grad():
+                for _, p in self.shared:
+                    dist.broadcast(p.data, src=0, group=self.group)
         total = sum(p.numel() for _, p in self.shared)
         ref = self.shared[0][1]
         # [shared grads ..., local loss]: the trailing slot carries the scalar loss so that logging needs no second collective
