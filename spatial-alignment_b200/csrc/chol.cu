@@ -515,7 +515,11 @@ template <> struct PkThreads<float> { static constexpr int v = PK_THREADS_F32; }
 // Ain -> Aout (may alias), log-determinant in TL
 template <typename T, typename TL>
 int potrf_launch(int M, int batch, const T* Ain, T* Aout, TL* half_logdet, int* info, cudaStream_t st) {
+#ifdef GPSA_DEBUG  // experiments only: force the panel kernels
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+#else
+  constexpr int no_packed = 0;
+#endif
   constexpr int TH = PkThreads<T>::v;
   const size_t psm = packed_smem<T>(M, 0);
   const size_t cap = sizeof(T) == 4 ? 113 * 1024 : 226 * 1024;  // fp32: two CTAs per SM
@@ -547,7 +551,11 @@ int potrf_launch(int M, int batch, const T* Ain, T* Aout, TL* half_logdet, int* 
 
 template <typename T>
 int trtri_launch(int M, int batch, const T* L, T* X, cudaStream_t st) {
+#ifdef GPSA_DEBUG  // experiments only: force the panel kernels
   static const int no_packed = [] { const char* e = getenv("GPSA_NO_PACKED_CHOL"); return e ? atoi(e) : 0; }();
+#else
+  constexpr int no_packed = 0;
+#endif
   constexpr int TH = PkThreads<T>::v;
   const size_t psm = packed_smem<T>(M, 2 * PB);
   if (!no_packed && psm <= 226 * 1024 && L != X) {

@@ -416,7 +416,11 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
     else gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
   } else {
     auto padded = [&](int t) { return (long)gpsa_cdiv(M, t) * t * ((long)gpsa_cdiv(N, t) * t); };
-    static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();  // experiments
+#ifdef GPSA_DEBUG  // experiments only: force a tile family
+    static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();
+#else
+    constexpr int force = 0;
+#endif
     // small problems (the per-view warp-layer products): the 8x8-micro-tile grid would not fill the machine
     const long big_ctas = (long)gpsa_cdiv(M, 104) * gpsa_cdiv(N, 104) * batch * split_k;
     // DMMA path: 104 x 104 CTA tiles (13 warps, 8 x 104 each) when M pads well to 208 (the M = 200 algebra), else

@@ -71,6 +71,46 @@ __global__ void __launch_bounds__(256) kmat_fwd_kernel(int M, long R, const floa
   }
 }
 
+// 128-bit variant (R % 4 == 0, 16-byte aligned x2 and K): one thread = four consecutive columns r, their 4*D
+// coordinates arrive as D float4 loads, every row of K leaves as one float4 store.
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) kmat_fwd4_kernel(int M, long R4, const float* __restrict__ x1,
+                                                        const float4* __restrict__ x2, const float* __restrict__ log_ls,
+                                                        const float* __restrict__ log_var, float4* __restrict__ K) {
+  __shared__ float z[FWD_MT * D];
+  const int m0 = blockIdx.y * FWD_MT;
+  if (threadIdx.x < FWD_MT * D) {
+    const int mm = threadIdx.x / D, d = threadIdx.x % D;
+    z[threadIdx.x] = (m0 + mm < M) ? x1[(long)(m0 + mm) * D + d] : 0.f;
+  }
+  __syncthreads();
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;  // columns 4q .. 4q+3
+  if (q >= R4) return;
+  const float inv_ls = expf(-log_ls[0]), var = expf(log_var[0]);
+  float c[4 * D];  // c[j*D + d] = x2[4q + j][d]
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float4 v = x2[q * D + i];
+    c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+  }
+#pragma unroll
+  for (int mm = 0; mm < FWD_MT; ++mm) {
+    if (m0 + mm >= M) break;
+    float k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float t = z[mm * D + d] - c[j * D + d];
+        r2 = fmaf(t, t, r2);
+      }
+      k[j] = kval<KIND>(r2, inv_ls, var);
+    }
+    K[(long)(m0 + mm) * R4 + q] = make_float4(k[0], k[1], k[2], k[3]);
+  }
+}
+
 // dK/d(stuff) pieces shared by both backward phases.  Returns K and writes
 //   coef : dK/dx1_d = -coef * (x1_d - x2_d),  dK/dx2_d = +coef * (x1_d - x2_d)
 //   dls  : dK/dlog_ls
@@ -196,8 +236,14 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(int M, long R, long 
 template <int D, int KIND>
 int launch_fwd(int M, long R, const float* x1, const float* x2, const float* ls, const float* var, float* K,
                cudaStream_t st) {
-  dim3 grid(gpsa_cdiv(R, 256), gpsa_cdiv(M, FWD_MT));
-  kmat_fwd_kernel<D, KIND><<<grid, 256, 0, st>>>(M, R, x1, x2, ls, var, K);
+  if ((R & 3) == 0 && R >= 1024 && ((reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(K)) & 15) == 0) {
+    dim3 grid(gpsa_cdiv(R / 4, 256), gpsa_cdiv(M, FWD_MT));
+    kmat_fwd4_kernel<D, KIND><<<grid, 256, 0, st>>>(M, R / 4, x1, reinterpret_cast<const float4*>(x2), ls, var,
+                                                    reinterpret_cast<float4*>(K));
+  } else {
+    dim3 grid(gpsa_cdiv(R, 256), gpsa_cdiv(M, FWD_MT));
+    kmat_fwd_kernel<D, KIND><<<grid, 256, 0, st>>>(M, R, x1, x2, ls, var, K);
+  }
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

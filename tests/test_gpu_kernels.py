@@ -34,7 +34,7 @@ def stream():
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["rbf", "matern12", "matern32"])
 @pytest.mark.parametrize("D", [1, 2, 3])
-@pytest.mark.parametrize("M,R", [(1, 1), (7, 33), (25, 300), (50, 1000), (200, 2049)])
+@pytest.mark.parametrize("M,R", [(1, 1), (7, 33), (25, 300), (50, 1000), (200, 2049), (37, 4096)])  # last: 128-bit path
 def test_kernel_matrix_fwd_bwd(L, kind, D, M, R):
     import gpsa
 
