@@ -308,13 +308,19 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
     from gpsa.parallel import gene_range
 
     S, N, P = cfg["S"], cfg["V"] * cfg["Nv"], cfg["P"]
-    lo, hi = gene_range(P, world, rank)
-    model, data_dict, X, Y, nl = build_model(cfg, args.seed, gene_range=(lo, hi) if world > 1 else None)
+    # what to shard: genes when every rank still fills a good part of a 256-gene MMA tile, else the
+    # Monte-Carlo samples (all gradients all-reduced) -- e.g. C4's 500 genes over 8 GPUs
+    sharding = args.sharding
+    if sharding == "auto":
+        sharding = "samples" if (world > 1 and P // world < 128 and S % world == 0) else "genes"
+    by_genes = sharding == "genes"
+    lo, hi = gene_range(P, world, rank) if by_genes else (0, P)
+    model, data_dict, X, Y, nl = build_model(cfg, args.seed, gene_range=(lo, hi) if (world > 1 and by_genes) else None)
     sharder = None
     if world > 1:
         from gpsa import parallel
 
-        sharder = parallel.GeneSharding(model, world, rank)
+        sharder = parallel.GeneSharding(model, world, rank) if by_genes else parallel.SampleSharding(model, world, rank)
     data_dev = {"expression": {"spatial_coords": data_dict["expression"]["spatial_coords"].cuda(),
                                "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
@@ -420,10 +426,12 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
                 else "fallback (B200_PROFILING.md ~1.4 PF sustained)")
     local_genes = (hi - lo) if world > 1 else P
     f_iter, f_q2 = flops_iter(cfg, genes=local_genes)
+    if world > 1 and not by_genes:  # this rank's share of the samples
+        f_iter, f_q2 = f_iter / world, f_q2 / world
     q_ms = sum(tot_ms[i] for i in range(3))
     q_launch = sum(counts[i] for i in range(3))
     names = ["fwd", "bwd_alpha", "bwd_omega"]
-    engine = _ops.pick_engine(cfg["M"], S * N, local_genes)
+    engine = _ops.pick_engine(cfg["M"], (S * N) if (by_genes or world == 1) else (S // world) * N, local_genes)
     tc = engine in _ops.TC_ENGINES
     kern = {"fwd": "tc_gemm_kernel<3> (implicit-feature forward)", "bwd_alpha": "tc_gemm_kernel<1>",
             "bwd_omega": "tc_gemm_kernel<2>"}
@@ -451,7 +459,9 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
         "whole_step_frac": f_iter / (ms_step * 1e-3) / 1e12 / peak_tf,
     }
     out["sharding"] = ("none" if world == 1 else
-                       f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads")
+                       f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"
+                       if by_genes else
+                       f"samples: the {S} Monte-Carlo samples split over {world} ranks, every rank holds all {P} outputs, one NCCL all-reduce of all grads")
     del model, opt, graphed, sharder, data_dev
     torch.cuda.empty_cache()
     return out
@@ -476,6 +486,8 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole iteration from one CUDA graph (gpsa.graph.GraphedIteration); for the "
                          "launch-bound toy configurations c1/c2")
+    ap.add_argument("--sharding", default="auto", choices=["auto", "genes", "samples"],
+                    help="multi-GPU partition: output genes, Monte-Carlo samples, or auto (samples when a rank would own < 128 genes)")
     ap.add_argument("--genes", type=int, default=None,
                     help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
                          "the JSON line is then NOT the named configuration and says so")
