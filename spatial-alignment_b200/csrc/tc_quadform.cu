@@ -1034,13 +1034,10 @@ extern "C" int gpsa_quadform_bwd_alpha_tc(int M, long R, int L, const float* A, 
   GemmParams p = {};
   p.n_mt = gpsa_cdiv(R, TM);
   p.n_nt = gpsa_cdiv(a.NF, TN);
-  // row tiles of G (hi + lo) that stay L2-resident while the feature panels of W^T sweep past: about half the L2
-  // (the packed W^T is re-read once per group: 5.2 GB of the 6.8 GB DRAM reads ncu saw at C3 with groups of 32)
-  {
-    const long tile_bytes = (long)TM * a.Lp * 4;
-    long gm = (60L << 20) / (tile_bytes > 0 ? tile_bytes : 1);
-    p.group_m = (int)(gm < 8 ? 8 : (gm > 256 ? 256 : gm));
-  }
+  // 32 row tiles of G (hi+lo) stay L2-resident while the feature panels of W^T sweep past.  (The packed W^T is re-read
+  // once per group -- 5.2 GB of the 6.8 GB DRAM reads ncu sees at C3 -- but DRAM is not the bound here: groups of 60
+  // row tiles halved those reads and made the kernel 5 % SLOWER, 26.4 vs 25.0 ms, profiles/r2_products.txt.)
+  p.group_m = 32;
   if (p.group_m > p.n_mt) p.group_m = p.n_mt;
   p.kblocks = gpsa_cdiv(L, BK);
   set_split(p, 1);
