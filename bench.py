@@ -310,17 +310,20 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
     S, N, P = cfg["S"], cfg["V"] * cfg["Nv"], cfg["P"]
     # what to shard: genes when every rank still fills a good part of a 256-gene MMA tile, else the
     # Monte-Carlo samples (all gradients all-reduced) -- e.g. C4's 500 genes over 8 GPUs
-    sharding = args.sharding
-    if sharding == "auto":
-        sharding = "samples" if (world > 1 and P // world < 128 and S % world == 0) else "genes"
-    by_genes = sharding == "genes"
-    lo, hi = gene_range(P, world, rank) if by_genes else (0, P)
-    model, data_dict, X, Y, nl = build_model(cfg, args.seed, gene_range=(lo, hi) if (world > 1 and by_genes) else None)
+    # ranks form a grid: Wg gene slices x Ws sample groups (rank = g * Ws + s); Ws = 1 is pure gene sharding,
+    # Ws = world pure sample sharding
+    Ws = sample_groups(args, world, S, P)
+    Wg = world // Ws
+    by_genes = Ws == 1
+    lo, hi = gene_range(P, Wg, rank // Ws)
+    model, data_dict, X, Y, nl = build_model(cfg, args.seed, gene_range=(lo, hi) if Wg > 1 else None)
     sharder = None
     if world > 1:
         from gpsa import parallel
 
-        sharder = parallel.GeneSharding(model, world, rank) if by_genes else parallel.SampleSharding(model, world, rank)
+        sharder = (parallel.GeneSharding(model, world, rank) if Ws == 1 else
+                   parallel.SampleSharding(model, world, rank) if Wg == 1 else
+                   parallel.HybridSharding(model, world, rank, Ws))
     data_dev = {"expression": {"spatial_coords": data_dict["expression"]["spatial_coords"].cuda(),
                                "outputs": data_dict["expression"]["outputs"].cuda(), "n_samples_list": nl}}
     view_idx, Ns, _, _ = model.create_view_idx_dict(data_dev)
@@ -424,14 +427,13 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks
                 else "fallback (B200_PROFILING.md ~1.4 PF sustained)")
-    local_genes = (hi - lo) if world > 1 else P
+    local_genes = hi - lo
     f_iter, f_q2 = flops_iter(cfg, genes=local_genes)
-    if world > 1 and not by_genes:  # this rank's share of the samples
-        f_iter, f_q2 = f_iter / world, f_q2 / world
+    f_iter, f_q2 = f_iter / Ws, f_q2 / Ws  # this rank's share of the samples
     q_ms = sum(tot_ms[i] for i in range(3))
     q_launch = sum(counts[i] for i in range(3))
     names = ["fwd", "bwd_alpha", "bwd_omega"]
-    engine = _ops.pick_engine(cfg["M"], (S * N) if (by_genes or world == 1) else (S // world) * N, local_genes)
+    engine = _ops.pick_engine(cfg["M"], (S // Ws) * N, local_genes)
     tc = engine in _ops.TC_ENGINES
     kern = {"fwd": "tc_gemm_kernel<3> (implicit-feature forward)", "bwd_alpha": "tc_gemm_kernel<1>",
             "bwd_omega": "tc_gemm_kernel<2>"}
@@ -461,10 +463,31 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
     out["sharding"] = ("none" if world == 1 else
                        f"genes: {P} outputs split over {world} ranks, shared front end replicated, one NCCL all-reduce of shared-parameter grads"
                        if by_genes else
-                       f"samples: the {S} Monte-Carlo samples split over {world} ranks, every rank holds all {P} outputs, one NCCL all-reduce of all grads")
+                       f"samples: the {S} Monte-Carlo samples split over {world} ranks, every rank holds all {P} outputs, one NCCL all-reduce of all grads"
+                       if Wg == 1 else
+                       f"hybrid: {Wg} gene slices x {Ws} sample groups; gene-local grads all-reduced inside a slice's {Ws} replicas, "
+                       f"shared grads over all {world} ranks")
+    out["rank_grid"] = {"gene_slices": Wg, "sample_groups": Ws}
     del model, opt, graphed, sharder, data_dev
     torch.cuda.empty_cache()
     return out
+
+
+def sample_groups(args, world, S, P):
+    """How many of the `world` ranks share one gene slice and split the Monte-Carlo samples between them."""
+    if world == 1:
+        return 1
+    if args.sharding == "genes":
+        return 1
+    if args.sharding == "samples":
+        return world
+    if args.sample_groups:
+        Ws = args.sample_groups
+        if world % Ws or S % Ws:
+            raise SystemExit(f"--sample-groups {Ws} must divide the world size {world} and S = {S}")
+        return Ws
+    # auto: genes while every rank still fills a good part of a 256-gene MMA tile, else the samples
+    return world if (P // world < 128 and S % world == 0) else 1
 
 
 def workload_of(name, cfg):
@@ -486,6 +509,8 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole iteration from one CUDA graph (gpsa.graph.GraphedIteration); for the "
                          "launch-bound toy configurations c1/c2")
+    ap.add_argument("--sample-groups", type=int, default=0,
+                    help="with --sharding auto: ranks per gene slice that split the Monte-Carlo samples (hybrid grid)")
     ap.add_argument("--sharding", default="auto", choices=["auto", "genes", "samples"],
                     help="multi-GPU partition: output genes, Monte-Carlo samples, or auto (samples when a rank would own < 128 genes)")
     ap.add_argument("--genes", type=int, default=None,

@@ -1,4 +1,5 @@
-"""One-process-per-GPU execution of the ELBO iteration: gene sharding.
+"""One-process-per-GPU execution of the ELBO iteration: gene sharding, Monte-Carlo-sample sharding and the two combined
+(SURVEY.md 8(e)).
 
 Given the warped coordinates, the data GP is independent across output genes: gene p owns its own
 Omega_sqt_F[p], delta_F[:, p], outputs[:, p] and noise draws.  Rank r therefore keeps a contiguous slice of
@@ -164,3 +165,79 @@ for _cls in (SampleSharding,):
     _cls.nbytes = GeneSharding.nbytes
     _cls.zero_grad = GeneSharding.zero_grad
     _cls.allreduce = GeneSharding.allreduce
+
+
+class HybridSharding(_FlatAllReduce):
+    """Genes x Monte-Carlo samples: world = n_gene_groups * n_sample_groups ranks, rank = g * n_sample_groups + s.
+
+    Gene sharding alone leaves the front end (warp layer, K_uf, A = K^-1 K_uf and their backward) replicated on every
+    rank; sample sharding alone leaves the gene-batched Omega_F algebra replicated.  On the grid, rank (g, s) holds
+    gene slice g (like GeneSharding over n_gene_groups) and evaluates sample share s of it (like SampleSharding over
+    n_sample_groups): the per-sample front end is divided by n_sample_groups, the per-gene algebra by n_gene_groups,
+    the products by both.  Two all-reduces per iteration: the gene-local gradients (Omega_sqt_F, delta_F of slice g)
+    over the n_sample_groups ranks that share the slice -- neighbouring ranks -- and the shared gradients over all.
+    loss_r = (S_loc / S) (-LL_r) + KL_F,g / n_sample_groups + KL_G / world sums over ranks to the negative ELBO."""
+
+    def __init__(self, model, world, rank, n_sample_groups, group=None):
+        self.model, self.world, self.rank, self.group = model, int(world), int(rank), group
+        Ws = int(n_sample_groups)
+        if Ws < 1 or self.world % Ws:
+            raise ValueError(f"n_sample_groups={Ws} must divide the world size {self.world}")
+        Wg = self.world // Ws
+        self.g, self.s, self.Wg, self.Ws = self.rank // Ws, self.rank % Ws, Wg, Ws
+        if any(model.n_latent_gps[m] is not None for m in model.modality_names):
+            raise NotImplementedError("hybrid sharding with LMC loadings is not supported (use GeneSharding)")
+        self.slice_group = None  # the ranks that hold my gene slice; every rank creates every group, in the same order
+        if self.world > 1 and dist.is_available() and dist.is_initialized():
+            for gi in range(Wg):
+                grp = dist.new_group([gi * Ws + si for si in range(Ws)]) if Ws > 1 else None
+                if gi == self.g:
+                    self.slice_group = grp
+        for mod in model.modality_names:
+            local = int(model.n_latent_outputs[mod])
+            counts = [local] * self.world
+            if self.world > 1 and dist.is_available() and dist.is_initialized():
+                counts = [None] * self.world
+                dist.all_gather_object(counts, local, group=group)
+            model._gene_off[mod] = int(sum(counts[gi * Ws] for gi in range(self.g)))
+            model._kl_F_scale[mod] = 1.0 / Ws
+        model._kl_G_scale = 1.0 / self.world
+        model._sample_shard = (self.s, Ws) if Ws > 1 else None
+        # shared parameters: one flat buffer over the world; gene-local parameters: a second one over the slice group
+        self._build_flat(model, list(SHARED))
+        named = dict(model.named_parameters())
+        shared_ids = {id(p) for _, p in self.shared}
+        self.local = [(n, p) for n, p in named.items() if id(p) not in shared_ids and p.requires_grad]
+        self.flat_local = None
+        if Ws > 1 and self.local:
+            ref = self.local[0][1]
+            self.flat_local = torch.zeros(sum(p.numel() for _, p in self.local), dtype=ref.dtype, device=ref.device)
+            off = 0
+            with torch.no_grad():
+                for _, p in self.local:
+                    if self.slice_group is not None:  # the replicas of a slice start identical
+                        dist.broadcast(p.data, src=self.g * Ws, group=self.slice_group)
+                    p.grad = self.flat_local[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_grad(self):
+        self.flat.zero_()
+        if self.flat_local is not None:
+            self.flat_local.zero_()
+        else:
+            shared_ids = {id(p) for _, p in self.shared}
+            for p in self.model.parameters():
+                if id(p) not in shared_ids:
+                    p.grad = None
+
+    def allreduce(self, loss=None):
+        if loss is not None:
+            self.flat[-1] = loss.detach()
+        if self.world > 1:
+            if self.flat_local is not None:
+                dist.all_reduce(self.flat_local, op=dist.ReduceOp.SUM, group=self.slice_group)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat[-1].clone() if loss is not None else None

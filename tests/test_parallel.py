@@ -114,19 +114,82 @@ def test_shared_gradient_allreduce_gloo_world2():
     assert dict(ret) == {0: True, 1: True}
 
 
+def _cpu_hybrid_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gpsa
+        from gpsa.parallel import SHARED, HybridSharding, gene_range, shard_data_dict, shard_state_dict
+
+        Ws = 2
+        Wg, gi, si = world // Ws, rank // Ws, rank % Ws
+        g = Golden("c1_shipped")
+        full, data_dict = _model_from_golden(g)
+        local_dd = shard_data_dict(data_dict, Wg, gi)
+        np.random.seed(rank)   # replicas of a slice start DIFFERENT: the sharder must make them equal
+        torch.manual_seed(rank)
+        model = gpsa.VariationalGPSA(local_dd, n_spatial_dims=2, m_X_per_view=g.cfg.m_X_per_view, m_G=g.cfg.m_G,
+                                     data_init=True, n_latent_gps=g.n_latent, fixed_view_idx=g.fixed)
+        if si == 0:
+            model.load_state_dict(shard_state_dict(full.state_dict(), Wg, gi))
+        sh = HybridSharding(model, world, rank, Ws)
+        mod = "expression"
+        P = full.state_dict()[f"delta_F_dict.{mod}"].shape[1]
+        ok = model._kl_G_scale == 1.0 / world and model._kl_F_scale[mod] == 1.0 / Ws
+        ok &= model._sample_shard == (si, Ws) and model._gene_off[mod] == gene_range(P, Wg, gi)[0]
+        named = dict(model.named_parameters())
+        want = shard_state_dict(full.state_dict(), Wg, gi)
+        ok &= torch.equal(named[f"delta_F_dict.{mod}"].detach(), want[f"delta_F_dict.{mod}"])        # slice broadcast
+        ok &= torch.equal(named["Xtilde"].detach(), full.state_dict()["Xtilde"])                    # world broadcast
+        for it in range(2):
+            sh.zero_grad()
+            loss = sum((rank + 1.0) * (p ** 2).sum() for n, p in named.items() if n in SHARED)
+            loss = loss + (rank + 1.0) * (named[f"delta_F_dict.{mod}"] ** 2).sum()
+            loss.backward()
+            total = sh.allreduce(loss)
+            wsum = sum(r + 1.0 for r in range(world))
+            lsum = sum(gi * Ws + k + 1.0 for k in range(Ws))   # the replicas of my slice only
+            for n, p in named.items():
+                if n in SHARED:
+                    ok &= torch.allclose(p.grad, 2 * wsum * p.detach(), rtol=1e-6)
+            d = named[f"delta_F_dict.{mod}"]
+            ok &= torch.allclose(d.grad, 2 * lsum * d.detach(), rtol=1e-6)
+            losses = [torch.zeros(()) for _ in range(world)]
+            dist.all_gather(losses, loss.detach())
+            ok &= bool(torch.isclose(total, sum(losses), rtol=1e-6))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_hybrid_grid_allreduce_gloo_world4():
+    """2 gene slices x 2 sample groups: parameters start equal inside a slice (and shared ones everywhere), gene-local
+    gradients sum over the slice's replicas only, shared ones over the world."""
+    world = 4
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cpu_hybrid_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}
+
+
 # --------------------------------------------------------------------------------------------------
 def _gpu_worker(rank, world, port, name, out, inject=True, mode="gene"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import gpsa
-        from gpsa.parallel import GeneSharding, SampleSharding, gene_range, shard_data_dict, shard_state_dict
+        from gpsa.parallel import (GeneSharding, HybridSharding, SampleSharding, gene_range, shard_data_dict,
+                                   shard_state_dict)
+
+        # gene-group coordinates: GeneSharding = (world, rank); hybrid 2 x 2 = (world / 2, rank // 2); samples = (1, 0)
+        Ws = 2 if mode == "hybrid" else 1
+        gw, gr = (world // Ws, rank // Ws) if mode in ("gene", "hybrid") else (1, 0)
 
         g = Golden(name)
         full, data_dict = _model_from_golden(g)
         sd = {k: torch.from_numpy(np.asarray(v)) for k, v in g.params.items() if k not in g.fixed_params}
         full.load_state_dict(sd, strict=True)
-        local_dd = shard_data_dict(data_dict, world, rank) if mode == "gene" else data_dict
+        local_dd = shard_data_dict(data_dict, gw, gr)
         kern = {"rbf": gpsa.rbf_kernel, "matern12": gpsa.matern12_kernel, "matern32": gpsa.matern32_kernel}
         np.random.seed(0)
         torch.manual_seed(0)
@@ -134,16 +197,14 @@ def _gpu_worker(rank, world, port, name, out, inject=True, mode="gene"):
                                      m_G=g.cfg.m_G, data_init=True, n_latent_gps=g.n_latent,
                                      kernel_func_warp=kern[g.cfg.kernel_warp], kernel_func_data=kern[g.cfg.kernel_data],
                                      fixed_view_idx=g.fixed)
-        if mode == "gene":
-            model.load_state_dict(shard_state_dict(full.state_dict(), world, rank, n_latent_gps=g.n_latent))
-        else:
-            model.load_state_dict(full.state_dict())
+        model.load_state_dict(shard_state_dict(full.state_dict(), gw, gr, n_latent_gps=g.n_latent))
         model = model.to("cuda")
         local_dd = {m: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()} for m, d in local_dd.items()}
-        sh = GeneSharding(model, world, rank) if mode == "gene" else SampleSharding(model, world, rank)
+        sh = (GeneSharding(model, world, rank) if mode == "gene" else
+              SampleSharding(model, world, rank) if mode == "sample" else HybridSharding(model, world, rank, Ws))
         view_idx, Ns, _, _ = model.create_view_idx_dict(local_dd)
         P = g.Y[g.mods[0]].shape[1]
-        lo, hi = gene_range(P, world, rank)
+        lo, hi = gene_range(P, gw, gr)
         lmc = any(v is not None for v in g.n_latent.values())
         if mode == "sample" or lmc:   # every rank holds every latent output: full noise (the model keeps its samples)
             lo_e, hi_e = 0, None
@@ -281,3 +342,33 @@ def test_lmc_gene_sharded_iteration_equals_unsharded():
     for n, gref in ref.items():
         how = "cols" if n == f"W_dict.{mod}" else "same"
         assert relerr(_gather(out, world, n, mod, how), gref) < 1e-4, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_shipped", "v3_d3_free"])
+def test_hybrid_sharded_iteration_equals_unsharded(name):
+    """Genes x samples on a 2 x 2 grid of ranks (4 processes sharing cuda:0 over gloo): gene-local gradients are
+    all-reduced inside the slice group, shared ones over the world; loss and gradients equal the unsharded iteration."""
+    from test_gpu_parity import build, run
+
+    g = Golden(name)
+    model, data_dict = build(g)
+    _, loss = run(g, model, data_dict)
+    ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    world, Ws = 4, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, True, "hybrid"), nprocs=world, join=True)
+    out = dict(out)
+    assert abs(out[0]["loss"] - float(loss)) <= 2e-5 * abs(float(loss))
+    mod = g.mods[0]
+    for n, gref in ref.items():
+        if n in (f"Omega_sqt_F_dict.{mod}", f"delta_F_dict.{mod}"):
+            axis = 0 if n.startswith("Omega") else 1
+            for gi in range(world // Ws):   # replicas of a gene slice hold bitwise-identical (all-reduced) gradients
+                assert np.array_equal(out[gi * Ws][n], out[gi * Ws + 1][n]), n
+            got = np.concatenate([out[gi * Ws][n] for gi in range(world // Ws)], axis)
+        else:
+            assert all(np.array_equal(out[0][n], out[r][n]) for r in range(1, world)), n
+            got = out[0][n]
+        assert relerr(got, gref) < 1e-4, n
