@@ -445,7 +445,7 @@ def run_config(config_name, cfg, args, steps, warmup, use_graph, world, rank, wi
                     "issued_tflops": passes * f_one / (per[n] * 1e-3) / 1e12 if per[n] > 0 else None} for n in names}
     dom = max(names, key=lambda n: per[n])
     achieved = products[dom]["algorithmic_tflops"]
-    traffic, traffic_src = load_traffic(config_name if (world == 1 and args.genes is None) else "", dom) if tc else (None, None)
+    traffic, traffic_src = load_traffic(config_name if (world == 1 and args.genes is None and args.samples is None) else "", dom) if tc else (None, None)
     out["roofline"] = {
         "bound": "tensor", "kernel": f"{products[dom]['kernel']} ({dom}: dominant of the three quadratic-form products)",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
@@ -516,6 +516,8 @@ def main():
     ap.add_argument("--genes", type=int, default=None,
                     help="profiling aid: run with this many output genes (e.g. P/8 to see one rank of an 8-GPU run); "
                          "the JSON line is then NOT the named configuration and says so")
+    ap.add_argument("--samples", type=int, default=None,
+                    help="profiling aid like --genes: this many Monte-Carlo samples (S/k = one rank of a k-way sample split)")
     ap.add_argument("--engine", type=int, default=None,
                     help="quadratic-form engine: 0 fp32 SIMT, 1 tcgen05 (default: auto)")
     args = ap.parse_args()
@@ -524,6 +526,9 @@ def main():
     if args.genes is not None:
         cfg["P"] = args.genes
         cfg["desc"] += f" [REDUCED to {args.genes} genes: profiling aid, not the named configuration]"
+    if args.samples is not None:
+        cfg["S"] = args.samples
+        cfg["desc"] += f" [REDUCED to S={args.samples}: profiling aid, not the named configuration]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -568,7 +573,7 @@ def main():
     main_res = run_config(config_name, cfg, args, args.steps, args.warmup, args.graph, world, rank)
 
     others = None
-    if args.config is None and world == 1 and not args.no_others and args.genes is None:
+    if args.config is None and world == 1 and not args.no_others and args.genes is None and args.samples is None:
         others = []
         for name, k, w, graph in (("c1", 50, 10, True), ("c2", 50, 10, True), ("c4", min(args.steps, 5), 3, False)):
             ocfg = dict(CONFIGS[name])

@@ -241,6 +241,8 @@ typedef struct {
   void* tc_ws;            /* engine 1: scratch, gpsa_quadform_tc_ws_bytes(M, R, L) bytes */
   size_t tc_ws_bytes;
   const float* Kuu_ext;   /* kind 3 only: k(Gt,Gt) [M,M] evaluated by the caller, and B is an INPUT holding k(Gt,G) [M,R] */
+  int prior_ready;        /* 1: Lk, Kinv, Kinv64, hld_K, info are INPUTS, already filled by gpsa_prior_prepare(_ext) -- the
+                             caller factorised K_uu ahead of time (it depends on parameters only), e.g. on another stream */
 } gpsa_data_fwd_args;
 int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t stream);
 

@@ -168,7 +168,7 @@ void data_layer_fwd(int64_t kind, int64_t D, int64_t M, int64_t L, int64_t R, co
                     const OT& log_var, const OT& dlt, const OT& Omega, const OT& hld_Omega, const OT& G, const OT& Lk,
                     const OT& Kinv, const OT& Kinv64, const OT& hld_K, const OT& info, const OT& A, const OT& B,
                     const OT& kq, const OT& W, const OT& KD, const OT& mean, const OT& q2, const OT& kl_acc, const OT& ws64,
-                    int64_t engine, const OT& tc_ws, const OT& Kuu_ext) {
+                    int64_t engine, const OT& tc_ws, const OT& Kuu_ext, int64_t prior_ready) {
   static constexpr const char* OPNAME = "data_layer_fwd";
   c10::cuda::CUDAGuard guard(Gt.device());
   gpsa_data_fwd_args a = {};
@@ -179,6 +179,7 @@ void data_layer_fwd(int64_t kind, int64_t D, int64_t M, int64_t L, int64_t R, co
   a.KD = DP(KD, 21); a.mean = FP(mean, 22); a.q2 = FP(q2, 23); a.kl_acc = DP(kl_acc, 24); a.ws64 = DP(ws64, 25);
   a.engine = (int)engine; a.tc_ws = tensor_ptr<void>(tc_ws, OPNAME, 27);
   a.tc_ws_bytes = (tc_ws.has_value() && tc_ws->defined()) ? (size_t)tc_ws->numel() : 0; a.Kuu_ext = FP(Kuu_ext, 28);
+  a.prior_ready = (int)prior_ready;
   const int rc = gpsa_data_layer_fwd(&a, stream_of(Gt));
   TORCH_CHECK(rc == 0, "gpsa_b200::data_layer_fwd failed: ", err_text(rc));
 }
@@ -288,7 +289,7 @@ TORCH_LIBRARY(gpsa_b200, m) {
         "Tensor? Omega, Tensor? hld_Omega, Tensor? G, Tensor(o0!)? Lk, Tensor(o1!)? Kinv, Tensor(o2!)? Kinv64, "
         "Tensor(o3!)? hld_K, Tensor(o4!)? info, Tensor(o5!)? A, Tensor(o6!)? B, Tensor(o7!)? kq, Tensor(o8!)? W, "
         "Tensor(o9!)? KD, Tensor(o10!)? mean, Tensor(o11!)? q2, Tensor(o12!)? kl_acc, Tensor(o13!)? ws64, int engine, "
-        "Tensor(o14!)? tc_ws, Tensor? Kuu_ext) -> ()", &data_layer_fwd);
+        "Tensor(o14!)? tc_ws, Tensor? Kuu_ext, int prior_ready) -> ()", &data_layer_fwd);
   m.def("data_layer_bwd(int kind, int D, int M, int L, int R, Tensor Gt, Tensor? log_ls, Tensor? log_var, Tensor? dlt, "
         "Tensor? Omega, Tensor? G, Tensor? Kinv, Tensor? Kinv64, Tensor? A, Tensor? B, Tensor? W, Tensor? KD, "
         "Tensor? mean_bar, Tensor? q2_bar, Tensor? kq_bar, Tensor? kl_bar, Tensor(o0!)? G_bar, Tensor(o1!)? acc_Gt, "

@@ -1093,11 +1093,13 @@ extern "C" int gpsa_data_layer_fwd(const gpsa_data_fwd_args* a, cudaStream_t st)
   if (a->engine == 1 && (!gpsa_tc_supported(M) || !a->tc_ws)) return GPSA_ERR_UNSUPPORTED;
   if (a->kind == GPSA_KIND_EXTERNAL) {
     // user-supplied covariance function: K_uu comes in, and B already holds K_uf [M,R]
-    if (!a->Kuu_ext) return GPSA_ERR_ARG;
-    TRY(gpsa_prior_prepare_ext(M, a->Kuu_ext, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info, a->ws64, st));
+    if (!a->Kuu_ext && !a->prior_ready) return GPSA_ERR_ARG;
+    if (!a->prior_ready)
+      TRY(gpsa_prior_prepare_ext(M, a->Kuu_ext, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info, a->ws64, st));
   } else {
-    TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
-                           a->ws64, st));
+    if (!a->prior_ready)
+      TRY(gpsa_prior_prepare(a->kind, D, M, a->Gt, a->log_ls, a->log_var, a->Lk, a->Kinv, a->Kinv64, a->hld_K, a->info,
+                             a->ws64, st));
     TRY(gpsa_kernel_matrix_fwd(a->kind, D, M, R, a->Gt, a->G, a->log_ls, a->log_var, a->B, st));
   }
   TRY((gemm_nn<double, double, float, float>(st, M, (int)R, M, 1.0, a->Kinv64, M, a->B, R, 0.0, a->A, R)));

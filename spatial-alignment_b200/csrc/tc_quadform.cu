@@ -69,7 +69,13 @@ constexpr int N_GEN_WARPS = 8;
 __host__ __device__ constexpr bool mode_gen(int mode) { return mode == MODE_OMEGA || mode == MODE_FWD; }
 __host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode_gen(mode) ? RAW_BYTES : 0); }
 __host__ __device__ constexpr int gemm_smem(int mode) { return NSTAGE * stage_bytes(mode) + 1024 /*alignment*/ + 256 /*barriers*/; }
-__host__ __device__ constexpr int gemm_threads(int mode) { return mode_gen(mode) ? 256 + 32 * N_GEN_WARPS : 256; }
+// MODE_ALPHA runs TWO epilogue warp groups (warps 4-7 and 8-11, each warp on the TMEM lane quadrant warp % 4): its K
+// dimension is the gene count, so a rank of an 8-way gene split has 4 K blocks (5 us of MMAs) per tile and one group's
+// contraction epilogue (four 8x8 feature blocks, each a TMEM load + 16 L2 loads + 16 reductions) took longer than that
+__host__ __device__ constexpr int epi_groups(int mode) { return mode == MODE_ALPHA ? 2 : 1; }
+__host__ __device__ constexpr int gemm_threads(int mode) {
+  return mode_gen(mode) ? 256 + 32 * N_GEN_WARPS : 128 + 128 * epi_groups(mode);
+}
 
 struct GemmParams {
   int n_mt, n_nt, group_m, n_split, kblocks, kb_per;
@@ -184,7 +190,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&empty[s], 1);
       mbar_init(&rawfull[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * epi_groups(MODE)); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -318,9 +324,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (!two_level) acc ^= 1;  // two-level: the chain accumulator is always stage 0, stage 1 is the second level
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + 4 * epi_groups(MODE)) {
     // ===== epilogue =====
+    constexpr int NGRP = epi_groups(MODE);
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;  // epilogue warp group: takes every NGRP-th column chunk / feature block
     int acc = 0;
     uint32_t acc_ph[2] = {0, 0};
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -336,7 +344,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&tfull[0], acc_ph[0]);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < TN / 32; ++c) {
+          for (int c = grp; c < TN / 32; c += NGRP) {
             uint32_t v[32];
             ld_acc32(lane_base + c * 32, lane_base + TN + c * 32, prev, v);
             tmem_st32(lane_base + TN + c * 32, v);
@@ -349,11 +357,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           prev = true;
         }
       }
+      const long row = (long)mt * TM + q * 32 + lane;
+      // MODE_ALPHA: this thread's a_r[i], a_r[j] of the feature blocks its group contracts, fetched while the tile's
+      // MMAs still run (L2 round trips under the operand stream are ~1 us: behind the TMEM wait they were the epilogue)
+      constexpr int NBLK_EPI = MODE == MODE_ALPHA ? (TN / FBK) / NGRP : 1;
+      float aI[NBLK_EPI][FB], aJ[NBLK_EPI][FB];
+      int bI[NBLK_EPI], bJ[NBLK_EPI];
+      if (MODE == MODE_ALPHA) {
+        const bool valid = row < p.R;
+#pragma unroll
+        for (int u = 0; u < NBLK_EPI; ++u) {
+          const int b = nt * (TN / FBK) + grp + u * NGRP;
+          bI[u] = -1;
+          bJ[u] = -1;
+          if (b < p.nblk) decode_block(b, p.nb, bI[u], bJ[u]);
+#pragma unroll
+          for (int t = 0; t < FB; ++t) {
+            const int mi = bI[u] * FB + t, mj = bJ[u] * FB + t;
+            aI[u][t] = (valid && bI[u] >= 0 && mi < p.Mind) ? __ldg(&p.Amat[(long)mi * p.R + row]) : 0.f;
+            aJ[u][t] = (valid && bI[u] >= 0 && mj < p.Mind) ? __ldg(&p.Amat[(long)mj * p.R + row]) : 0.f;
+          }
+        }
+      }
       mbar_wait(&tfull[acc], acc_ph[acc]);
       tc_fence_after();
       const uint32_t taddr = lane_base + (uint32_t)acc * TN;  // two-level: acc == 0
       const uint32_t taddr2 = lane_base + TN;
-      const long row = (long)mt * TM + q * 32 + lane;
       if (MODE == MODE_TEST || MODE == MODE_OMEGA || MODE == MODE_FWD) {
         float* Cb = p.C + (MODE == MODE_TEST ? (long)item_batch(p, item) * p.sC : 0);
         const float alpha = MODE == MODE_TEST ? p.alpha : 1.f;
@@ -404,35 +433,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       } else {  // MODE_ALPHA: Abar[:, r] += contraction of Psi[r, (i,j)] with a_r
         const bool valid = row < p.R;
-#pragma unroll 1
-        for (int bb = 0; bb < TN / FBK; ++bb) {
-          const int b = nt * (TN / FBK) + bb;
-          if (b >= p.nblk) break;
-          int I, J;
-          decode_block(b, p.nb, I, J);
-          uint32_t v[64];
-          ld_acc32(taddr + bb * FBK, taddr2 + bb * FBK, prev, v);
-          ld_acc32(taddr + bb * FBK + 32, taddr2 + bb * FBK + 32, prev, v + 32);
-          float aI[FB], aJ[FB], sJ[FB];
 #pragma unroll
-          for (int t = 0; t < FB; ++t) {
-            const int mi = I * FB + t, mj = J * FB + t;
-            aI[t] = (valid && mi < p.Mind) ? __ldg(&p.Amat[(long)mi * p.R + row]) : 0.f;
-            aJ[t] = (valid && mj < p.Mind) ? __ldg(&p.Amat[(long)mj * p.R + row]) : 0.f;
-            sJ[t] = 0.f;
-          }
+        for (int u = 0; u < NBLK_EPI; ++u) {
+          const int bb = grp + u * NGRP;
+          const int I = bI[u], J = bJ[u];
+          if (I < 0) break;  // warp-uniform: past the last feature block
+          float sJ[FB];
+#pragma unroll
+          for (int t = 0; t < FB; ++t) sJ[t] = 0.f;
           const bool diag = (I == J);
 #pragma unroll
-          for (int il = 0; il < FB; ++il) {
-            float si = 0.f;
+          for (int half = 0; half < 2; ++half) {  // 4 feature rows il = 32 accumulator columns at a time
+            uint32_t v[32];
+            ld_acc32(taddr + bb * FBK + half * 32, taddr2 + bb * FBK + half * 32, prev, v);
 #pragma unroll
-            for (int jl = 0; jl < FB; ++jl) {
-              const float psi = __uint_as_float(v[il * FB + jl]);
-              si = fmaf(psi, aJ[jl], si);
-              sJ[jl] = fmaf(psi, aI[il], sJ[jl]);
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int il = half * 4 + i4;
+              float si = 0.f;
+#pragma unroll
+              for (int jl = 0; jl < FB; ++jl) {
+                const float psi = __uint_as_float(v[i4 * FB + jl]);
+                si = fmaf(psi, aJ[u][jl], si);
+                sJ[jl] = fmaf(psi, aI[u][il], sJ[jl]);
+              }
+              const int mi = I * FB + il;
+              if (valid && mi < p.Mind) atomicAdd(&p.Abar[(long)mi * p.R + row], diag ? 2.f * si : si);
             }
-            const int mi = I * FB + il;
-            if (valid && mi < p.Mind) atomicAdd(&p.Abar[(long)mi * p.R + row], diag ? 2.f * si : si);
           }
           if (!diag) {
 #pragma unroll

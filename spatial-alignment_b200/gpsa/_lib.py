@@ -92,7 +92,7 @@ class DataFwdArgs(C.Structure):
         ("Lk", P), ("Kinv", P), ("Kinv64", P), ("hld_K", P), ("info", P),
         ("A", P), ("B", P), ("kq", P), ("W", P), ("KD", P), ("mean", P), ("q2", P),
         ("kl_acc", P), ("ws64", P), ("engine", I), ("tc_ws", P), ("tc_ws_bytes", C.c_size_t),
-        ("Kuu_ext", P),
+        ("Kuu_ext", P), ("prior_ready", I),
     ]
 
 

@@ -42,6 +42,31 @@ def _zeros(like, *shape, dtype=f32):
 
 
 _SIDE = {}
+_OMEGA_STREAM = {}
+
+
+def omega_stream(device, which="omega"):
+    """The stream the gene-batched variational covariances (OmegaChain) are prepared and differentiated on;
+    which="prior": the stream the data layer's K_uu is factorised on ahead of the layer (prior_prepare)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), which)
+    if key not in _OMEGA_STREAM:
+        _OMEGA_STREAM[key] = torch.cuda.Stream(device=device)
+    return _OMEGA_STREAM[key]
+
+
+def prior_prepare(kind, Z, log_ls, log_var):
+    """fp64 factorisation of k(Z,Z) + 1e-5 I (reference gpsa/models/vgpsa.py:390-394) on the current stream:
+    (Lk fp32, K^-1 fp32, K^-1 fp64, half log-det [1] fp64, info [1]) -- what DataLayerPre takes as meta["prior"].  K_uu
+    depends on parameters only, so the model factorises it while the warp layer runs."""
+    Z = _c(Z.detach())
+    M, D = Z.shape
+    with torch.cuda.device(Z.device):
+        Lk, Kinv, Kinv64 = _new(Z, M, M), _new(Z, M, M), _new(Z, M, M, dtype=f64)
+        hldK, info = _zeros(Z, 1, dtype=f64), _zeros(Z, 1, dtype=i32)
+        ws64 = _new(Z, 2 * M * M, dtype=f64)
+        ops().prior_prepare(kind, D, M, Z, _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1)), Lk, Kinv, Kinv64,
+                            hldK, info, ws64)
+    return Lk, Kinv, Kinv64, hldK, info
 
 
 def _side_streams(device, n):
@@ -166,6 +191,44 @@ class OmegaFromSqt(torch.autograd.Function):
         return omega_grad(Osq, None, sym, None)
 
 
+class OmegaChain(torch.autograd.Function):
+    """The variational covariances of one modality as their own autograd node (reference gpsa/models/vgpsa.py:206-210,
+    :410-412):  Osq [L,M,M] -> Omega = Osq Osq^T + 1e-5 I and half log-dets hld [L] (float64), both differentiable, plus
+    the factor (Ltril fp32, L64 fp64 or None when the batch is factorised in fp32) and the info flags.
+
+    Being a node of its own, it runs on whatever stream is current when it is applied -- the model applies it on a side
+    stream -- and autograd runs its backward on that same stream: the gene-batched factorisation overlaps the warp
+    layer's forward, and Osq_bar = 2 (Obar + hld_bar/2 Omega^-1) Osq (trtri + three batched GEMMs) overlaps the warp
+    layer's backward.  meta["tc"] (set by the consumer before the backward) selects the tcgen05 engine for 2 Obar Osq."""
+
+    @staticmethod
+    @on_device_of(2)
+    def forward(ctx, meta, Osq):
+        Osq = _c(Osq.detach())
+        Omega, Ltril, Lfac, hld, info = _omega_prepare(Osq)
+        ctx.meta = meta
+        ctx.save_for_backward(Osq, Lfac)
+        L64 = Lfac if Lfac.dtype == f64 else None
+        ctx.mark_non_differentiable(Ltril, info, *([L64] if L64 is not None else []))
+        return Omega, hld, Ltril, L64, info
+
+    @staticmethod
+    @on_device_of(2)
+    def backward(ctx, Obar, hld_bar, _1, _2, _3):
+        Osq, Lfac = ctx.saved_tensors
+        cur = torch.cuda.current_stream()
+        if Obar is None:
+            Obar = _zeros(Osq, *Osq.shape)
+        else:
+            Obar = _c(Obar)
+            Obar.record_stream(cur)  # produced on the consumer's stream, read here on this node's
+        coef = None
+        if hld_bar is not None:
+            hld_bar.record_stream(cur)
+            coef = _c((0.5 * hld_bar).to(f32))  # d hld / d Omega = 1/2 Omega^-1
+        return None, omega_grad(Osq, Lfac, Obar, coef, tc=bool(ctx.meta.get("tc", False)))
+
+
 def omega_grad(Osq, Lfac, Obar, coef, tc=False):
     """Osq_bar = 2 (Obar + coef Omega^-1) Osq; tc=True runs the 2 Obar Osq product on the tcgen05 engine.
     Lfac: the factor omega_prepare returned for the backward (fp64, or fp32 for large batches); None if coef is None."""
@@ -211,11 +274,7 @@ class WarpLayer(torch.autograd.Function):
         hldK = _zeros(Xtilde, V, dtype=f64)
         saved, outs = [], []
         cur = torch.cuda.current_stream()
-        # meta["overlap"]: work that does not depend on the warp layer (the caller passes the preparation of the
-        # gene-batched Omega_F: large kernels).  It is enqueued on the caller's stream between fork and join, so the
-        # views' latency-bound chains of small kernels run underneath it.
-        overlap = meta.get("overlap")
-        side = _side_streams(Xtilde.device, min(len(free), 4)) if (len(free) > 1 or (overlap and free)) else []
+        side = _side_streams(Xtilde.device, min(len(free), 4)) if len(free) > 1 else []
         keep = []
         ext = kind == _lib.KIND_EXTERNAL
         nper = 4 if ext else 2
@@ -246,8 +305,6 @@ class WarpLayer(torch.autograd.Function):
             keep.append(var)
             saved += [X, eps, Kinv, A, B, T, Ke]
             outs += [Gmean, Gs]
-        if overlap:
-            overlap()
         for s_ in side:
             cur.wait_stream(s_)
         del keep
@@ -330,18 +387,22 @@ class WarpLayer(torch.autograd.Function):
 class DataLayerPre(torch.autograd.Function):
     """One modality of the data GP up to its predictive moments (reference gpsa/models/vgpsa.py:390-421, KL :520-530).
 
-    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D][, Kuu [M,M], Kuf [M,S*N]])
+    forward(meta, Gtilde, log_ls, log_var, delta_F, Omega_sqt_F, G [S,N,D][, Kuu [M,M], Kuf [M,S*N][, Omega, hld]])
       -> (mean [S,N,L], q2 [S,N,L], kq [S,N], KL_F, Kuu_chol_F, Omega_tril_F, info)
-    The last two inputs only with kind = KIND_EXTERNAL (user-supplied covariance callable): k(Gt,Gt) and k(Gt,G) are
-    evaluated by the caller with torch and the backward returns dLoss/dK for both (and nothing for Gtilde / G).
     with q2[s,n,p] = a^T Omega_p a (the hot contraction) and kq = sigma^2 - a^T K a; the marginal variance is
     kq + q2 + 2e-5 and the sample F = mean + sqrt(var) eps is the sampling stage (SampleF / SampleNLL below).
-    meta = dict(kind=int, with_kl=bool[, omega=omega_prepare(Omega_sqt_F)])
+    Kuu, Kuf: only with kind = KIND_EXTERNAL (user-supplied covariance callable): k(Gt,Gt) and k(Gt,G) are evaluated by
+    the caller with torch and the backward returns dLoss/dK for both (and nothing for Gtilde / G); None otherwise.
+    Omega [L,M,M], hld [L]: the differentiable outputs of OmegaChain, whose other outputs come in
+    meta["omega_chain"] = (Ltril, info, chain_meta).  The variational covariances are then a node of their own: the
+    backward returns dLoss/dOmega and dLoss/dhld for them and nothing for Omega_sqt_F.  Without them the layer prepares
+    Omega itself (or takes meta["omega"]) and differentiates it inline.
+    meta = dict(kind=int, with_kl=bool[, omega=omega_prepare(Omega_sqt_F) | omega_chain=(...)][, prior=prior_prepare(...)])
     """
 
     @staticmethod
     @on_device_of(1)
-    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, Kuu=None, Kuf=None):
+    def forward(ctx, meta, Gtilde, log_ls, log_var, delta_F, Osq_F, G, Kuu=None, Kuf=None, Omega_in=None, hld_in=None):
         Gtilde, delta_F, Osq_F = _c(Gtilde.detach()), _c(delta_F.detach()), _c(Osq_F.detach())
         log_ls, log_var = _c(log_ls.detach().reshape(1)), _c(log_var.detach().reshape(1))
         G = _c(G.detach())
@@ -353,15 +414,27 @@ class DataLayerPre(torch.autograd.Function):
         ext = kind == _lib.KIND_EXTERNAL
         if ext and (Kuu is None or Kuf is None or tuple(Kuu.shape) != (M, M) or tuple(Kuf.shape) != (M, R)):
             raise ValueError("external covariance: expected Kuu [M,M] and Kuf [M,S*N]")
-        pre = meta.get("omega")
-        Omega, Ltril, L64, hld, info_O = pre if pre is not None else _omega_prepare(Osq_F)
-        Lk, Kinv, Kinv64 = _new(G, M, M), _new(G, M, M), _new(G, M, M, dtype=f64)
-        hldK = _zeros(G, 1, dtype=f64)
-        info = _zeros(G, 1, dtype=i32)
+        chained = Omega_in is not None
+        if chained:
+            Ltril, info_O, chain_meta = meta["omega_chain"]
+            L64 = None
+            Omega, hld = _c(Omega_in.detach()), _c(hld_in.detach())
+        else:
+            pre = meta.get("omega")
+            Omega, Ltril, L64, hld, info_O = pre if pre is not None else _omega_prepare(Osq_F)
+        prior = meta.get("prior")
+        if prior is not None:
+            Lk, Kinv, Kinv64, hldK, info = prior
+        else:
+            Lk, Kinv, Kinv64 = _new(G, M, M), _new(G, M, M), _new(G, M, M, dtype=f64)
+            hldK = _zeros(G, 1, dtype=f64)
+            info = _zeros(G, 1, dtype=i32)
         A, kq = _new(G, M, R), _new(G, S, N)
         B = _c(Kuf.detach().to(f32)) if ext else _new(G, M, R)  # external: B comes in filled
         Kuu_e = _c(Kuu.detach().to(f32)) if ext else None
         engine = pick_engine(M, R, L)
+        if chained:
+            chain_meta["tc"] = engine in TC_ENGINES
         W = _new(G, _lib.feat_count(M), L) if engine == 0 else _new(G, 1)
         tc_ws = _lib.tc_workspace(M, R, L, G) if engine in TC_ENGINES else None
         KD = _new(G, M, L, dtype=f64)
@@ -369,12 +442,15 @@ class DataLayerPre(torch.autograd.Function):
         kl = _zeros(G, 1, dtype=f64)
         ws64 = _new(G, 2 * M * M, dtype=f64)
         ops().data_layer_fwd(kind, D, M, L, R, Gtilde, log_ls, log_var, delta_F, Omega, hld, G, Lk, Kinv, Kinv64, hldK, info,
-                             A, B, kq, W, KD, mean, q2, kl if meta["with_kl"] else None, ws64, engine, tc_ws, Kuu_e)
+                             A, B, kq, W, KD, mean, q2, kl if meta["with_kl"] else None, ws64, engine, tc_ws, Kuu_e,
+                             1 if prior is not None else 0)
         ctx.meta = meta
         ctx.engine = engine
         ctx.dims = (S, N)
-        ctx.n_in = 9 if Kuu is not None or Kuf is not None else 7
-        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64, Kinv, Kinv64, A, B, W, KD)
+        ctx.n_in = 11 if chained else (9 if Kuu is not None or Kuf is not None else 7)
+        ctx.chained = chained
+        ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64 if not chained else None, Kinv, Kinv64, A, B, W,
+                              KD)
         info_all = torch.cat([info_O, info])
         ctx.mark_non_differentiable(Lk, Ltril, info_all)
         return mean, q2, kq, kl.to(f32).reshape(()), Lk, Ltril, info_all
@@ -408,13 +484,18 @@ class DataLayerPre(torch.autograd.Function):
         ops().data_layer_bwd(meta["kind"], D, M, L, R, Gtilde, log_ls, log_var, delta_F, Omega, G, Kinv, Kinv64, A, B, W, KD,
                              mean_bar, q2_bar, kq_bar, klb, G_bar, acc_Gt, acc_hyp, dlt_bar, Obar, q1bar, Abar, Cm, H, ws64,
                              engine, tc_ws, Kuu_b)
-        coef = _c((-0.5 * klb).expand(L)) if use_kl else None
         del tc_ws
-        Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
         hyp = acc_hyp.to(f32)
+        if ctx.chained:  # OmegaChain turns (dLoss/dOmega, dLoss/dhld) into Osq_bar, on its own stream
+            Osq_bar = None
+            tail = (Obar, (-klb.to(f64)).expand(L) if use_kl else None)  # KL_F holds -hld_p for every gene
+        else:
+            coef = _c((-0.5 * klb).expand(L)) if use_kl else None
+            Osq_bar = omega_grad(Osq_F, L64, Obar, coef, tc=(engine in TC_ENGINES))
+            tail = ()
         if ext:  # C = dLoss/dK_uf; the covariance function's own arguments get their gradients through the caller's autograd
-            return None, None, None, hyp[1:2], dlt_bar, Osq_bar, None, Kuu_b, Cm
-        return (None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar) + ((None, None) if ctx.n_in == 9 else ())
+            return (None, None, None, hyp[1:2], dlt_bar, Osq_bar, None, Kuu_b, Cm) + tail
+        return (None, acc_Gt.to(f32), hyp[0:1], hyp[1:2], dlt_bar, Osq_bar, G_bar) + ((None, None) if ctx.n_in >= 9 else ()) + tail
 
 
 class SampleF(torch.autograd.Function):

@@ -291,17 +291,31 @@ class VariationalGPSA(GPSA):
 
         if not self._kl_mask_ready(free):
             self._set_kl_mask(free)
-        # Omega_F = Omega_sqt Omega_sqt^T + eps I and its factor do not depend on the warp layer: prepared while the
-        # per-view chains run on their side streams (see _ops.WarpLayer.forward)
-        pre_F = {}
-
-        def _prepare_omega_F():
+        # Omega_F = Omega_sqt Omega_sqt^T + eps I and its factor do not depend on the warp layer: an autograd node of its
+        # own (_ops.OmegaChain) on a side stream, so the gene-batched factorisation runs under the warp layer's
+        # latency-bound per-view chains -- and its backward (the inverse and three batched GEMMs) under their backward
+        chain_F = {}
+        cur = torch.cuda.current_stream(dev)
+        om_stream = _ops.omega_stream(dev)
+        om_stream.wait_stream(cur)
+        with torch.cuda.stream(om_stream):
             for mod in mods:
-                pre_F[mod] = _ops.omega_prepare(self.Omega_sqt_F_dict[mod].detach().contiguous())
+                cm = {}
+                chain_F[mod] = _ops.OmegaChain.apply(cm, self.Omega_sqt_F_dict[mod]) + (cm,)
+
+        # ... and so is the data layer's K_uu = k(Gtilde, Gtilde): a single-matrix fp64 factorisation + inverse, pure
+        # latency, that would otherwise sit on the critical path between the two layers
+        prior_F, pr_stream = None, None
+        if self._kind_data is not None:
+            pr_stream = _ops.omega_stream(dev, "prior")
+            pr_stream.wait_stream(cur)
+            with torch.cuda.stream(pr_stream):
+                prior_F = _ops.prior_prepare(_ops.KINDS[self._kind_data], self.Gtilde, self.data_kernel_lengthscale,
+                                             self.data_kernel_variance)
 
         ext_w = self._kind_warp is None
         meta = {"kind": _lib.KIND_EXTERNAL if ext_w else _ops.KINDS[self._kind_warp], "V": V, "S": S, "free": free,
-                "with_kl": True, "kl_mask": self._kl_mask, "overlap": _prepare_omega_F}
+                "with_kl": True, "kl_mask": self._kl_mask}
         flat = []
         for vv in free:
             flat += [X_views[vv], eps_G[vv]]
@@ -353,6 +367,15 @@ class VariationalGPSA(GPSA):
         self.F_latent_samples, self.F_observed_samples = {}, {}
         if G_test is not None:
             self.F_latent_samples_test, self.F_observed_samples_test = {}, {}
+        cur.wait_stream(om_stream)  # join the Omega_F chain; its tensors live in the side stream's pool
+        for mod in mods:
+            for t in chain_F[mod][:5]:
+                if t is not None:
+                    t.record_stream(cur)
+        if prior_F is not None:
+            cur.wait_stream(pr_stream)
+            for t in prior_F:
+                t.record_stream(cur)
         kl = kl_G if self._kl_G_scale == 1.0 else kl_G * self._kl_G_scale
         infos = [info_G]
         ext_d = self._kind_data is None
@@ -372,7 +395,7 @@ class VariationalGPSA(GPSA):
             L = self.n_latent_outputs[mod]
             N = int(Ns[mod])
             Osq = self.Omega_sqt_F_dict[mod]
-            pre = pre_F[mod] if mod in pre_F else _ops.omega_prepare(Osq.detach().contiguous())
+            Omega_F, hld_F, Ltril_O, L64_O, info_O, chain_meta = chain_F[mod]
             # noise of the sampling stage (reference :423): explicit, torch's stream, or a key for the in-kernel generator
             eps_F, key = None, None
             if _eps is not None:
@@ -384,9 +407,9 @@ class VariationalGPSA(GPSA):
             else:
                 raise ValueError(f"rng_mode must be 'philox' or 'torch', got {self.rng_mode!r}")
             mean, q2, kq, kl_F, self.Kuu_chol_F, Ltril_F, info_F = _ops.DataLayerPre.apply(
-                {"kind": kind_d, "with_kl": True, "omega": pre},
+                {"kind": kind_d, "with_kl": True, "omega_chain": (Ltril_O, info_O, chain_meta), "prior": prior_F},
                 self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod], Osq,
-                G_samples[mod], *_k_ext(G_samples[mod]),
+                G_samples[mod], *(_k_ext(G_samples[mod]) or (None, None)), Omega_F, hld_F,
             )
             kl = kl + (kl_F if self._kl_F_scale[mod] == 1.0 else kl_F * self._kl_F_scale[mod])
             infos.append(info_F)
@@ -421,6 +444,7 @@ class VariationalGPSA(GPSA):
                     eps_t = _eps["F_test"][mod].to(dev, torch.float32)
                 else:
                     eps_t = torch.randn(Gt.shape[0], Gt.shape[1], L, device=dev)
+                pre = (Omega_F.detach(), Ltril_O, L64_O if L64_O is not None else Ltril_O, hld_F.detach(), info_O)
                 F_t = _ops.DataLayer.apply(
                     {"kind": kind_d, "with_kl": False, "omega": pre},
                     self.Gtilde, self.data_kernel_lengthscale, self.data_kernel_variance, self.delta_F_dict[mod],
