@@ -69,9 +69,10 @@ constexpr int N_GEN_WARPS = 8;
 __host__ __device__ constexpr bool mode_gen(int mode) { return mode == MODE_OMEGA || mode == MODE_FWD; }
 __host__ __device__ constexpr int stage_bytes(int mode) { return OPER_BYTES + (mode_gen(mode) ? RAW_BYTES : 0); }
 __host__ __device__ constexpr int gemm_smem(int mode) { return NSTAGE * stage_bytes(mode) + 1024 /*alignment*/ + 256 /*barriers*/; }
-// MODE_ALPHA runs TWO epilogue warp groups (warps 4-7 and 8-11, each warp on the TMEM lane quadrant warp % 4): its K
-// dimension is the gene count, so a rank of an 8-way gene split has 4 K blocks (5 us of MMAs) per tile and one group's
-// contraction epilogue (four 8x8 feature blocks, each a TMEM load + 16 L2 loads + 16 reductions) took longer than that
+// MODE_ALPHA runs TWO epilogue warp groups (warps 4-7 and 8-11, each warp on the TMEM lane quadrant warp % 4), one per
+// accumulator stage: its K dimension is the gene count, so a rank of an 8-way gene split has 4 K blocks (3 us of MMAs)
+// per tile and one group's contraction epilogue (four 8x8 feature blocks: TMEM loads, 64 L2 loads, 64 reductions per
+// thread) took longer than that
 __host__ __device__ constexpr int epi_groups(int mode) { return mode == MODE_ALPHA ? 2 : 1; }
 __host__ __device__ constexpr int gemm_threads(int mode) {
   return mode_gen(mode) ? 256 + 32 * N_GEN_WARPS : 128 + 128 * epi_groups(mode);
@@ -190,7 +191,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&empty[s], 1);
       mbar_init(&rawfull[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * epi_groups(MODE)); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -326,13 +327,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp >= 4 && warp < 4 + 4 * epi_groups(MODE)) {
     // ===== epilogue =====
+    // NGRP warp groups (MODE_ALPHA: 2).  One-level items alternate between the two accumulator stages, and group g owns
+    // stage g: it drains every NGRP-th item of this CTA, so one group's epilogue has two tile times to finish.  Two-level
+    // items (chains through stage 0 into the second-level accumulator) are all drained by group 0.
     constexpr int NGRP = epi_groups(MODE);
     const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;  // epilogue warp group: takes every NGRP-th column chunk / feature block
-    int acc = 0;
+    const int grp = (warp - 4) >> 2;
+    int acc = (NGRP > 1 && !two_level) ? grp : 0;
     uint32_t acc_ph[2] = {0, 0};
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int local = 0;  // index of the item among this CTA's items
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+      if (NGRP > 1 && (two_level ? grp != 0 : (local % NGRP) != grp)) continue;  // another group's item
       int mt, nt, ks;
       decode_item(p, item, mt, nt, ks);
       const int kb0 = ks * p.kb_per;
@@ -344,7 +350,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&tfull[0], acc_ph[0]);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = grp; c < TN / 32; c += NGRP) {
+          for (int c = 0; c < TN / 32; ++c) {
             uint32_t v[32];
             ld_acc32(lane_base + c * 32, lane_base + TN + c * 32, prev, v);
             tmem_st32(lane_base + TN + c * 32, v);
@@ -358,23 +364,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
       const long row = (long)mt * TM + q * 32 + lane;
-      // MODE_ALPHA: this thread's a_r[i], a_r[j] of the feature blocks its group contracts, fetched while the tile's
-      // MMAs still run (L2 round trips under the operand stream are ~1 us: behind the TMEM wait they were the epilogue)
-      constexpr int NBLK_EPI = MODE == MODE_ALPHA ? (TN / FBK) / NGRP : 1;
+      // MODE_ALPHA: this thread's a_r[i], a_r[j] for the tile's feature blocks (I_u, J_u), fetched while the tile's MMAs
+      // still run (L2 round trips under the operand stream are ~1 us: behind the TMEM wait they were the epilogue).
+      // Consecutive blocks mostly share I (feat.cu order: J runs from I to nb - 1): a_r[I-rows] is fetched once per run.
+      constexpr int NBLK_EPI = MODE == MODE_ALPHA ? TN / FBK : 1;
       float aI[NBLK_EPI][FB], aJ[NBLK_EPI][FB];
       int bI[NBLK_EPI], bJ[NBLK_EPI];
       if (MODE == MODE_ALPHA) {
         const bool valid = row < p.R;
 #pragma unroll
         for (int u = 0; u < NBLK_EPI; ++u) {
-          const int b = nt * (TN / FBK) + grp + u * NGRP;
+          const int b = nt * (TN / FBK) + u;
           bI[u] = -1;
           bJ[u] = -1;
           if (b < p.nblk) decode_block(b, p.nb, bI[u], bJ[u]);
+          const bool same_I = u > 0 && bI[u] == bI[u > 0 ? u - 1 : 0];  // warp-uniform
 #pragma unroll
           for (int t = 0; t < FB; ++t) {
             const int mi = bI[u] * FB + t, mj = bJ[u] * FB + t;
-            aI[u][t] = (valid && bI[u] >= 0 && mi < p.Mind) ? __ldg(&p.Amat[(long)mi * p.R + row]) : 0.f;
+            if (same_I) aI[u][t] = aI[u > 0 ? u - 1 : 0][t];
+            else aI[u][t] = (valid && bI[u] >= 0 && mi < p.Mind) ? __ldg(&p.Amat[(long)mi * p.R + row]) : 0.f;
             aJ[u][t] = (valid && bI[u] >= 0 && mj < p.Mind) ? __ldg(&p.Amat[(long)mj * p.R + row]) : 0.f;
           }
         }
@@ -432,10 +441,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
       } else {  // MODE_ALPHA: Abar[:, r] += contraction of Psi[r, (i,j)] with a_r
+        // Abar[I-rows] of a run of blocks with the same I is summed in registers and reduced to memory once per run
+        // (the L2 reduction units, not the MMAs, bounded this product at small gene counts): 8 + 8 reductions per block
+        // become 8 per block + 8 per run
         const bool valid = row < p.R;
+        float sI[FB];
+#pragma unroll
+        for (int t = 0; t < FB; ++t) sI[t] = 0.f;
 #pragma unroll
         for (int u = 0; u < NBLK_EPI; ++u) {
-          const int bb = grp + u * NGRP;
           const int I = bI[u], J = bJ[u];
           if (I < 0) break;  // warp-uniform: past the last feature block
           float sJ[FB];
@@ -445,7 +459,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int half = 0; half < 2; ++half) {  // 4 feature rows il = 32 accumulator columns at a time
             uint32_t v[32];
-            ld_acc32(taddr + bb * FBK + half * 32, taddr2 + bb * FBK + half * 32, prev, v);
+            ld_acc32(taddr + u * FBK + half * 32, taddr2 + u * FBK + half * 32, prev, v);
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               const int il = half * 4 + i4;
@@ -456,8 +470,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 si = fmaf(psi, aJ[u][jl], si);
                 sJ[jl] = fmaf(psi, aI[u][il], sJ[jl]);
               }
-              const int mi = I * FB + il;
-              if (valid && mi < p.Mind) atomicAdd(&p.Abar[(long)mi * p.R + row], diag ? 2.f * si : si);
+              sI[il] += diag ? 2.f * si : si;
             }
           }
           if (!diag) {
@@ -467,13 +480,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (valid && mj < p.Mind) atomicAdd(&p.Abar[(long)mj * p.R + row], sJ[jl]);
             }
           }
+          const bool last_of_run = (u + 1 == NBLK_EPI) || bI[u + 1 < NBLK_EPI ? u + 1 : u] != I;  // warp-uniform
+          if (last_of_run) {
+#pragma unroll
+            for (int il = 0; il < FB; ++il) {
+              const int mi = I * FB + il;
+              if (valid && mi < p.Mind) atomicAdd(&p.Abar[(long)mi * p.R + row], sI[il]);
+              sI[il] = 0.f;
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc_ph[acc] ^= 1;
-      if (!two_level) acc ^= 1;
+      if (NGRP == 1 && !two_level) acc ^= 1;
     }
   } else if (MODE == MODE_OMEGA && warp >= 8) {
     // ===== feature-operand generators =====

@@ -14,6 +14,13 @@ from golden_io import Golden, relerr
 from test_host_api import _model_from_golden
 
 
+def _manager():
+    """The result dict's server process must be SPAWNED: a fork of this process inherits its CUDA tensors, and the
+    child's garbage collector freeing one of them (the allocator then records events for blocks used on several
+    streams) aborts with "CUDA error: initialization error" -- seen intermittently on the GPU box."""
+    return mp.get_context("spawn").Manager()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -108,7 +115,7 @@ def _cpu_worker(rank, world, port, ret):
 
 def test_shared_gradient_allreduce_gloo_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = _manager()
     ret = mgr.dict()
     mp.spawn(_cpu_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
@@ -166,7 +173,7 @@ def test_hybrid_grid_allreduce_gloo_world4():
     """2 gene slices x 2 sample groups: parameters start equal inside a slice (and shared ones everywhere), gene-local
     gradients sum over the slice's replicas only, shared ones over the world."""
     world = 4
-    mgr = mp.Manager()
+    mgr = _manager()
     ret = mgr.dict()
     mp.spawn(_cpu_hybrid_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {r: True for r in range(world)}
@@ -240,7 +247,7 @@ def test_sharded_iteration_equals_unsharded(name):
     _, loss = run(g, model, data_dict)
     ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
     world = 2
-    mgr = mp.Manager()
+    mgr = _manager()
     out = mgr.dict()
     mp.spawn(_gpu_worker, args=(world, _free_port(), name, out), nprocs=world, join=True)
     out = dict(out)
@@ -276,7 +283,7 @@ def test_sharded_iteration_equals_unsharded_without_injected_noise(name):
     loss.backward()
     ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
     world = 2
-    mgr = mp.Manager()
+    mgr = _manager()
     out = mgr.dict()
     mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, False), nprocs=world, join=True)
     out = dict(out)
@@ -313,7 +320,7 @@ def test_sample_sharded_iteration_equals_unsharded(name):
     _, loss = run(g, model, data_dict)
     ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
     world = 2
-    mgr = mp.Manager()
+    mgr = _manager()
     out = mgr.dict()
     mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, True, "sample"), nprocs=world, join=True)
     out = dict(out)
@@ -333,7 +340,7 @@ def test_lmc_gene_sharded_iteration_equals_unsharded():
     _, loss = run(g, model, data_dict)
     ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
     world = 2
-    mgr = mp.Manager()
+    mgr = _manager()
     out = mgr.dict()
     mp.spawn(_gpu_worker, args=(world, _free_port(), "lmc", out, True, "gene"), nprocs=world, join=True)
     out = dict(out)
@@ -356,7 +363,7 @@ def test_hybrid_sharded_iteration_equals_unsharded(name):
     _, loss = run(g, model, data_dict)
     ref = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
     world, Ws = 4, 2
-    mgr = mp.Manager()
+    mgr = _manager()
     out = mgr.dict()
     mp.spawn(_gpu_worker, args=(world, _free_port(), name, out, True, "hybrid"), nprocs=world, join=True)
     out = dict(out)
