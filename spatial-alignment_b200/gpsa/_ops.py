@@ -51,6 +51,11 @@ def omega_stream(device, which="omega"):
     key = (device.index if device.index is not None else torch.cuda.current_device(), which)
     if key not in _OMEGA_STREAM:
         _OMEGA_STREAM[key] = torch.cuda.Stream(device=device)
+        # Omega_sqt_F's gradient is produced on this stream and accumulated on the parameter's: intended (autograd
+        # synchronises the two), so the advisory about it is switched off
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
     return _OMEGA_STREAM[key]
 
 
