@@ -595,7 +595,7 @@ def main():
         return
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
         r = reference_rate(cfg, config_name, args.seed, 2, 1)
         cpu = {"value": r["rate"], "unit": "spot-samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "value_is_extrapolated": r["extrapolated"]}
@@ -608,7 +608,7 @@ def main():
                    "l2": "working set (Omega_sqt 320 MB, two [S,N,L] buffers of 1 GB each at c3) far exceeds the 126 MB L2",
                    "noise": "eps_F drawn in-kernel (Philox4x32-10 keyed by seed, sample, spot, global gene); F_samples never materialised (fused sampling + likelihood)",
                    "optimizer": "gpsa.optim.Adam(lr=1e-2): torch.optim.Adam's update as one launch of this library", "cuda_graph": main_res["cuda_graph"],
-                   "sharding": main_res["sharding"]},
+                   "sharding": main_res["sharding"], "rank_grid": main_res.get("rank_grid")},
         "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
         "cpu_baseline": cpu, "clocks": main_res["clocks"], "loss_last": main_res["loss_last"],
     }
