@@ -604,7 +604,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "iters_per_s": main_res["iters_per_s"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload,
-                   "arithmetic": "fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; MxM factorisations fp64",
+                   "arithmetic": ("fp32 data; quadratic form = bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate; prior K_uu / warp-layer MxM algebra fp64; "
+                                  "gene-batched Omega_F: fp64-accumulated SYRK, fp32 factorisation, fp64 log-det"),
                    "l2": "working set (Omega_sqt 320 MB, two [S,N,L] buffers of 1 GB each at c3) far exceeds the 126 MB L2",
                    "noise": "eps_F drawn in-kernel (Philox4x32-10 keyed by seed, sample, spot, global gene); F_samples never materialised (fused sampling + likelihood)",
                    "optimizer": "gpsa.optim.Adam(lr=1e-2): torch.optim.Adam's update as one launch of this library", "cuda_graph": main_res["cuda_graph"],
