@@ -52,24 +52,52 @@ __global__ void __launch_bounds__(256) feat_pack_kernel(int M, int L, const floa
 }
 
 // Obar[p,i,j] (symmetric) = H[(i,j),p] + add_scale * Add[i,j]
+// One CTA per (index block b = (I,J), 32 genes): the 64 x 32 piece of H is read along the genes (128-byte rows) into
+// shared memory and written out as the 8 x 8 block (I,J) of each gene's matrix -- and, off the diagonal, its mirror
+// image (J,I) -- in 32-byte row segments.  (A thread per output element reading H[k(i,j), p] directly touched one
+// 32-byte sector per value: 0.49 ms at C3 for 0.5 GB of useful traffic.)
 __global__ void __launch_bounds__(256) feat_unpack_kernel(int M, int L, const float* __restrict__ H,
                                                           const float* __restrict__ Add, float add_scale,
                                                           const float* __restrict__ add_scale_dev,
                                                           float* __restrict__ Obar) {
+  __shared__ float t[FBK][33];
   const int nb = feat_nb(M);
+  const int b = blockIdx.x;
+  int I, J;
+  decode_block(b, nb, I, J);
   if (add_scale_dev) add_scale *= add_scale_dev[0];
-  const long total = (long)L * M * M;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int j = idx % M;
-    const int i = (idx / M) % M;
-    const int p = idx / ((long)M * M);
-    int a = i, c = j;
-    if (a / FB > c / FB) { a = j; c = i; }
-    const int b = encode_block(a / FB, c / FB, nb);
-    const long k = (long)b * FBK + (a % FB) * FB + (c % FB);
-    float v = H[k * L + p];
-    if (Add) v += add_scale * Add[(long)i * M + j];
-    Obar[idx] = v;
+  const long MM = (long)M * M;
+  for (int p0 = blockIdx.y * 32; p0 < L; p0 += gridDim.y * 32) {
+    for (int idx = threadIdx.x; idx < FBK * 32; idx += 256) {
+      const int pl = idx & 31, f = idx >> 5;
+      t[f][pl] = (p0 + pl < L) ? H[((long)b * FBK + f) * L + p0 + pl] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < FBK * 32; idx += 256) {
+      const int f = idx & (FBK - 1), pl = idx >> 6;
+      const int p = p0 + pl;
+      const int il = f >> 3, jl = f & 7;
+      const int i = I * FB + il, j = J * FB + jl;
+      if (p < L && i < M && j < M) {
+        float v = t[f][pl];
+        if (Add) v += add_scale * Add[(long)i * M + j];
+        Obar[p * MM + (long)i * M + j] = v;
+      }
+    }
+    if (I != J) {
+      for (int idx = threadIdx.x; idx < FBK * 32; idx += 256) {
+        const int g = idx & (FBK - 1), pl = idx >> 6;
+        const int p = p0 + pl;
+        const int jl = g >> 3, il = g & 7;  // il fastest: consecutive threads walk a row of the mirrored block
+        const int i = I * FB + il, j = J * FB + jl;
+        if (p < L && i < M && j < M) {
+          float v = t[il * FB + jl][pl];
+          if (Add) v += add_scale * Add[(long)j * M + i];
+          Obar[p * MM + (long)j * M + i] = v;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -260,9 +288,8 @@ extern "C" int gpsa_feat_pack(int M, int L, const float* Omega, float* W, cudaSt
 extern "C" int gpsa_feat_unpack(int M, int L, const float* H, const float* Add, float add_scale,
                                 const float* add_scale_dev, float* Obar, cudaStream_t st) {
   if (M <= 0 || L <= 0) return GPSA_OK;
-  const long total = (long)L * M * M;
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  feat_unpack_kernel<<<blocks, 256, 0, st>>>(M, L, H, Add, add_scale, add_scale_dev, Obar);
+  dim3 grid((unsigned)feat_nblk(M), (unsigned)((L + 31) / 32 < 64 ? (L + 31) / 32 : 64));
+  feat_unpack_kernel<<<grid, 256, 0, st>>>(M, L, H, Add, add_scale, add_scale_dev, Obar);
   GPSA_LAUNCH_CHECK();
   return GPSA_OK;
 }

@@ -411,11 +411,14 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
   if (split_k < 1) split_k = 1;
 #define GPSA_GEMM_ARGS st, M, N, K, alpha, A, ars, acs, sA, B, brs, bcs, sB, beta, Cm, ldc, sC, batch, split_k, diag, \
                        lower_only, alpha_dev, alpha_dev_stride, tri
+  auto padded = [&](int t) { return (long)gpsa_cdiv(M, t) * t * ((long)gpsa_cdiv(N, t) * t); };
   if (sizeof(T) == 4) {
+    // (104 x 104 tiles, which pad M = 200 to 208 instead of 256, were measured on the two gene-batched Omega^-1 Omega_sqt
+    // products: 1.33 -> 1.21 ms for Linv Osq but 1.33 -> 1.58 ms for Linv^T Y -- 169-thread CTAs, rows that straddle
+    // warps -- so fp32 stays on 128 x 128; profiles/r2_final_launches_c3_summary.txt has the tile that shipped.)
     if (M >= 96 && N >= 96) gemm_launch_cfg<GemmCfg<T, 128, 128, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);
     else gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
   } else {
-    auto padded = [&](int t) { return (long)gpsa_cdiv(M, t) * t * ((long)gpsa_cdiv(N, t) * t); };
 #ifdef GPSA_DEBUG  // experiments only: force a tile family
     static const int force = [] { const char* e = getenv("GPSA_F64_TILE"); return e ? atoi(e) : 0; }();
 #else
@@ -449,7 +452,12 @@ static int gemm_strided(cudaStream_t st, int M, int N, long K, double alpha, con
         return GPSA_OK;
       }
     }
-    if (force == 64 || (force == 0 && big_ctas < 2 * 148)) {
+    // single M x M products of the prior / warp-layer chains (16 CTAs of 64 x 64 at M = 200, LDS-bound on 16 SMs):
+    // 32 x 32 tiles put the same work on 4x as many SMs, same k order per element
+    const long small_ctas = (long)gpsa_cdiv(M, 64) * gpsa_cdiv(N, 64) * batch * split_k;
+    if (force == 0 && big_ctas < 2 * 148 && small_ctas <= 74) {
+      gemm_launch_cfg<GemmCfg<T, 32, 32, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
+    } else if (force == 64 || (force == 0 && big_ctas < 2 * 148)) {
       gemm_launch_cfg<GemmCfg<T, 64, 64, 16, 4, 4>, TA, TB, TC>(GPSA_GEMM_ARGS);
     } else if (M >= 96 && N >= 96) {
       if (force == 104 || (force == 0 && padded(104) < padded(128))) gemm_launch_cfg<GemmCfg<T, 104, 104, 8, 8, 8>, TA, TB, TC>(GPSA_GEMM_ARGS);

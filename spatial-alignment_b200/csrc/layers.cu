@@ -866,14 +866,24 @@ extern "C" int gpsa_prior_prepare_ext(int M, const float* Kuu, float* Lk, float*
 }
 
 namespace {
-// in place: upper triangle <- lower triangle, per matrix
-__global__ void mirror_lower_kernel(long n, int M, float* __restrict__ A) {
-  const long MM = (long)M * M;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
-    const long b = idx / MM;
-    const int e = (int)(idx - b * MM);
-    const int i = e / M, j = e - i * M;
-    if (j > i) A[idx] = A[b * MM + (long)j * M + i];
+// in place: upper triangle <- lower triangle, per matrix.  One CTA (32 x 8) per pair of 32 x 32 tiles (ti >= tj) of one
+// matrix: the lower tile is read along its rows and its transpose written along the rows of the upper tile (a thread
+// per upper element reading A[j][i] directly walks a column: one 32-byte sector per value).
+__global__ void __launch_bounds__(256) mirror_lower_kernel(int M, int nt, float* __restrict__ A) {
+  __shared__ float t[32][33];
+  int ti = 0, rem = blockIdx.x;  // blockIdx.x enumerates the nt (nt + 1) / 2 tile pairs, row by row
+  while (rem > ti) { rem -= ti + 1; ++ti; }
+  const int tj = rem;
+  float* Ab = A + (long)blockIdx.y * M * M;
+  const int i0 = ti * 32, j0 = tj * 32;
+  for (int yy = threadIdx.y; yy < 32; yy += 8) {
+    const int i = i0 + yy, j = j0 + threadIdx.x;
+    t[yy][threadIdx.x] = (i < M && j < M) ? Ab[(long)i * M + j] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += 8) {
+    const int r = j0 + yy, c = i0 + threadIdx.x;  // element (r, c) of the upper tile (tj, ti) = element (c, r) below
+    if (r < M && c < M && c > r) Ab[(long)r * M + c] = t[threadIdx.x][yy];
   }
 }
 }  // namespace
@@ -889,8 +899,14 @@ extern "C" int gpsa_omega_prepare(int M, int B, const float* Osq, float* Omega, 
     // Cholesky per matrix, two CTAs per SM, log-determinant summed in fp64.
     TRY((gemm_strided<double, float, float, float>(st, M, M, M, 1.0, Osq, M, 1, MM, Osq, 1, M, MM, 0.0, Omega, M, MM, B, 1,
                                                    (double)GPSA_OFF, 1)));
-    mirror_lower_kernel<<<grid_for(MM * B), 256, 0, st>>>(MM * B, M, Omega);
-    GPSA_LAUNCH_CHECK();
+    {
+      const int nt = gpsa_cdiv(M, 32);
+      for (int b0 = 0; b0 < B; b0 += 65535) {  // grid.y limit
+        const int nb_ = B - b0 < 65535 ? B - b0 : 65535;
+        mirror_lower_kernel<<<dim3(nt * (nt + 1) / 2, nb_), dim3(32, 8), 0, st>>>(M, nt, Omega + (long)b0 * MM);
+        GPSA_LAUNCH_CHECK();
+      }
+    }
     return gpsa_potrf_batched_f32_ld64(M, B, Omega, Ltril, half_logdet, info, st);
   }
   // Omega = Osq Osq^T + 1e-5 I with fp64 accumulation, kept in fp64 for the factorisation

@@ -669,26 +669,30 @@ __global__ void pack_G_kernel(long R, int L, int Lp, const float* __restrict__ G
 // (R = 6.4 M) every 128-byte row of every TMA box sat in its own 2 MB page and the product ran at 224 TF/s against
 // 403 TF/s at R = 128 000 (the rate fell monotonically with the row stride: 256 KB / 1.3 MB / 1.6 MB / 12.8 MB ->
 // 403 / 347 / 318 / 224 TF/s).
-__global__ void pack_Gt_kernel(long R, int L, const float* __restrict__ G, __nv_bfloat16* __restrict__ hi,
-                               __nv_bfloat16* __restrict__ lo) {
-  __shared__ float t[32][33];
-  const long r0 = (long)blockIdx.x * 32;
-  const int p0 = blockIdx.y * 32;
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+__global__ void __launch_bounds__(256) pack_Gt_kernel(long R, int L, const float* __restrict__ G,
+                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // one 64 r x 64 gene tile per CTA (block 32 x 8): 128-byte reads along the genes, and every (gene, K block) row of the
+  // output -- 64 consecutive r = 128 bytes of bf16 -- written by one warp as bf16 pairs
+  __shared__ float t[64][65];
+  const long r0 = (long)blockIdx.x * 64;
+  const int p0 = blockIdx.y * 64;
+  for (int yy = threadIdx.y; yy < 64; yy += 8) {
     const long r = r0 + yy;
-    const int pp = p0 + threadIdx.x;
-    t[yy][threadIdx.x] = (r < R && pp < L) ? G[r * L + pp] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pp = p0 + threadIdx.x + 32 * h;
+      t[yy][threadIdx.x + 32 * h] = (r < R && pp < L) ? G[r * L + pp] : 0.f;  // zero beyond R: the tail of the last block
+    }
   }
   __syncthreads();
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+  for (int yy = threadIdx.y; yy < 64; yy += 8) {
     const int pp = p0 + yy;
-    const long r = r0 + threadIdx.x;  // r0 is a multiple of 32: the 32 lanes stay inside one 64-row K block
     if (pp < L) {
-      __nv_bfloat16 h, l;
-      split_one(t[threadIdx.x][yy], h, l);  // zero beyond R
-      const long o = ((r >> 6) * L + pp) * 64 + (r & 63);
-      hi[o] = h;
-      lo[o] = l;
+      uint32_t h, l;
+      split_pair(t[2 * threadIdx.x][yy], t[2 * threadIdx.x + 1][yy], h, l);
+      const long o = ((long)blockIdx.x * L + pp) * 64 + 2 * threadIdx.x;
+      *reinterpret_cast<uint32_t*>(hi + o) = h;
+      *reinterpret_cast<uint32_t*>(lo + o) = l;
     }
   }
 }
@@ -740,30 +744,44 @@ static inline bool pack4_ok(const float* src, long ld, long sIn, int K, int Kp) 
          (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 }
 
-__global__ void pack_trans_kernel(long rows, int K, int Kp, long ld, long sIn, const float* __restrict__ in,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  __shared__ float t[32][33];
+__global__ void __launch_bounds__(256) pack_trans_kernel(long rows, int K, int Kp, long ld, long sIn,
+                                                         const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo) {
+  // one 64 row x 64 k tile per CTA (block 32 x 8): 128-byte reads along the rows of the K x rows source, 128-byte writes
+  // (bf16 pairs) along k
+  __shared__ float t[64][65];
   const int b = blockIdx.z;
   const float* src = in + (long)b * sIn;
   const long obase = (long)b * rows * Kp;
   // flattened (row tile, K tile) index on x: either extent can exceed the 65535 limit of grid.y (R-sized operands)
-  const unsigned nkt = (unsigned)((K + 31) / 32);
-  const long r0 = (long)(blockIdx.x / nkt) * 32;
-  const int k0 = (int)(blockIdx.x % nkt) * 32;
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+  const unsigned nkt = (unsigned)((K + 63) / 64);
+  const long r0 = (long)(blockIdx.x / nkt) * 64;
+  const int k0 = (int)(blockIdx.x % nkt) * 64;
+  for (int yy = threadIdx.y; yy < 64; yy += 8) {
     const int k = k0 + yy;
-    const long r = r0 + threadIdx.x;
-    t[yy][threadIdx.x] = (k < K && r < rows) ? src[(long)k * ld + r] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long r = r0 + threadIdx.x + 32 * h;
+      t[yy][threadIdx.x + 32 * h] = (k < K && r < rows) ? src[(long)k * ld + r] : 0.f;
+    }
   }
   __syncthreads();
-  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+  for (int yy = threadIdx.y; yy < 64; yy += 8) {
     const long r = r0 + yy;
-    const int k = k0 + threadIdx.x;
+    const int k = k0 + 2 * threadIdx.x;
     if (r < rows && k < K) {
-      __nv_bfloat16 h, l;
-      split_one(t[threadIdx.x][yy], h, l);
-      hi[obase + r * Kp + k] = h;
-      lo[obase + r * Kp + k] = l;
+      const long o = obase + r * Kp + k;  // even: Kp is a multiple of 8
+      if (k + 1 < K) {
+        uint32_t h, l;
+        split_pair(t[2 * threadIdx.x][yy], t[2 * threadIdx.x + 1][yy], h, l);
+        *reinterpret_cast<uint32_t*>(hi + o) = h;
+        *reinterpret_cast<uint32_t*>(lo + o) = l;
+      } else {
+        __nv_bfloat16 h, l;
+        split_one(t[2 * threadIdx.x][yy], h, l);
+        hi[o] = h;
+        lo[o] = l;
+      }
     }
   }
 }
@@ -961,7 +979,7 @@ extern "C" int gpsa_gemm_tc(long Mr, long Nc, int K, int batch, const float* A, 
       dim3 grid((unsigned)blocks, 1, batch);
       pack_rows_kernel<<<grid, 256, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
     } else {
-      dim3 grid((unsigned)((long)gpsa_cdiv(rows, 32) * gpsa_cdiv(K, 32)), 1, batch), block(32, 8);
+      dim3 grid((unsigned)((long)gpsa_cdiv(rows, 64) * gpsa_cdiv(K, 64)), 1, batch), block(32, 8);
       pack_trans_kernel<<<grid, block, 0, st>>>(rows, K, Kp, ld, sIn, src, hi, lo);
     }
   };
@@ -1105,7 +1123,7 @@ extern "C" int gpsa_quadform_bwd_omega_tc(int M, long R, int L, const float* A, 
   uint8_t* w = static_cast<uint8_t*>(ws);
   __nv_bfloat16 *gt_hi = (__nv_bfloat16*)w, *gt_lo = (__nv_bfloat16*)(w + o.gt);
   {
-    dim3 grid((unsigned)(o.Rp / 32), gpsa_cdiv(L, 32)), block(32, 8);
+    dim3 grid((unsigned)(o.Rp / 64), gpsa_cdiv(L, 64)), block(32, 8);
     pack_Gt_kernel<<<grid, block, 0, st>>>(R, L, G, gt_hi, gt_lo);
     GPSA_LAUNCH_CHECK();
   }

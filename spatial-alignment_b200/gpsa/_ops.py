@@ -212,6 +212,9 @@ class OmegaChain(torch.autograd.Function):
         Osq = _c(Osq.detach())
         Omega, Ltril, Lfac, hld, info = _omega_prepare(Osq)
         ctx.meta = meta
+        # no zero tensors for the gradients of outputs nothing differentiates (autograd would fill an [L,M,M] buffer for
+        # the factor on every backward); the backward handles None
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(Osq, Lfac)
         L64 = Lfac if Lfac.dtype == f64 else None
         ctx.mark_non_differentiable(Ltril, info, *([L64] if L64 is not None else []))
@@ -314,6 +317,7 @@ class WarpLayer(torch.autograd.Function):
             cur.wait_stream(s_)
         del keep
         ctx.meta = meta
+        ctx.set_materialize_grads(False)  # unused outputs (G_means, the cached factors) arrive as None, not as zero tensors
         ctx.save_for_backward(Xtilde, delta_G, Osq_G, log_ls, log_var, Omega_G, L64_G, *saved)
         info_all = torch.cat([info_G, info])
         ctx.mark_non_differentiable(Lk_all, Ltril_G, info_all)
@@ -452,6 +456,7 @@ class DataLayerPre(torch.autograd.Function):
         ctx.meta = meta
         ctx.engine = engine
         ctx.dims = (S, N)
+        ctx.set_materialize_grads(False)  # no [L,M,M] zero fill for the gradient of the cached factor
         ctx.n_in = 11 if chained else (9 if Kuu is not None or Kuf is not None else 7)
         ctx.chained = chained
         ctx.save_for_backward(Gtilde, log_ls, log_var, delta_F, Osq_F, G, Omega, L64 if not chained else None, Kinv, Kinv64, A, B, W,
